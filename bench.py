@@ -1,0 +1,320 @@
+#!/usr/bin/env python
+"""Headline benchmark: quaternion-MACs/s of the fused Hamilton conv forward (BASELINE.json configs[1]).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|dense]
+
+A step = one QuaternionConv1D forward (64 filters, kernel 3, stride 1, `same`, bias, relu) over a synthetic
+x[256, 256, 160] fp32 batch -- one launch of the fused tensor-core kernel through the layer API / C ABI.
+N > 1 (under torchrun): every rank runs the same per-GPU batch on its own GPU (weak scaling, batch-sharded data
+parallelism; the forward has no collective); value = all ranks' qMACs / max-over-ranks time.
+`--impl reference` times the CPU restatement of the reference path (oracle/qoracle.py: slice -> negate -> concatenate
+-> im2col -> sgemm -> bias -> relu, fp32) on the host cores, on a bounded sample of the same workload.
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "quaternion-convolutional-neural-networks-for-end-to-end-automatic-speech-recognition_b200")
+for p in (REPO, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+METRIC = "quaternion-MACs/sec (QConv1D+QDense fwd)"
+WORKLOADS = {
+    # name: (kind, batch, steps T, in_q, filters, kernel)
+    "cfg2": dict(kind="conv1d", B=256, T=256, in_q=40, F=64, k=3,
+                 desc="QuaternionConv1D fwd x[256,256,4x40] 64 filters k=3 same relu (BASELINE configs[1])"),
+    "dense": dict(kind="dense", B=65536, T=1, in_q=40, F=64, k=1,
+                  desc="QuaternionDense fwd x[65536,160] -> 256 relu (north-star dense shape)"),
+}
+
+
+def qmacs(w, batch=None):
+    return (batch if batch is not None else w["B"]) * w["T"] * w["k"] * w["in_q"] * w["F"]
+
+
+def alg_bytes(w):
+    """Algorithmic HBM bytes per step: read x once, write y once, read the stored (un-expanded) kernel and bias."""
+    return 4 * (w["B"] * w["T"] * 4 * w["in_q"] + w["B"] * w["T"] * 4 * w["F"] + w["k"] * w["in_q"] * 4 * w["F"] + 4 * w["F"])
+
+
+def peaks():
+    try:
+        m = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
+        return dict(hbm_gbs=float(m["hbm_gbs"]), bf16=float(m["bf16_tflops"]), src="measured (MEASURED_PEAKS.json)")
+    except Exception:
+        return dict(hbm_gbs=6650.0, bf16=1590.0, src="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and throttle reasons with nvidia-smi while the timed region runs."""
+
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._stop_evt.wait(0.1)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=6)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_step(w, sample_batch, rng):
+    """One pass of the reference CPU path on `sample_batch` samples; returns a closure and the qMACs it performs."""
+    from oracle import qoracle as O
+    if w["kind"] == "conv1d":
+        x = rng.normal(size=(sample_batch, w["T"], 4 * w["in_q"])).astype(np.float32)
+        kern = (rng.normal(size=(w["k"], w["in_q"], 4 * w["F"])) * 0.05).astype(np.float32)
+        bias = rng.normal(0, 0.1, 4 * w["F"]).astype(np.float32)
+        return (lambda: O.qconv1d_forward_f32(x, kern, bias, w["F"], "same", True)), qmacs(w, sample_batch)
+    x = rng.normal(size=(sample_batch, 4 * w["in_q"])).astype(np.float32)
+    kern = (rng.normal(size=(w["in_q"], 4 * w["F"])) * 0.05).astype(np.float32)
+    bias = rng.normal(0, 0.1, 4 * w["F"]).astype(np.float32)
+    return (lambda: O.qdense_forward_f32(x, kern, bias, 4 * w["F"], True)), qmacs(w, sample_batch)
+
+
+def host_cores():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args, w):
+    """The reference arm: CPU restatement of complexnn/conv.py:288-345 on the box's host cores (NumPy + its BLAS threads)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    rng = np.random.default_rng(0)
+    sample = 32 if w["kind"] == "conv1d" else 8192
+    step, q = cpu_reference_step(w, sample, rng)
+    for _ in range(max(args.warmup, 1)):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    val = q / dt
+    sample_desc = "%d of %d %s per step (NumPy fp32: expand+im2col+sgemm+bias+relu)" % (
+        sample, w["B"], "sequences" if w["kind"] == "conv1d" else "rows")
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "qMAC/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": w["desc"], "sample": sample_desc},
+            "cpu_baseline": {"value": val, "unit": "qMAC/s", "cores": host_cores(), "kind": "port", "sample": sample_desc},
+            "e2e": {"value": val, "unit": "qMAC/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+    return 0
+
+
+def run_ours(args, w):
+    import torch
+    import torch.distributed as dist
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("qnn_build", os.path.join(PKG, "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    if rank == 0:
+        mod.build()
+    if world > 1:
+        dist.barrier()
+    import complexnn
+    from complexnn import _native
+
+    rng = np.random.default_rng(1234 + rank)
+    np.random.seed(0)
+    if w["kind"] == "conv1d":
+        layer = complexnn.QuaternionConv1D(w["F"], w["k"], padding="same", activation="relu")
+        in_shape = (w["B"], w["T"], 4 * w["in_q"])
+    else:
+        layer = complexnn.QuaternionDense(4 * w["F"], activation="relu")
+        in_shape = (w["B"], 4 * w["in_q"])
+    layer.build((None,) + in_shape[1:])
+    layer.built = True
+    ws = layer.get_weights()
+    ws[-1] = rng.normal(0, 0.1, ws[-1].shape).astype(np.float32)       # non-zero bias: the epilogue does real work
+    layer.set_weights(ws)
+
+    # ---- inputs resident in HBM; rotate buffer sets so no step finds its input in the 126 MB L2
+    n_sets = 3
+    xs = [torch.randn(in_shape, device="cuda", dtype=torch.float32) for _ in range(n_sets)]
+    y = None
+    for i in range(max(args.warmup, 3)):
+        y = layer(xs[i % n_sets])
+    torch.cuda.synchronize()
+
+    # parity gate on the very tensors that are timed: a fast wrong kernel is not a result
+    if rank == 0:
+        from oracle import qoracle as O
+        sl = slice(0, 4) if w["kind"] == "conv1d" else slice(0, 1024)
+        xh = xs[(max(args.warmup, 3) - 1) % n_sets][sl].cpu().numpy()
+        if w["kind"] == "conv1d":
+            ref = O.qconv_forward(xh, ws[0], ws[1], w["F"], 1, "same", "channels_last", 1, "relu")
+        else:
+            ref = O.qdense_forward(xh, ws[0], ws[1], 4 * w["F"], "relu")
+        got = y[sl].cpu().numpy()
+        err = float(np.abs(got - ref).max() / np.abs(ref).max())
+        if not err <= 1e-3:
+            raise SystemExit("parity check failed before timing: max-rel error %.3e" % err)
+    else:
+        err = None
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    if sampler:
+        sampler.start()
+    l0 = _native.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        y = layer(xs[i % n_sets])
+    e1.record()
+    torch.cuda.synchronize()
+    launches = _native.launch_count() - l0
+    ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+    clocks = sampler.stop() if sampler else None
+
+    # ---- end to end through the public layer call with HOST buffers: pinned x -> H2D -> kernel -> D2H pinned y
+    e2e_steps = max(3, min(args.steps, 20))
+    xh_t = torch.empty(in_shape, dtype=torch.float32).pin_memory()
+    xh_t.copy_(xs[0])
+    xh = xh_t.numpy()
+    layer(xh)                                           # warm (allocates the library's device scratch)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        yh = layer(xh)                                  # returns after the result landed on the host
+    e2e_s = (time.perf_counter() - t0) / e2e_steps
+    if world > 1:
+        t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    h2d = int(xh.nbytes + sum(a.nbytes for a in ws))
+    d2h = int(yh.nbytes)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    pk = peaks()
+    q = qmacs(w)
+    flops = 32.0 * q
+    tf32_peak = pk["bf16"] / 2.0
+    t_s = ms * 1e-3
+    achieved_tf = flops / t_s / 1e12
+    hbm_gbs = alg_bytes(w) / t_s / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    cpu_step, cpu_q = cpu_reference_step(w, 32 if w["kind"] == "conv1d" else 8192, np.random.default_rng(0))
+    cpu_step()
+    t0 = time.perf_counter()
+    reps = 0
+    while reps < 3 or time.perf_counter() - t0 < 10.0:
+        cpu_step()
+        reps += 1
+        if reps >= 200:
+            break
+    cpu_val = cpu_q * reps / (time.perf_counter() - t0)
+
+    line = {
+        "metric": METRIC, "value": world * q / t_s, "unit": "qMAC/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "tf32", "data": "synthetic",
+        "config": {"workload": w["desc"], "per_gpu_batch": w["B"], "global_batch": w["B"] * world,
+                   "parallelism": "dp%d (batch shards, no collective in forward)" % world,
+                   "l2": "rotating %d input sets (%.0f MB > 126 MB L2), output rewritten each step" % (
+                       n_sets, n_sets * alg_bytes(w) / 1e6),
+                   "math": "tf32 operands (round-to-nearest), fp32 accumulate, fp32 I/O",
+                   "parity_max_rel_err": err},
+        "e2e": {"value": world * q / e2e_s, "unit": "qMAC/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": tf32_peak, "unit": "TFLOP/s",
+                     "frac": achieved_tf / tf32_peak, "traffic": traffic, "kernel": "k_hamilton_tc",
+                     "peak_source": "tf32 dense = 1/2 x bf16 burst, " + pk["src"],
+                     "flops_per_launch": flops, "hbm_achieved_gbs": hbm_gbs, "hbm_peak_gbs": pk["hbm_gbs"],
+                     "hbm_frac": hbm_gbs / pk["hbm_gbs"], "algorithmic_bytes_per_launch": alg_bytes(w)},
+        "cpu_baseline": {"value": cpu_val, "unit": "qMAC/s", "cores": host_cores(), "kind": "port",
+                         "sample": "%d x (32 of 256 sequences): NumPy fp32 expand+im2col+sgemm+bias+relu" % reps
+                         if w["kind"] == "conv1d" else "%d x 8192 of 65536 rows, NumPy fp32" % reps},
+    }
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    args = ap.parse_args()
+    w = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        return run_reference(args, w)
+    return run_ours(args, w)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,135 @@
+/* qnn.h -- C ABI of the B200-native quaternion convolution / dense hot path (libqnn_b200.so).
+ *
+ * The reference (Orkis-Research QCNN, /root/reference) has no FFI: the path sits behind the Keras 2 `Layer` protocol and
+ * all arithmetic is delegated to Keras-backend calls.  Each entry point below replaces one such delegation; the
+ * Python layer mirror (`complexnn` inside the *_b200 package) binds them with ctypes.
+ *
+ * Conventions: every function returns 0 (QNN_OK) or a negative qnn_status; nothing throws; caller owns every buffer;
+ * pointers are DEVICE pointers unless the name says `_host`; work is enqueued asynchronously on `stream`
+ * (a cudaStream_t passed as void*; NULL = legacy default stream) and no call synchronises the device;
+ * qnn_last_error() returns a thread-local message for the last failing call on this thread.
+ * Tensors are fp32.  Channel axes are component-BLOCKED: [r(0:C) | i(C:2C) | j(2C:3C) | k(3C:4C)]
+ * (reference: complexnn/conv.py:294-307, complexnn/dense.py:131-134, complexnn/utils.py:17-79).
+ */
+#ifndef QNN_B200_H
+#define QNN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define QNN_ABI_VERSION 1
+#if defined(__GNUC__)
+#define QNN_API __attribute__((visibility("default")))
+#else
+#define QNN_API
+#endif
+
+typedef enum qnn_status {
+    QNN_OK = 0,
+    QNN_E_INVALID = -1,     /* bad argument (maps to ValueError in the Python mirror)            */
+    QNN_E_UNSUPPORTED = -2, /* shape / option outside what the selected algorithm implements    */
+    QNN_E_CUDA = -3,        /* a CUDA runtime / driver call failed                              */
+    QNN_E_WORKSPACE = -4,   /* workspace missing or too small                                   */
+    QNN_E_COMM = -5,        /* NCCL unavailable or a collective failed                          */
+    QNN_E_STATE = -6        /* call sequence error (e.g. all-reduce before qnn_comm_init)       */
+} qnn_status;
+
+typedef enum qnn_padding { QNN_PAD_VALID = 0, QNN_PAD_SAME = 1, QNN_PAD_CAUSAL = 2 } qnn_padding;
+
+/* keras.activations handled in the fused epilogue (complexnn/conv.py:342-343, dense.py:161-162). */
+typedef enum qnn_activation {
+    QNN_ACT_LINEAR = 0,
+    QNN_ACT_RELU = 1,
+    QNN_ACT_TANH = 2,
+    QNN_ACT_SIGMOID = 3,
+    QNN_ACT_HARD_SIGMOID = 4,
+    QNN_ACT_SOFTPLUS = 5,
+    QNN_ACT_SOFTSIGN = 6,
+    QNN_ACT_ELU = 7,
+    QNN_ACT_SELU = 8,
+    QNN_ACT_EXPONENTIAL = 9
+} qnn_activation;
+
+/* Arithmetic of the contraction.  TF32: operands rounded to nearest tf32, fp32 accumulate in tensor memory
+ * (tcgen05.mma kind::tf32).  FP32: CUDA-core FMA.  3XTF32: hi/lo split, three tensor-core products (fp32-faithful). */
+typedef enum qnn_math { QNN_MATH_TF32 = 0, QNN_MATH_FP32 = 1, QNN_MATH_3XTF32 = 2 } qnn_math;
+
+/* Kernel selection.  AUTO picks the tensor-core kernel when the shape qualifies, else the general kernel. */
+typedef enum qnn_algo { QNN_ALGO_AUTO = 0, QNN_ALGO_GENERAL = 1, QNN_ALGO_TENSOR = 2 } qnn_algo;
+
+/* One quaternion convolution (QuaternionConv.__init__ / build, complexnn/conv.py:93-152, 154-286).
+ * x:      channels_last  [batch, in_spatial..., 4*in_q]   or channels_first [batch, 4*in_q, in_spatial...]
+ * kernel: [kernel[0..rank), in_q, 4*filters]  (the layout qconv_init really produces, complexnn/init.py:91)
+ * y:      channels_last  [batch, out_spatial..., 4*filters] or channels_first [batch, 4*filters, out_spatial...]   */
+typedef struct qnn_conv_desc {
+    int32_t rank;          /* 1, 2 or 3 */
+    int32_t batch;
+    int32_t in_spatial[3];
+    int32_t in_q;          /* quaternion input channels  = real channels / 4 */
+    int32_t filters;       /* quaternion output channels = real channels / 4 */
+    int32_t kernel[3];
+    int32_t stride[3];
+    int32_t dilation[3];
+    int32_t padding;        /* qnn_padding; CAUSAL only for rank 1 */
+    int32_t channels_first; /* 0 = channels_last */
+    int32_t activation;     /* qnn_activation */
+    int32_t math;           /* qnn_math */
+    int32_t algo;           /* qnn_algo */
+} qnn_conv_desc;
+
+QNN_API int qnn_abi_version(void);
+QNN_API const char* qnn_last_error(void);
+/* 1 when the tensor-core kernel will be used for this descriptor under QNN_ALGO_AUTO, else 0. */
+QNN_API int qnn_conv_uses_tensor_cores(const qnn_conv_desc* d);
+QNN_API int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units);
+
+/* replaces conv_utils.conv_output_length at complexnn/conv.py:347-372 */
+QNN_API int qnn_conv_out_spatial(const qnn_conv_desc* d, int32_t out_spatial[3]);
+
+/* replaces the whole of QuaternionConv.call, complexnn/conv.py:288-345:
+ * slice r,i,j,k -> Hamilton expansion -> K.conv{1,2,3}d -> K.bias_add -> activation, fused, nothing expanded in HBM.
+ * bias may be NULL (use_bias=False). */
+QNN_API int qnn_conv_forward(const qnn_conv_desc* d, const float* x, const float* kernel, const float* bias, float* y,
+                     void* stream);
+
+/* replaces QuaternionDense.call, complexnn/dense.py:126-164 (transposed Hamilton table).
+ * x [rows, 4*in_q], kernel [in_q, 4*q_units], bias [4*q_units] or NULL, y [rows, 4*q_units]. */
+QNN_API int qnn_dense_forward(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
+                      const float* bias, int32_t activation, int32_t math, int32_t algo, float* y, void* stream);
+
+/* Gradients TF autodiff derives from the same graph.  `y` is the forward output (needed for the
+ * activation derivative; only LINEAR and RELU are differentiable here).  Any of dx / dkernel / dbias may be NULL to
+ * skip it.  dkernel / dbias are OVERWRITTEN (not accumulated) and have the stored-kernel / bias shapes, so they can
+ * point into a flat gradient bucket that qnn_allreduce_f32 then reduces. */
+QNN_API int qnn_conv_backward(const qnn_conv_desc* d, const float* x, const float* kernel, const float* y, const float* dy,
+                      float* dx, float* dkernel, float* dbias, void* stream);
+QNN_API int qnn_dense_backward(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
+                       const float* y, const float* dy, int32_t activation, float* dx, float* dkernel, float* dbias,
+                       void* stream);
+
+/* Host-buffer convenience (the end-to-end call a non-CUDA caller makes): pageable or pinned HOST pointers in, HOST
+ * result out; the library stages through its own device scratch on `stream` and returns after the result landed. */
+QNN_API int qnn_conv_forward_host(const qnn_conv_desc* d, const float* x_host, const float* kernel_host,
+                          const float* bias_host, float* y_host, void* stream);
+QNN_API int qnn_dense_forward_host(int64_t rows, int32_t in_q, int32_t q_units, const float* x_host, const float* kernel_host,
+                           const float* bias_host, int32_t activation, int32_t math, int32_t algo, float* y_host,
+                           void* stream);
+
+/* Data-parallel gradient exchange (absent from the reference): one NCCL communicator per process.
+ * qnn_comm_unique_id fills 128 bytes on rank 0; every rank passes the same bytes to qnn_comm_init. */
+QNN_API int qnn_comm_unique_id(void* out_128_bytes);
+QNN_API int qnn_comm_init(int32_t rank, int32_t world_size, const void* unique_id_128_bytes);
+QNN_API int qnn_allreduce_f32(float* buf, size_t count, void* stream); /* in-place sum */
+QNN_API int qnn_comm_destroy(void);
+
+/* Number of GPU kernels this library has launched in this process (all threads) -- for bench.py's gpu_launches. */
+QNN_API uint64_t qnn_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* QNN_B200_H */

@@ -42,7 +42,7 @@ class VarianceScaling(Initializer):
     def __call__(self, shape, dtype=None):
         fan_in, fan_out = _compute_fans(shape)
         n = {"fan_in": fan_in, "fan_out": fan_out, "fan_avg": (fan_in + fan_out) / 2.0}[self.mode]
-        rng = np.random.RandomState(self.seed)
+        rng = np.random if self.seed is None else np.random.RandomState(self.seed)
         if self.distribution == "normal":
             w = rng.normal(0.0, np.sqrt(self.scale / max(1.0, n)), shape)
         else:

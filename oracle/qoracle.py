@@ -315,8 +315,10 @@ def _quaternion_init(kernel_shape, fan_in, fan_out, criterion, seed):
     v_i = np.random.uniform(0.0, 1.0, n)
     v_j = np.random.uniform(0.0, 1.0, n)
     v_k = np.random.uniform(0.0, 1.0, n)
-    norm = np.sqrt(v_i ** 2 + v_j ** 2 + v_k ** 2) + 0.0001
-    v_i, v_j, v_k = (v / norm).reshape(kernel_shape), (v_j / norm).reshape(kernel_shape), (v_k / norm).reshape(kernel_shape)
+    # the reference squares NumPy *scalars* (libm pow), which is not always bit-identical to the vectorised x*x
+    sq = lambda v: np.fromiter((e ** 2 for e in v), dtype=np.float64, count=n)
+    norm = np.sqrt(sq(v_i) + sq(v_j) + sq(v_k)) + 0.0001
+    v_i, v_j, v_k = (v_i / norm).reshape(kernel_shape), (v_j / norm).reshape(kernel_shape), (v_k / norm).reshape(kernel_shape)
     rng = np.random.RandomState(1337 if seed is None else seed)
     modulus = rng.rayleigh(scale=s, size=kernel_shape)
     phase = rng.uniform(low=-np.pi, high=np.pi, size=kernel_shape)

@@ -1,0 +1,68 @@
+// Internal declarations shared by the kernels and the C-ABI translation unit.
+#pragma once
+#include <cstdint>
+#include <cstdarg>
+#include <cstdio>
+#include <atomic>
+#include <cuda_runtime.h>
+#include "../../include/qnn.h"
+
+namespace qnn {
+
+// Geometry of one quaternion convolution, normalised to three spatial axes (leading axes have extent 1 for rank < 3).
+// A dense layer is the degenerate case: one position per row, one tap, `conj_w` set (transposed Hamilton table).
+struct Geom {
+    int batch;
+    int in_sp[3], out_sp[3], k[3], s[3], d[3], pad_lo[3];
+    int in_q, F;
+    int channels_first;
+    int act;
+    int conj_w;  // 1 = dense convention y = conj(W) (x) x  (complexnn/dense.py:139-143), 0 = conv  y = W (x) x
+};
+
+void set_error(const char* fmt, ...);
+extern std::atomic<unsigned long long> g_launches;
+inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+
+// general (CUDA-core, fp32) kernels: any rank / stride / dilation / padding / data_format
+int general_forward(const Geom& g, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+int general_backward(const Geom& g, const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw,
+                     float* db, cudaStream_t st);
+
+// tensor-core kernel (tcgen05 / TMEM / TMA): channels_last rows with taps along the innermost spatial axis
+struct TcPlan {
+    int ok;           // shape qualifies
+    int f_tile;       // filters per pass (<= 64)
+    int n_ftiles;
+    int in_q_pad;     // in_q rounded up to 8
+    int rows_in;      // 128 + (taps-1)*dilation
+    int x_stages;
+    size_t smem_bytes;
+    const char* why;  // reason when !ok
+};
+TcPlan tc_plan(const Geom& g, int rank);
+int tc_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+
+}  // namespace qnn
+
+// ---------------------------------------------------------------------------------------------------------------------
+// activation (device): keras.activations semantics
+// ---------------------------------------------------------------------------------------------------------------------
+#ifdef __CUDACC__
+namespace qnn {
+__device__ __forceinline__ float act_apply(float v, int act) {
+    switch (act) {
+        case QNN_ACT_RELU: return fmaxf(v, 0.f);
+        case QNN_ACT_TANH: return tanhf(v);
+        case QNN_ACT_SIGMOID: return 1.f / (1.f + expf(-v));
+        case QNN_ACT_HARD_SIGMOID: return fminf(fmaxf(0.2f * v + 0.5f, 0.f), 1.f);
+        case QNN_ACT_SOFTPLUS: return fmaxf(v, 0.f) + log1pf(expf(-fabsf(v)));
+        case QNN_ACT_SOFTSIGN: return v / (1.f + fabsf(v));
+        case QNN_ACT_ELU: return v > 0.f ? v : expm1f(v);
+        case QNN_ACT_SELU: return 1.0507009873554805f * (v > 0.f ? v : 1.6732632423543772f * expm1f(v));
+        case QNN_ACT_EXPONENTIAL: return expf(v);
+        default: return v;
+    }
+}
+}  // namespace qnn
+#endif

@@ -1,0 +1,345 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).  Every call goes through the layer mirror -> ctypes ->
+C ABI -> hand-written kernels and is compared with (a) the golden vectors produced by the reference's own code and
+(b) the NumPy oracle on seeded inputs.
+
+Tolerances (stated here, as the north star asks: "within 1e-3 relative fp32 tolerance"):
+  * tensor-core kernel, math TF32 (operands rounded to nearest tf32, fp32 accumulation):
+        max|y - ref| <= 1e-3 * max|ref|     and     ||y - ref||_F <= 1e-3 * ||ref||_F
+  * general kernel, math FP32: the same two metrics at 2e-5 (only summation order differs from the oracle).
+"""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from cases import CONV_CASES, DENSE_CASES, conv_kwargs  # noqa: E402
+from oracle import qoracle as O  # noqa: E402
+
+TF32_TOL = 1e-3
+FP32_TOL = 2e-5
+
+
+def errs(y, ref):
+    y = np.asarray(y, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert y.shape == ref.shape, (y.shape, ref.shape)
+    if ref.size == 0:
+        return 0.0, 0.0
+    d = y - ref
+    return float(np.abs(d).max() / (np.abs(ref).max() + 1e-30)), float(np.linalg.norm(d) / (np.linalg.norm(ref) + 1e-30))
+
+
+def check(y, ref, tol, what=""):
+    emax, efro = errs(y, ref)
+    assert emax <= tol and efro <= tol, "%s: max-rel %.3e fro-rel %.3e > %.1e" % (what, emax, efro, tol)
+    return emax, efro
+
+
+@pytest.fixture(scope="module")
+def cnn(native_lib):
+    assert torch.cuda.is_available(), "these tests need the B200"
+    import complexnn
+    return complexnn
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def make_conv(cnn, rank, filters, ksz, kw, kernel, bias):
+    cls = {1: cnn.QuaternionConv1D, 2: cnn.QuaternionConv2D, 3: cnn.QuaternionConv3D}[rank]
+    layer = cls(filters, ksz, **kw)
+    return layer, ([kernel] if bias is None else [kernel, bias])
+
+
+@pytest.mark.parametrize("algo", ["general", "auto"])
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_conv_forward_vs_reference_golden(cnn, golden, monkeypatch, case, algo):
+    name, rank, xs, filters, ksz, kw = case
+    g = golden.load("conv_forward")
+    monkeypatch.setenv("QNN_ALGO", algo)
+    monkeypatch.setenv("QNN_MATH", "fp32" if algo == "general" else "tf32")
+    layer, weights = make_conv(cnn, rank, filters, ksz, kw, g[name + ".kernel"], g.get(name + ".bias"))
+    x = dev(g[name + ".x"])
+    layer.build((None,) + tuple(x.shape[1:]))
+    layer.built = True
+    layer.set_weights(weights)
+    y = layer(x)
+    assert y.is_cuda and y.dtype == torch.float32
+    uses_tc = algo == "auto" and name.startswith("c1_tc_")
+    check(y.cpu().numpy(), g[name + ".y"], TF32_TOL if uses_tc else FP32_TOL, name)
+    # host-buffer path (NumPy in, NumPy out) goes through qnn_conv_forward_host
+    yh = layer(g[name + ".x"])
+    assert isinstance(yh, np.ndarray)
+    np.testing.assert_array_equal(yh, y.cpu().numpy())
+
+
+@pytest.mark.parametrize("algo", ["general", "auto"])
+@pytest.mark.parametrize("case", DENSE_CASES, ids=[c[0] for c in DENSE_CASES])
+def test_dense_forward_vs_reference_golden(cnn, golden, monkeypatch, case, algo):
+    name, xs, units, kw = case
+    g = golden.load("dense_forward")
+    monkeypatch.setenv("QNN_ALGO", algo)
+    monkeypatch.setenv("QNN_MATH", "fp32" if algo == "general" else "tf32")
+    layer = cnn.QuaternionDense(units, **kw)
+    layer.build((None, xs[1]))
+    layer.built = True
+    layer.set_weights([g[name + ".kernel"]] + ([g[name + ".bias"]] if name + ".bias" in g else []))
+    y = layer(dev(g[name + ".x"]))
+    uses_tc = algo == "auto" and name.startswith("d_tc_")
+    check(y.cpu().numpy(), g[name + ".y"], TF32_TOL if uses_tc else FP32_TOL, name)
+    np.testing.assert_array_equal(layer(g[name + ".x"]), y.cpu().numpy())
+
+
+def test_kat_on_gpu(cnn, golden):
+    kat = golden.load("kat")
+    c = cnn.QuaternionConv1D(1, 1)
+    x = np.array([[[5, 6, 7, 8.0]]], dtype=np.float32)
+    c.build((None, 1, 4))
+    c.built = True
+    c.set_weights([np.array([[[1, 2, 3, 4.0]]], dtype=np.float32), np.zeros(4, np.float32)])
+    np.testing.assert_array_equal(c(dev(x)).cpu().numpy(), kat["conv_w1234_x5678"])
+    d = cnn.QuaternionDense(4)
+    d.build((None, 4))
+    d.built = True
+    d.set_weights([np.array([[1, 2, 3, 4.0]], dtype=np.float32), np.zeros(4, np.float32)])
+    np.testing.assert_array_equal(d(dev(x[0])).cpu().numpy(), kat["dense_w1234_x5678"])
+
+
+def _tc_shapes():
+    rng = np.random.default_rng(42)
+    out = []
+    for _ in range(28):
+        in_q = int(rng.choice([4, 8, 12, 20, 32, 40, 64, 100]))
+        F = int(rng.choice([16, 32, 48, 64, 128, 192]))
+        k = int(rng.integers(1, 6))
+        d = int(rng.integers(1, 4))
+        pad = str(rng.choice(["same", "valid", "causal"]))
+        T = int(rng.choice([1, 7, 127, 128, 129, 250, 300, 517]))
+        B = int(rng.integers(1, 5))
+        if pad == "valid" and T < (k - 1) * d + 1:
+            T = (k - 1) * d + 3
+        out.append((B, T, in_q, F, k, d, pad, str(rng.choice(["relu", "linear", "tanh"])), bool(rng.integers(0, 2))))
+    return out
+
+
+@pytest.mark.parametrize("shape", _tc_shapes(), ids=lambda s: "B%d_T%d_q%d_F%d_k%d_d%d_%s_%s_b%d" % s)
+def test_tensor_core_conv1d_random_shapes_vs_oracle(cnn, native_lib, shape):
+    from complexnn import _native, _ops
+    from complexnn._layer import Variable
+    B, T, in_q, F, k, d, pad, act, use_bias = shape
+    rng = np.random.default_rng(hash(shape) % (2 ** 31))
+    x = rng.normal(size=(B, T, 4 * in_q)).astype(np.float32)
+    kern = (rng.normal(size=(k, in_q, 4 * F)) / np.sqrt(4 * in_q * k)).astype(np.float32)
+    bias = rng.normal(0, 0.1, size=4 * F).astype(np.float32) if use_bias else None
+    desc = _native.make_conv_desc(1, B, (T,), in_q, F, (k,), (1,), (d,), pad, "channels_last", act)
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(desc)) == 1
+    y = _ops.conv_forward(dev(x), Variable(kern), Variable(bias) if use_bias else None, F, (k,), (1,), pad,
+                          "channels_last", (d,), act, math="tf32", algo="tensor")
+    ref = O.qconv_forward(x, kern, bias, F, 1, pad, "channels_last", d, act)
+    check(y.cpu().numpy(), ref, TF32_TOL, str(shape))
+    # and the general kernel on the same problem at fp32 tolerance
+    yg = _ops.conv_forward(dev(x), Variable(kern), Variable(bias) if use_bias else None, F, (k,), (1,), pad,
+                           "channels_last", (d,), act, math="fp32", algo="general")
+    check(yg.cpu().numpy(), ref, FP32_TOL, "general " + str(shape))
+
+
+@pytest.mark.parametrize("rows,in_q,units", [(1, 4, 64), (127, 8, 128), (129, 40, 256), (1000, 128, 512), (333, 64, 768),
+                                             (4096, 36, 192)])
+def test_tensor_core_dense_vs_oracle(cnn, native_lib, rows, in_q, units):
+    from complexnn import _ops
+    from complexnn._layer import Variable
+    rng = np.random.default_rng(rows + in_q)
+    x = rng.normal(size=(rows, 4 * in_q)).astype(np.float32)
+    kern = (rng.normal(size=(in_q, units)) / np.sqrt(4 * in_q)).astype(np.float32)
+    bias = rng.normal(0, 0.1, size=units).astype(np.float32)
+    assert native_lib.qnn_dense_uses_tensor_cores(rows, in_q, units // 4) == 1
+    y = _ops.dense_forward(dev(x), Variable(kern), Variable(bias), units, "relu", math="tf32", algo="tensor")
+    check(y.cpu().numpy(), O.qdense_forward(x, kern, bias, units, "relu"), TF32_TOL)
+
+
+def test_tensor_algo_refuses_unsupported_shapes(cnn):
+    from complexnn import _ops
+    from complexnn._layer import Variable
+    x = dev(np.zeros((2, 10, 12), np.float32))          # in_q = 3: not a multiple of 4
+    with pytest.raises(NotImplementedError, match="tensor-core kernel"):
+        _ops.conv_forward(x, Variable(np.zeros((3, 3, 64), np.float32)), None, 16, (3,), (1,), "same", "channels_last",
+                          (1,), "relu", algo="tensor")
+
+
+def test_baseline_config2_full_size(cnn):
+    """BASELINE.json configs[1]: QuaternionConv1D forward, x[256,256,160], 64 filters, kernel 3, same, relu."""
+    from complexnn import _native
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(256, 256, 160)).astype(np.float32)
+    np.random.seed(0)
+    layer = cnn.QuaternionConv1D(64, 3, padding="same", activation="relu")
+    xd = dev(x)
+    n0 = _native.launch_count()
+    y = layer(xd)
+    assert _native.launch_count() == n0 + 1            # one fused launch, nothing else
+    layer.set_weights([layer.get_weights()[0], rng.normal(0, 0.1, 256).astype(np.float32)])
+    y = layer(xd)
+    kern, bias = layer.get_weights()
+    ref = O.qconv_forward(x, kern, bias, 64, 1, "same", "channels_last", 1, "relu")
+    emax, efro = check(y.cpu().numpy(), ref, TF32_TOL, "cfg2")
+    print("cfg2 full size: max-rel %.3e fro-rel %.3e" % (emax, efro))
+    # size-independent properties at full size
+    # (1) batch shards are independent: any shard reproduces the same bits (this is what data parallelism relies on)
+    y_half = layer(xd[128:].contiguous())
+    assert torch.equal(y_half, y[128:])
+    # (2) linearity of the pre-activation map in x (no bias, no activation)
+    lin = cnn.QuaternionConv1D(64, 3, padding="same", use_bias=False)
+    lin.build((None, 256, 160))
+    lin.built = True
+    lin.set_weights([kern])
+    x2 = dev(rng.normal(size=(256, 256, 160)).astype(np.float32))
+    lhs = lin(2.0 * xd - 0.5 * x2)
+    rhs = 2.0 * lin(xd) - 0.5 * lin(x2)
+    check(lhs.cpu().numpy(), rhs.cpu().numpy(), 2 * TF32_TOL, "linearity")
+
+
+def test_northstar_dense_full_size(cnn):
+    rng = np.random.default_rng(1)
+    x = rng.normal(size=(65536, 160)).astype(np.float32)
+    np.random.seed(1)
+    layer = cnn.QuaternionDense(256, activation="relu")
+    y = layer(dev(x))
+    kern, bias = layer.get_weights()
+    check(y.cpu().numpy(), O.qdense_forward(x, kern, bias, 256, "relu"), TF32_TOL, "dense north star")
+
+
+def test_quaternion_norm_is_multiplicative_on_gpu(cnn):
+    """|w (x) x| = |w| |x| for single quaternions: a property no sign-table mistake survives."""
+    rng = np.random.default_rng(3)
+    x = rng.normal(size=(4096, 1, 4)).astype(np.float32)
+    w = rng.normal(size=(1, 1, 4)).astype(np.float32)
+    layer = cnn.QuaternionConv1D(1, 1, use_bias=False)
+    layer.build((None, 1, 4))
+    layer.built = True
+    layer.set_weights([w])
+    y = layer(dev(x)).cpu().numpy()
+    np.testing.assert_allclose(np.linalg.norm(y, axis=-1).ravel(), np.linalg.norm(w) * np.linalg.norm(x, axis=-1).ravel(),
+                               rtol=1e-5)
+
+
+BWD_CASES = [
+    ("conv1d", dict(rank=1, xs=(3, 17, 8), F=4, k=(3,), s=(1,), d=(1,), pad="same", cf=False, act="relu")),
+    ("conv1d_s2_causal", dict(rank=1, xs=(2, 20, 12), F=3, k=(3,), s=(2,), d=(2,), pad="causal", cf=False, act="linear")),
+    ("conv2d_cf", dict(rank=2, xs=(2, 8, 7, 6), F=3, k=(3, 2), s=(1, 2), d=(1, 1), pad="same", cf=True, act="relu")),
+    ("conv2d_valid_d2", dict(rank=2, xs=(2, 9, 8, 4), F=2, k=(2, 3), s=(1, 1), d=(2, 1), pad="valid", cf=False, act="relu")),
+    ("conv3d", dict(rank=3, xs=(1, 4, 5, 6, 4), F=2, k=(2, 2, 3), s=(1, 1, 2), d=(1, 1, 1), pad="same", cf=False, act="relu")),
+    ("conv1d_cfg2_slice", dict(rank=1, xs=(4, 64, 160), F=64, k=(3,), s=(1,), d=(1,), pad="same", cf=False, act="relu")),
+]
+
+
+@pytest.mark.parametrize("name,c", BWD_CASES, ids=[b[0] for b in BWD_CASES])
+def test_conv_backward_vs_oracle(cnn, monkeypatch, name, c):
+    monkeypatch.setenv("QNN_ALGO", "general")
+    monkeypatch.setenv("QNN_MATH", "fp32")
+    rng = np.random.default_rng(len(name))
+    rank, F = c["rank"], c["F"]
+    x = rng.normal(size=c["xs"]).astype(np.float32)
+    in_q = c["xs"][1 if c["cf"] else -1] // 4
+    kern = (rng.normal(size=c["k"] + (in_q, 4 * F)) / np.sqrt(4 * in_q)).astype(np.float32)
+    bias = rng.normal(0, 0.1, 4 * F).astype(np.float32)
+    fmt = "channels_first" if c["cf"] else "channels_last"
+    cls = {1: cnn.QuaternionConv1D, 2: cnn.QuaternionConv2D, 3: cnn.QuaternionConv3D}[rank]
+    layer = cls(F, c["k"], strides=c["s"], dilation_rate=c["d"], padding=c["pad"], data_format=fmt, activation=c["act"])
+    layer.build((None,) + c["xs"][1:])
+    layer.built = True
+    layer.set_weights([kern, bias])
+    xd = dev(x)
+    y = layer(xd)
+    dy = rng.normal(size=tuple(y.shape)).astype(np.float32)
+    dx, dk, db = layer.backward(xd, y, dev(dy))
+    rdx, rdk, rdb = O.qconv_backward(x, kern, bias, F, c["s"], c["pad"], fmt, c["d"], c["act"], dy)
+    check(dx.cpu().numpy(), rdx, 1e-4, "dx")
+    check(dk.cpu().numpy(), rdk, 1e-4, "dkernel")
+    check(db.cpu().numpy(), rdb, 1e-4, "dbias")
+
+
+def test_dense_backward_vs_oracle(cnn, monkeypatch):
+    monkeypatch.setenv("QNN_ALGO", "general")
+    monkeypatch.setenv("QNN_MATH", "fp32")
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(37, 24)).astype(np.float32)
+    kern = rng.normal(size=(6, 20)).astype(np.float32)
+    bias = rng.normal(size=20).astype(np.float32)
+    layer = cnn.QuaternionDense(20, activation="relu")
+    layer.build((None, 24))
+    layer.built = True
+    layer.set_weights([kern, bias])
+    xd = dev(x)
+    y = layer(xd)
+    dy = rng.normal(size=(37, 20)).astype(np.float32)
+    bucket = torch.zeros(6 * 20 + 20, device="cuda")          # gradients written straight into a flat bucket
+    dx, dk, db = layer.backward(xd, y, dev(dy), grad_kernel_out=bucket[:120].view(6, 20), grad_bias_out=bucket[120:])
+    rdx, rdk, rdb = O.qdense_backward(x, kern, bias, 20, "relu", dy)
+    check(dx.cpu().numpy(), rdx, 1e-4)
+    check(bucket[:120].view(6, 20).cpu().numpy(), rdk, 1e-4)
+    check(bucket[120:].cpu().numpy(), rdb, 1e-4)
+
+
+def _avg_pool_same(x, pool):
+    """AveragePooling1D(pool, padding='same') with TF semantics (divisor counts in-range samples only)."""
+    n = x.shape[1]
+    out = -(-n // pool)
+    total = max((out - 1) * pool + pool - n, 0)
+    lo = total // 2
+    ys = []
+    for o in range(out):
+        a, b = max(o * pool - lo, 0), min(o * pool - lo + pool, n)
+        ys.append(x[:, a:b].mean(dim=1))
+    return torch.stack(ys, dim=1)
+
+
+def test_decoda_models_vs_reference_golden(cnn, golden):
+    """BASELINE.json configs[0]: the reference's own DNN / CNN builders (models/example_model.py) on DECODA documents;
+    the quaternion layers are ours, pooling / flatten / the softmax head are plain torch ops in this test."""
+    g = golden.load("decoda_models")
+    x = dev(g["x"])
+    # QDNN: Flatten -> 3 x QuaternionDense(512, relu) -> Dense(8, softmax)   (example_model.py:69-79)
+    h = x.reshape(x.shape[0], -1)
+    for i in range(3):
+        layer = cnn.QuaternionDense(512, activation="relu")
+        layer.build((None, h.shape[1]))
+        layer.built = True
+        layer.set_weights([g["QDNN.w%d" % (2 * i)], g["QDNN.w%d" % (2 * i + 1)]])
+        h = layer(h)
+    probs = torch.softmax(h @ dev(g["QDNN.w6"]) + dev(g["QDNN.w7"]), dim=-1)
+    check(probs.cpu().numpy(), g["QDNN.probs"], TF32_TOL, "QDNN")
+    # QCNN: QConv1D(32,3) -> AvgPool(2) -> QConv1D(64,3) -> AvgPool(4) -> Flatten -> QDense(256) -> Dense(8)  (:22-47)
+    c1 = cnn.QuaternionConv1D(32, 3, strides=1, activation="relu", padding="same")
+    c1.build((None, 250, 4))
+    c1.built = True
+    c1.set_weights([g["QCNN.w0"], g["QCNN.w1"]])
+    h = _avg_pool_same(c1(x), 2)
+    c2 = cnn.QuaternionConv1D(64, 3, strides=1, activation="relu", padding="same")
+    c2.build((None, 125, 128))
+    c2.built = True
+    c2.set_weights([g["QCNN.w2"], g["QCNN.w3"]])
+    h = _avg_pool_same(c2(h.contiguous()), 4)
+    h = h.reshape(h.shape[0], -1)
+    d = cnn.QuaternionDense(256, activation="relu")
+    d.build((None, h.shape[1]))
+    d.built = True
+    d.set_weights([g["QCNN.w4"], g["QCNN.w5"]])
+    h = d(h.contiguous())
+    probs = torch.softmax(h @ dev(g["QCNN.w6"]) + dev(g["QCNN.w7"]), dim=-1)
+    check(probs.cpu().numpy(), g["QCNN.probs"], TF32_TOL, "QCNN")
+
+
+def test_empty_batch_and_short_sequences(cnn):
+    layer = cnn.QuaternionConv1D(16, 3, padding="valid")
+    y = layer(torch.zeros((0, 5, 16), device="cuda"))
+    assert tuple(y.shape) == (0, 3, 64)
+    y = layer(torch.zeros((2, 2, 16), device="cuda"))      # shorter than the kernel -> no output positions
+    assert tuple(y.shape) == (2, 0, 64)
+    d = cnn.QuaternionDense(64)
+    assert tuple(d(torch.zeros((0, 16), device="cuda")).shape) == (0, 64)

@@ -1,0 +1,254 @@
+"""CPU tests of the host side: the `complexnn` mirror keeps the reference's API surface (names, constructor
+arguments, stored-weight layout, output shapes, config keys, error behaviour) and the C-ABI library loads and exports
+what include/qnn.h declares.  No compute call is made here (that needs a GPU; see test_gpu_parity.py)."""
+import ctypes
+import json
+import os
+import re
+
+import numpy as np
+import pytest
+
+import complexnn
+from complexnn import (QuaternionConv, QuaternionConv1D, QuaternionConv2D, QuaternionConv3D, QuaternionDense,
+                       qconv_init, qdense_init, sqrt_init)
+from cases import CONV_CASES, conv_kwargs
+from oracle import qoracle as O
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "quaternion-convolutional-neural-networks-for-end-to-end-automatic-speech-recognition_b200")
+
+
+def test_export_list_matches_reference():
+    # reference complexnn/__init__.py:9-17
+    names = ["QuaternionConv", "QuaternionConv1D", "QuaternionConv2D", "QuaternionConv3D", "QuaternionDense",
+             "sqrt_init", "qdense_init", "qconv_init", "GetRFirst", "GetIFirst", "GetJFirst", "GetKFirst",
+             "getpart_quaternion_output_shape_first", "get_rpart_first", "get_ipart_first", "get_jpart_first",
+             "get_kpart_first"]
+    for n in names:
+        assert hasattr(complexnn, n), n
+    from complexnn.conv import QuaternionConvolution1D, QuaternionConvolution2D, QuaternionConvolution3D  # conv.py:818-820
+    assert QuaternionConvolution1D is QuaternionConv1D and QuaternionConvolution3D is QuaternionConv3D
+
+
+def test_product_never_imports_the_oracle():
+    for root, _, files in os.walk(PKG):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(root, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle", src, re.M), os.path.join(root, f)
+                assert "qoracle" not in src, os.path.join(root, f)
+
+
+def test_initialisers_bit_exact_with_reference(golden):
+    g = golden.load("init")
+    np.random.seed(7)
+    np.testing.assert_array_equal(qconv_init((3,), 5, 1, 6, "he")((3, 5, 6)), g["conv1d_he"])
+    np.random.seed(8)
+    np.testing.assert_array_equal(qconv_init((2, 3), 4, 2, 3, "glorot")((2, 3, 4, 3)), g["conv2d_glorot"])
+    np.random.seed(9)
+    np.testing.assert_array_equal(qdense_init((6, 5), "he")((6, 20)), g["dense_he"])
+    np.random.seed(10)
+    np.testing.assert_array_equal(qdense_init((4, 7), "glorot")((4, 28)), g["dense_glorot"])
+    with pytest.raises(ValueError, match="Invalid criterion"):
+        qdense_init((4, 7), "lecun")((4, 28))
+    assert np.allclose(sqrt_init()((3,)), 1 / np.sqrt(2))
+
+
+def test_stored_weight_layout():
+    c = QuaternionConv1D(64, 3, padding="same", activation="relu")
+    c.build((None, 256, 160))
+    assert c.kernel_shape == (3, 40, 64)                 # what build declares (conv.py:165) ...
+    assert c.kernel.shape == (3, 40, 256)                # ... and what the initialiser really returns
+    assert c.bias.shape == (256,)
+    assert [w.shape for w in c.weights] == [(3, 40, 256), (256,)]
+    c2 = QuaternionConv2D(128, (3, 3), data_format="channels_first")
+    c2.build((None, 256, 128, 128))
+    assert c2.kernel.shape == (3, 3, 64, 512)
+    d = QuaternionDense(256)                             # units = REAL outputs: 64 quaternion units
+    d.build((None, 160))
+    assert d.q_units == 64 and d.kernel.shape == (40, 256) and d.bias.shape == (256,)
+    n = QuaternionConv(1, 4, 3, normalize_weight=True)   # gammas exist (and are never used), order as conv.py:175-278
+    n.build((None, 10, 8))
+    assert [w.name.split("/")[1] for w in n.weights] == ["kernel", "gamma_rr", "gamma_ri", "gamma_rj", "gamma_rk",
+                                                          "gamma_ii", "gamma_ij", "gamma_ik", "gamma_jj", "gamma_jk",
+                                                          "gamma_kk", "bias"]
+    assert n.gamma_rr.shape == (2 * 4,) and np.allclose(n.gamma_rr.numpy(), 1 / np.sqrt(2)) and not n.gamma_ri.numpy().any()
+    nb = QuaternionDense(8, use_bias=False)
+    nb.build((None, 12))
+    assert nb.bias is None and len(nb.weights) == 1
+
+
+def test_constructor_defaults_and_normalisation():
+    c = QuaternionConv2D(8, 3)
+    assert c.kernel_size == (3, 3) and c.strides == (1, 1) and c.dilation_rate == (1, 1)
+    assert c.padding == "valid" and c.data_format == "channels_last" and c.use_bias and c.init_criterion == "he"
+    assert c.activation.name == "linear" and c.input_spec.ndim == 4
+    assert QuaternionConv3D(2, (1, 2, 3), strides=2).strides == (2, 2, 2)
+    with pytest.raises(ValueError):
+        QuaternionConv1D(8, (3, 3))
+    with pytest.raises(ValueError):
+        QuaternionConv1D(8, 3, padding="full")
+    with pytest.raises(ValueError):
+        QuaternionConv1D(8, 3, data_format="nchw")
+    with pytest.raises(TypeError):
+        QuaternionConv1D(8, 3, bogus=1)
+    d = QuaternionDense(16, input_dim=8, name="head")
+    assert d.name == "head" and d.batch_input_shape == (None, 8) and d.supports_masking
+    assert QuaternionConv1D(1, 1).name.startswith("quaternion_conv1d_")
+
+
+def test_error_behaviour_matches_reference():
+    with pytest.raises(KeyError):                        # conv.py:167: only 'quaternion' is a key
+        QuaternionConv1D(4, 3, kernel_initializer="quaternion_independent").build((None, 10, 8))
+    with pytest.raises(ValueError, match="channel dimension"):       # conv.py:161-163
+        QuaternionConv1D(4, 3).build((None, 10, None))
+    with pytest.raises(AssertionError):                  # dense.py:94
+        QuaternionDense(8).build((None, 4, 8))
+    with pytest.raises(AssertionError):                  # dense.py:95
+        QuaternionDense(8).build((None, 7))
+    with pytest.raises(ValueError, match="ndim"):        # InputSpec(ndim=rank+2)
+        QuaternionConv1D(4, 3)(np.zeros((2, 8), np.float32))
+    d = QuaternionDense(8)
+    d.build((None, 12))
+    d.built = True
+    with pytest.raises(ValueError, match="axis"):        # InputSpec(axes={-1: 4*in_q}) after build
+        d(np.zeros((2, 16), np.float32))
+    QuaternionDense(8, kernel_initializer="random_uniform").build((None, 8))    # silently ignored
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
+def test_compute_output_shape(golden, case):
+    name, rank, xs, filters, ksz, kw = case
+    cls = {1: QuaternionConv1D, 2: QuaternionConv2D, 3: QuaternionConv3D}[rank]
+    layer = cls(filters, ksz, **kw)
+    assert tuple(layer.compute_output_shape((None,) + xs[1:]))[1:] == golden.load("conv_forward")[name + ".y"].shape[1:]
+    assert QuaternionDense(12).compute_output_shape((5, 8)) == (5, 12)
+
+
+CONV_KEYS = {"filters", "kernel_size", "strides", "padding", "data_format", "dilation_rate", "activation", "use_bias",
+             "normalize_weight", "kernel_initializer", "bias_initializer", "gamma_diag_initializer",
+             "gamma_off_initializer", "kernel_regularizer", "bias_regularizer", "gamma_diag_regularizer",
+             "gamma_off_regularizer", "activity_regularizer", "kernel_constraint", "bias_constraint",
+             "gamma_diag_constraint", "gamma_off_constraint", "init_criterion", "spectral_parametrization", "rank"}
+DENSE_KEYS = {"units", "activation", "use_bias", "init_criterion", "kernel_initializer", "bias_initializer",
+              "kernel_regularizer", "bias_regularizer", "activity_regularizer", "kernel_constraint", "bias_constraint",
+              "seed"}
+
+
+def test_get_config_key_sets_and_json_safety():
+    base = {"name", "trainable", "dtype"}
+    cfg = QuaternionConv(2, 4, 3).get_config()                          # conv.py:375-401
+    assert set(cfg) - base == CONV_KEYS
+    cfg1 = QuaternionConv1D(4, 3, activation="relu").get_config()       # pops rank and data_format (conv.py:520-524)
+    assert set(cfg1) - base == CONV_KEYS - {"rank", "data_format"}
+    cfg2 = QuaternionConv2D(4, 3).get_config()                          # pops rank (conv.py:655-658)
+    assert set(cfg2) - base == CONV_KEYS - {"rank"}
+    assert set(QuaternionConv3D(4, 3).get_config()) - base == CONV_KEYS - {"rank"}
+    d = QuaternionDense(8, activation="relu", seed=3)
+    cfgd = d.get_config()                                               # dense.py:178-191
+    assert set(cfgd) - base == DENSE_KEYS and cfgd["seed"] == 3
+    for c in (cfg, cfg1, cfg2, cfgd):
+        json.dumps(c)                                                   # the shipped reference fails here
+    assert cfg1["activation"] == "relu" and cfg1["kernel_initializer"] == "quaternion"
+    assert cfg1["gamma_diag_initializer"] == "sqrt_init" and cfg1["bias_initializer"]["class_name"] == "Zeros"
+    clone = QuaternionConv1D.from_config(cfg1)
+    assert clone.get_config() == cfg1
+    clone_d = QuaternionDense.from_config(cfgd)
+    assert clone_d.get_config() == cfgd
+
+
+def test_get_set_weights_roundtrip():
+    np.random.seed(0)
+    c = QuaternionConv1D(4, 3)
+    c.build((None, 9, 8))
+    w = c.get_weights()
+    assert [a.dtype for a in w] == [np.float32, np.float32] and w[0].shape == (3, 2, 16)
+    new = [np.full_like(w[0], 0.5), np.arange(16, dtype=np.float32)]
+    c.set_weights(new)
+    np.testing.assert_array_equal(c.get_weights()[1], new[1])
+    with pytest.raises(ValueError):
+        c.set_weights([new[0]])
+    with pytest.raises(ValueError):
+        c.set_weights([new[0][:, :, :4], new[1]])
+    assert c.count_params() == 3 * 2 * 16 + 16
+
+
+def test_component_getters_blocked_layout():
+    from complexnn import (get_rpart_first, get_ipart_first, get_jpart_first, get_kpart_first, GetKFirst,
+                           getpart_quaternion_output_shape_first)
+    x3 = np.arange(2 * 3 * 8).reshape(2, 3, 8)            # ndim 3 -> last axis (utils.py:25-27)
+    np.testing.assert_array_equal(get_ipart_first(x3), x3[:, :, 2:4])
+    x4 = np.arange(2 * 8 * 3 * 3).reshape(2, 8, 3, 3)     # otherwise axis 1 (channels_first hard-wired, utils.py:20-23)
+    np.testing.assert_array_equal(get_rpart_first(x4), x4[:, 0:2])
+    np.testing.assert_array_equal(get_jpart_first(x4), x4[:, 4:6])
+    np.testing.assert_array_equal(get_kpart_first(x4), x4[:, 6:])
+    x2 = np.arange(2 * 8).reshape(2, 8)
+    np.testing.assert_array_equal(GetKFirst()(x2), x2[:, 6:])
+    assert getpart_quaternion_output_shape_first((None, 8, 3, 3)) == (None, 2, 3, 3)
+    assert getpart_quaternion_output_shape_first((None, 5, 8)) == (None, 5, 2)
+
+
+# --------------------------------------------------------------------------------------------------------- C ABI
+def test_library_exports_every_declared_symbol(native_lib):
+    header = open(os.path.join(REPO, "include", "qnn.h")).read()
+    declared = set(re.findall(r"QNN_API[^;]*?\b(qnn_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 16
+    from complexnn import _native
+    assert declared == set(_native.SIGNATURES), declared ^ set(_native.SIGNATURES)
+    raw = ctypes.CDLL(_native.LIB_PATH)
+    for sym in declared:
+        assert hasattr(raw, sym), sym
+    assert native_lib.qnn_abi_version() == 1
+    assert native_lib.qnn_launch_count() == 0
+
+
+def test_abi_geometry_matches_oracle_padding_rules(native_lib):
+    from complexnn import _native
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        rank = int(rng.integers(1, 4))
+        sp = [int(rng.integers(0, 30)) for _ in range(rank)]
+        ks = [int(rng.integers(1, 6)) for _ in range(rank)]
+        st = [int(rng.integers(1, 4)) for _ in range(rank)]
+        dl = [int(rng.integers(1, 4)) for _ in range(rank)]
+        pad = ["valid", "same", "causal"][int(rng.integers(0, 3 if rank == 1 else 2))]
+        d = _native.make_conv_desc(rank, 2, sp, 4, 8, ks, st, dl, pad, "channels_last", "relu")
+        out = (ctypes.c_int32 * 3)()
+        assert native_lib.qnn_conv_out_spatial(ctypes.byref(d), ctypes.byref(out)) == 0
+        expect = [O.pad_amounts(sp[a], ks[a], st[a], dl[a], pad)[2] for a in range(rank)]
+        assert list(out)[:rank] == expect, (sp, ks, st, dl, pad)
+        assert expect == [max(O.conv_output_length(sp[a], ks[a], pad, st[a], dl[a]), 0) for a in range(rank)]
+
+
+def test_abi_argument_errors_and_kernel_selection(native_lib):
+    from complexnn import _native
+    bad = _native.make_conv_desc(2, 1, (4, 4), 4, 16, (3, 3), (1, 1), (1, 1), "causal", "channels_last", None)
+    out = (ctypes.c_int32 * 3)()
+    assert native_lib.qnn_conv_out_spatial(ctypes.byref(bad), ctypes.byref(out)) == -1
+    assert b"causal" in native_lib.qnn_last_error()
+    with pytest.raises(ValueError, match="causal"):
+        _native.check(-1)
+    bad2 = _native.make_conv_desc(1, 1, (4,), 0, 16, (3,), (1,), (1,), "same", "channels_last", None)
+    assert native_lib.qnn_conv_out_spatial(ctypes.byref(bad2), ctypes.byref(out)) == -1
+    # BASELINE config 2 and the north-star dense shape run on the tensor-core kernel, ragged channel counts do not
+    cfg2 = _native.make_conv_desc(1, 256, (256,), 40, 64, (3,), (1,), (1,), "same", "channels_last", "relu")
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cfg2)) == 1
+    assert native_lib.qnn_dense_uses_tensor_cores(65536, 40, 64) == 1
+    assert native_lib.qnn_dense_uses_tensor_cores(32, 250, 128) == 0          # DECODA first layer: in_q % 4 != 0
+    s2 = _native.make_conv_desc(1, 8, (64,), 40, 64, (3,), (2,), (1,), "same", "channels_last", "relu")
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(s2)) == 0
+    cf = _native.make_conv_desc(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cf)) == 0
+    assert native_lib.qnn_allreduce_f32(None, 4, None) == -6                  # QNN_E_STATE: no communicator yet
+    assert native_lib.qnn_comm_init(2, 2, None) == -1
+
+
+def test_no_silent_cpu_fallback():
+    """Without a GPU the layer call must fail loudly, never compute on the host."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    layer = QuaternionDense(16)
+    with pytest.raises(RuntimeError, match="qnn error"):
+        layer(np.zeros((4, 16), np.float32))
