@@ -126,6 +126,10 @@ QNN_API int qnn_comm_init(int32_t rank, int32_t world_size, const void* unique_i
 QNN_API int qnn_allreduce_f32(float* buf, size_t count, void* stream); /* in-place sum */
 QNN_API int qnn_comm_destroy(void);
 
+/* Diagnostics: when `device_buffer` (>= 64 * 8 bytes per CTA, i.e. 148 * 512 bytes) is set, the tensor-core kernel
+ * records per-CTA clock64() timestamps of its pipeline events into it (layout: tools/tc_trace.py). NULL disables. */
+QNN_API int qnn_debug_trace(void* device_buffer, size_t bytes);
+
 /* Number of GPU kernels this library has launched in this process (all threads) -- for bench.py's gpu_launches. */
 QNN_API uint64_t qnn_launch_count(void);
 

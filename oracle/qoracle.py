@@ -166,6 +166,17 @@ def qdense_forward(x, kernel, bias, units, activation=None, acc_dtype=np.float64
     return y.astype(out_dtype) if out_dtype is not None else y
 
 
+def qconv_abs_bound(x, kernel, filters, strides=1, padding="valid", data_format="channels_last", dilation_rate=1):
+    """sum_k |x_k| |w_k| of every output's dot product (no bias): the scale a componentwise rounding bound refers to.
+    A product of two operands each rounded to nearest tf32 (10 mantissa bits) is off by at most 2^-10 |x_k w_k|."""
+    w_abs = np.abs(expand_conv_kernel(kernel, filters))
+    return real_conv(np.abs(x), w_abs, strides, padding, data_format, dilation_rate)
+
+
+def qdense_abs_bound(x, kernel, units):
+    return np.abs(x).astype(np.float64) @ np.abs(expand_dense_kernel(kernel, units // 4)).astype(np.float64)
+
+
 def qconv_output_shape(input_shape, filters, kernel_size, strides, padding, data_format, dilation_rate):
     """complexnn/conv.py:347-372."""
     rank = len(kernel_size)

@@ -42,6 +42,7 @@ SIGNATURES = {
     "qnn_conv_forward_host": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
     "qnn_dense_forward_host": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P,
                                               ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P]),
+    "qnn_debug_trace": (ctypes.c_int, [_P, ctypes.c_size_t]),
     "qnn_comm_unique_id": (ctypes.c_int, [_P]),
     "qnn_comm_init": (ctypes.c_int, [ctypes.c_int32, ctypes.c_int32, _P]),
     "qnn_allreduce_f32": (ctypes.c_int, [_P, ctypes.c_size_t, _P]),

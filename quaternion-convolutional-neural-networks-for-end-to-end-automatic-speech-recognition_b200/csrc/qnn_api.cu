@@ -361,6 +361,11 @@ int qnn_dense_forward_host(int64_t rows, int32_t in_q, int32_t q_units, const fl
                         static_cast<cudaStream_t>(stream));
 }
 
+int qnn_debug_trace(void* device_buffer, size_t bytes) {
+    tc_set_trace(device_buffer, bytes);
+    return QNN_OK;
+}
+
 int qnn_comm_unique_id(void* out_128_bytes) {
     std::lock_guard<std::mutex> lock(g_comm_mu);
     if (!out_128_bytes) {

@@ -41,6 +41,7 @@ struct TcPlan {
     const char* why;  // reason when !ok
 };
 TcPlan tc_plan(const Geom& g, int rank);
+void tc_set_trace(void* device_buffer, size_t bytes);
 int tc_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
 
 }  // namespace qnn

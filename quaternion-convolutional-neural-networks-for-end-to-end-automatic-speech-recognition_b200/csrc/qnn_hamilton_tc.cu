@@ -6,15 +6,16 @@
 // exists: the 16 signed blocks are 16 tcgen05.mma instructions that share 4 A operands (the input components) and
 // 4 B operands (the sub-filters); the sign is the instruction descriptor's negate bit.
 //
-// One persistent CTA per SM, 384 threads, warp-specialised:
-//   warp 0      TMA producer: raw fp32 x tiles (128 rows + halo, one component, <=32 channels) -> 128B-swizzled smem ring
-//   warps 4-7   converters  : smem -> registers, round-to-nearest tf32 (the tensor core would truncate), tcgen05.st into
-//                             a ring of A-operand slots in tensor memory; the tap shift is a row offset in this read
-//   warp 1      MMA issuer  : per slot 4 k-steps x 4 output components, A from TMEM, B = sub-filter block resident in
-//                             smem (packed + rounded once per CTA, K-major / no swizzle), accumulators in TMEM
-//   warps 8-11  epilogue    : tcgen05.ld -> +bias -> activation -> swizzled staging -> TMA store (clips ragged tiles)
-//   warp 2      owns the TMEM allocation
-// TMEM columns: [0,256) four fp32 accumulators y_r|y_i|y_j|y_k (F <= 64 per pass), [256,512) eight 32-column A slots.
+// One persistent CTA per SM, 512 threads, warp-specialised:
+//   warp 0       TMA producer: raw fp32 x tiles (128 rows + halo, one component, <=32 channels) -> 128B-swizzled smem ring
+//   warps 4-7    converters  : smem -> registers, round-to-nearest tf32 (the tensor core would truncate), tcgen05.st into
+//                              a ring of A-operand slots in tensor memory; the tap shift is a row offset in this read
+//   warps 1,2    MMA issuers : warp 1 feeds accumulators y_r,y_i, warp 2 feeds y_j,y_k; per slot <=4 k-steps x 2 blocks,
+//                              A from TMEM, B = sub-filter block resident in smem (K-major, no swizzle)
+//   warps 8-15   epilogue    : first pack + round the sub-filters into smem (overlapping the first x loads), then per
+//                              tile tcgen05.ld -> +bias -> activation -> swizzled staging -> TMA store (clips ragged tiles)
+//   warp 3       owns the TMEM allocation
+// TMEM columns: [0,256) four fp32 accumulators y_r|y_i|y_j|y_k (<= 64 filters per pass), [256,512) eight 32-column A slots.
 #include <algorithm>
 #include <mutex>
 #include "qnn_common.h"
@@ -26,36 +27,120 @@ namespace {
 using namespace ptx;
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 384;
+constexpr int kThreads = 512;
 constexpr int kASlots = 8;
 constexpr int kASlotCols = 32;
 constexpr int kAccCols = 256;
 constexpr int kMaxXStages = 4;
 constexpr int kStagingBytes = kTileM * 128;  // one [128 x 32] fp32 store tile
 constexpr uint32_t kSmemLimit = 232448;      // 227 KB opt-in maximum per CTA
+constexpr int kPackThreads = 256;            // the epilogue warps
 
-// bit (a*4+b) set when block (input component a -> output component b) enters negated: conv table, SURVEY 3.2
+// bit (a*4+b) set when block (input component a -> output component b) enters negated: conv table, SURVEY 3.2.
+// The dense layer uses the transposed table (bit b*4+a), SURVEY 3.3.
 constexpr uint32_t kNegConv = (1u << 4) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 12) | (1u << 14);
+__host__ __device__ constexpr bool block_negated(int a, int b, bool conj) {
+    return ((kNegConv >> (conj ? (b * 4 + a) : (a * 4 + b))) & 1u) != 0;
+}
+
+enum { kActLinear = 0, kActRelu = 1, kActGeneric = 2 };
+
+// Optional per-CTA event trace (diagnostics, qnn_debug_trace): 64 clock64() slots per CTA, see tools/tc_trace.py
+constexpr int kTraceSlots = 64;
+enum { kTrStart = 0, kTrSetup = 1, kTrPacked = 2, kTrFirstTma = 3, kTrTmaDone = 4, kTrFirstX = 5, kTrWReady = 6,
+       kTrFirstA = 7, kTrTile0 = 8 /* + 5 * tile: acc_empty passed, acc_full committed, epilogue got acc, TMEM released,
+                                     stores issued */, kTrEnd = 58, kTrGlobalStart = 59, kTrGlobalEnd = 60, kTrSm = 61 };
 
 struct TcParams {
+    unsigned long long* trace;
     int n_tiles, tiles_per_seq;
     int taps, dil, pad_lo;
     int in_q, in_q_pad, n_chunks;
     int F, f_tile, n_ftiles;
     int rows_in, x_stages, x_stage_bytes;
-    int act, conj_w, has_bias;
+    int act, has_bias;
     uint32_t w_bytes;
 };
 
 struct __align__(8) Barriers {
     uint64_t x_full[kMaxXStages], x_empty[kMaxXStages];
     uint64_t a_full[kASlots], a_empty[kASlots];
-    uint64_t acc_full, acc_empty;
+    uint64_t acc_full, acc_empty, w_ready;
     uint32_t tmem_base;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void trace(const TcParams& p, int slot) {
+    if (p.trace && slot < kTraceSlots) p.trace[(size_t)blockIdx.x * kTraceSlots + slot] = (unsigned long long)clock64();
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
 
+__device__ __forceinline__ void group_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+
+// D[tmem] (+)= A[tmem] * B[smem]; descriptor passed as two 32-bit halves
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
+                                       uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 d;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// All MMAs of input component A for this issuer's two output components (B0, B0+1), every chunk and tap.
+template <int A, int B0, bool CONJ>
+__device__ __forceinline__ void issue_component(const TcParams& p, Barriers* bars, bool elected, uint32_t t_acc,
+                                                uint32_t t_a, uint32_t w_lo, uint32_t desc_hi, uint32_t idesc_pos,
+                                                uint32_t idesc_neg, uint32_t& as, uint32_t& aph, uint32_t& accumulate) {
+    const int Fp = p.f_tile, KQ = p.in_q_pad >> 2;
+    const uint32_t sub_stride = (uint32_t)KQ * Fp;  // descriptor-lo units (16 B) between sub-filters
+    const uint32_t tap_stride = 4u * sub_stride;
+    for (int ch = 0; ch < p.n_chunks; ++ch) {
+        const int ksteps = min(32, p.in_q_pad - ch * 32) >> 3;
+        for (int tap = 0; tap < p.taps; ++tap) {
+            mbar_wait(&bars->a_full[as], aph);
+            tc_fence_after_sync();
+            if (A == 0 && B0 == 0 && ch == 0 && tap == 0 && accumulate == 0 && elected) trace(p, kTrFirstA);
+            if (elected) {
+                const uint32_t base = w_lo + tap * tap_stride + (uint32_t)(ch * 8) * Fp;
+                const uint32_t a_col = t_a + as * kASlotCols;
+                for (int ks = 0; ks < ksteps; ++ks) {
+                    const uint32_t kofs = base + (uint32_t)(ks * 2) * Fp;
+#pragma unroll
+                    for (int bb = 0; bb < 2; ++bb) {
+                        constexpr int dummy = 0;
+                        (void)dummy;
+                        const int b = B0 + bb;
+                        const int c = A ^ b;  // sub-filter index: IDX[a][b] = a xor b
+                        mma_ts(t_acc + b * Fp, a_col + ks * 8, kofs + c * sub_stride, desc_hi,
+                               block_negated(A, b, CONJ) ? idesc_neg : idesc_pos, accumulate);
+                    }
+                    accumulate = 1;
+                }
+                mma_commit(&bars->a_empty[as]);  // one of the two arrivals that free the slot
+            }
+            __syncwarp();
+            if (++as == kASlots) { as = 0; aph ^= 1; }
+        }
+    }
+}
+
+template <int ACT>
+__device__ __forceinline__ float activate(float v, int act_rt) {
+    if (ACT == kActLinear) return v;
+    if (ACT == kActRelu) return fmaxf(v, 0.f);
+    return act_apply(v, act_rt);
+}
+
+template <bool CONJ, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const TcParams p,
               const float* __restrict__ w, const float* __restrict__ bias) {
@@ -63,14 +148,22 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* w_s = smem;                                               // resident sub-filters of the current f-tile
     uint8_t* x_s = w_s + ((p.w_bytes + 1023u) & ~1023u);               // x ring
-    uint8_t* y_s = x_s + (size_t)p.x_stages * p.x_stage_bytes;         // 2 staging tiles
+    uint8_t* y_s = x_s + (size_t)p.x_stages * p.x_stage_bytes;         // 2 staging tiles (one per epilogue group)
     float* bias_s = reinterpret_cast<float*>(y_s + 2 * kStagingBytes); // 4 * f_tile floats
     Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(bias_s) + 1024);
 
-    const int tid = threadIdx.x, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
     const int Fp = p.f_tile, KQ = p.in_q_pad >> 2;
 
     if (tid == 0) {
+        trace(p, kTrStart);
+        if (p.trace) {
+            p.trace[(size_t)blockIdx.x * kTraceSlots + kTrGlobalStart] = globaltimer_ns();
+            uint32_t smid;
+            asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+            p.trace[(size_t)blockIdx.x * kTraceSlots + kTrSm] = smid;
+        }
         tma_prefetch_desc(&tmx);
         tma_prefetch_desc(&tmy);
         for (int i = 0; i < kMaxXStages; ++i) {
@@ -79,13 +172,14 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         }
         for (int i = 0; i < kASlots; ++i) {
             mbar_init(&bars->a_full[i], 128);
-            mbar_init(&bars->a_empty[i], 1);
+            mbar_init(&bars->a_empty[i], 2);
         }
-        mbar_init(&bars->acc_full, 1);
-        mbar_init(&bars->acc_empty, 128);
+        mbar_init(&bars->acc_full, 2);
+        mbar_init(&bars->acc_empty, 256);
+        mbar_init(&bars->w_ready, kPackThreads);
         fence_mbar_init();
     }
-    if (warp == 2) {
+    if (warp == 3) {
         tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
@@ -94,31 +188,16 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     tc_fence_after_sync();
     const uint32_t t_acc = bars->tmem_base;
     const uint32_t t_a = t_acc + kAccCols;
+    if (tid == 0) trace(p, kTrSetup);
 
     // pipeline state persists across tiles and f-tile passes
-    uint32_t xs = 0, xph = 0, as = 0, aph = 0, accph = 0, sbuf = 0;
+    uint32_t xs = 0, xph = 0, as = 0, aph = 0, accph = 0;
 
     for (int ft = 0; ft < p.n_ftiles; ++ft) {
-        // ---- pack the four sub-filters of this f-tile: stored [tap][q][c*F+f] -> smem [(tap*4+c)][q/4][f][q%4], tf32-rn
-        {
-            const int per_tap = p.in_q_pad * 4 * Fp;
-            const int total = p.taps * per_tap;
-            for (int i = tid; i < total; i += kThreads) {
-                const int f = i % Fp, c = (i / Fp) & 3, q = (i / (4 * Fp)) % p.in_q_pad, tap = i / per_tap;
-                float v = 0.f;
-                if (q < p.in_q) v = __ldg(w + ((size_t)tap * p.in_q + q) * 4 * p.F + c * p.F + ft * Fp + f);
-                const uint32_t off = ((((uint32_t)(tap * 4 + c) * KQ + (q >> 2)) * Fp + f) << 4) + ((q & 3) << 2);
-                *reinterpret_cast<uint32_t*>(w_s + off) = f32_to_tf32_rn(v);
-            }
-            for (int i = tid; i < 4 * Fp; i += kThreads)
-                bias_s[i] = p.has_bias ? __ldg(bias + (i / Fp) * p.F + ft * Fp + (i % Fp)) : 0.f;
-            fence_proxy_async_smem();  // generic-proxy writes above are read by the tensor core (async proxy)
-            __syncthreads();
-        }
-
         if (warp == 0) {
             // =========================== TMA producer ===========================
-            if (tid == 0) {
+            if (elect_one()) {
+                bool first = ft == 0;
                 for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                     const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
                     for (int a = 0; a < 4; ++a)
@@ -127,47 +206,43 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                             mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)p.rows_in * 128u);
                             tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], ch * 32, a,
                                         t0 - p.pad_lo, b);
+                            if (first) { trace(p, kTrFirstTma); first = false; }
                             if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
                         }
                 }
+                trace(p, kTrTmaDone);
             }
-        } else if (warp == 1) {
-            // =========================== MMA issuer ===========================
-            if (tid == 32) {
-                const uint32_t idesc_pos = idesc_tf32(kTileM, Fp, false, false);
-                const uint32_t idesc_neg = idesc_tf32(kTileM, Fp, false, true);
-                const uint32_t w_addr = smem_u32(w_s);
-                const uint32_t lbo = (uint32_t)Fp * 16u;
-                for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                    mbar_wait(&bars->acc_empty, accph ^ 1);
-                    tc_fence_after_sync();
-                    uint32_t accumulate = 0;
-                    for (int a = 0; a < 4; ++a)
-                        for (int ch = 0; ch < p.n_chunks; ++ch) {
-                            const int ksteps = min(32, p.in_q_pad - ch * 32) >> 3;
-                            for (int tap = 0; tap < p.taps; ++tap) {
-                                mbar_wait(&bars->a_full[as], aph);
-                                tc_fence_after_sync();
-                                for (int ks = 0; ks < ksteps; ++ks) {
-                                    const uint32_t a_col = t_a + as * kASlotCols + ks * 8;
-#pragma unroll
-                                    for (int b = 0; b < 4; ++b) {
-                                        const int c = a ^ b;  // sub-filter index: IDX[a][b] = a xor b
-                                        const uint32_t bit = p.conj_w ? (b * 4 + a) : (a * 4 + b);
-                                        const uint32_t b_addr =
-                                            w_addr + (((uint32_t)(tap * 4 + c) * KQ + (ch * 8 + ks * 2)) * Fp << 4);
-                                        mma_tf32_ts(t_acc + b * Fp, a_col, smem_desc_kmajor_noswz(b_addr, lbo, 128),
-                                                    ((kNegConv >> bit) & 1u) ? idesc_neg : idesc_pos, accumulate);
-                                    }
-                                    accumulate = 1;
-                                }
-                                mma_commit(&bars->a_empty[as]);  // slot free once these MMAs have read it
-                                if (++as == kASlots) { as = 0; aph ^= 1; }
-                            }
-                        }
-                    mma_commit(&bars->acc_full);
-                    accph ^= 1;
+        } else if (warp == 1 || warp == 2) {
+            // =========================== MMA issuers (whole warp runs the loops, one lane issues) ===========================
+            const bool elected = elect_one();
+            const uint32_t idesc_pos = idesc_tf32(kTileM, Fp, false, false);
+            const uint32_t idesc_neg = idesc_tf32(kTileM, Fp, false, true);
+            const uint32_t lbo = (uint32_t)Fp * 16u;
+            const uint64_t d0 = smem_desc_kmajor_noswz(smem_u32(w_s), lbo, 128);
+            const uint32_t w_lo = (uint32_t)d0, desc_hi = (uint32_t)(d0 >> 32);
+            mbar_wait(&bars->w_ready, ft & 1);  // this pass' sub-filters are packed and visible to the async proxy
+            if (warp == 1 && elected && ft == 0) trace(p, kTrWReady);
+            int tcount = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
+                mbar_wait(&bars->acc_empty, accph ^ 1);
+                tc_fence_after_sync();
+                if (warp == 1 && elected && ft == 0) trace(p, kTrTile0 + 5 * tcount);
+                uint32_t accumulate = 0;
+                if (warp == 1) {
+                    issue_component<0, 0, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
+                    issue_component<1, 0, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
+                    issue_component<2, 0, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
+                    issue_component<3, 0, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
+                } else {
+                    issue_component<0, 2, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
+                    issue_component<1, 2, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
+                    issue_component<2, 2, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
+                    issue_component<3, 2, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
                 }
+                if (elected) mma_commit(&bars->acc_full);
+                if (warp == 1 && elected && ft == 0) trace(p, kTrTile0 + 5 * tcount + 1);
+                __syncwarp();
+                accph ^= 1;
             }
         } else if (warp >= 4 && warp < 8) {
             // =========================== converters: smem fp32 -> tf32(rn) -> TMEM A slots ===========================
@@ -178,6 +253,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     for (int ch = 0; ch < p.n_chunks; ++ch) {
                         const int kc = min(32, p.in_q_pad - ch * 32);
                         mbar_wait(&bars->x_full[xs], xph);
+                        if (r == 0 && a == 0 && ch == 0 && tile == (int)blockIdx.x && ft == 0) trace(p, kTrFirstX);
                         const uint8_t* xb = x_s + (size_t)xs * p.x_stage_bytes;
                         for (int tap = 0; tap < p.taps; ++tap) {
                             const uint32_t row = (uint32_t)(r + tap * p.dil);
@@ -201,56 +277,106 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     }
             }
         } else if (warp >= 8) {
-            // =========================== epilogue ===========================
-            const int r = tid - 256;
+            // =========================== packers, then epilogue ===========================
+            const int e = tid - 256;  // 0..255
+            {
+                // stored [tap][q][c*F + f] -> smem [(tap*4+c)][q/4][f][q%4] (K-major core matrices), rounded to tf32.
+                // One item = 4 consecutive q of one (tap, c, f): 4 coalesced loads, one 16-byte shared store.
+                const int items = p.taps * 4 * KQ * Fp;
+                for (int i0 = e; i0 < items; i0 += 4 * kPackThreads) {
+                    float v[4][4];
+                    uint32_t off[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = i0 + u * kPackThreads;
+                        const int f = i % Fp, q4 = (i / Fp) % KQ, c = (i / (Fp * KQ)) & 3, tap = i / (Fp * KQ * 4);
+                        off[u] = (uint32_t)i << 4;  // item index == 16-byte slot index in the packed image
+                        const bool in = i < items;
+                        const float* src = w + ((size_t)(in ? tap : 0) * p.in_q + q4 * 4) * 4 * p.F + c * p.F + ft * Fp + f;
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            v[u][j] = (in && q4 * 4 + j < p.in_q) ? __ldg(src + (size_t)j * 4 * p.F) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        if (i0 + u * kPackThreads < items)
+                            *reinterpret_cast<uint4*>(w_s + off[u]) =
+                                make_uint4(f32_to_tf32_rn(v[u][0]), f32_to_tf32_rn(v[u][1]), f32_to_tf32_rn(v[u][2]),
+                                           f32_to_tf32_rn(v[u][3]));
+                }
+                for (int i = e; i < 4 * Fp; i += kPackThreads)
+                    bias_s[i] = p.has_bias ? __ldg(bias + (i / Fp) * p.F + ft * Fp + (i % Fp)) : 0.f;
+                fence_proxy_async_smem();  // generic-proxy writes above are read by the tensor core (async proxy)
+                mbar_arrive(&bars->w_ready);
+                asm volatile("bar.sync 3, 256;" ::: "memory");  // bias_s visible to every epilogue thread
+                if (e == 0 && ft == 0) trace(p, kTrPacked);
+            }
+            const int grp = e >> 7;        // epilogue group: 0 handles even 32-column chunks, 1 the odd ones
+            const int r = e & 127;         // accumulator row == TMEM lane
             const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
-            const int n_chunks_out = (4 * Fp) >> 5;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+            const int n_pairs = (4 * Fp) >> 6;  // 32-column chunks per group
+            uint8_t* st = y_s + grp * kStagingBytes;
+            int tcount = 0;
+            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
                 const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
                 mbar_wait(&bars->acc_full, accph);
                 tc_fence_after_sync();
-                for (int c = 0; c < n_chunks_out; ++c) {
-                    uint32_t v[32];
-                    tmem_ld32(t_acc + lane_base + c * 32, v);
+                if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 2);
+                for (int i0 = 0; i0 < n_pairs; i0 += 2) {
+                    const bool two = i0 + 1 < n_pairs;
+                    const int c0 = (i0 * 2) + grp, c1 = c0 + 2;
+                    uint32_t v0[32], v1[32];
+                    tmem_ld32(t_acc + lane_base + c0 * 32, v0);
+                    if (two) tmem_ld32(t_acc + lane_base + c1 * 32, v1);
                     tmem_wait_ld();
-                    if (c == n_chunks_out - 1) {  // accumulators drained: the next tile's MMAs may start
+                    if (i0 + 2 >= n_pairs) {  // this thread's share of the accumulators is in registers
                         tc_fence_before_sync();
                         mbar_arrive(&bars->acc_empty);
+                        if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 3);
                     }
-                    if (r == 0) tma_store_wait_read<1>();  // the store that last used this staging tile has read it
-                    epi_bar_sync();
-                    uint8_t* st = y_s + sbuf * kStagingBytes;
-                    const float* bs = bias_s + c * 32;
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        float4 o;
-                        o.x = act_apply(__uint_as_float(v[4 * j + 0]) + bs[4 * j + 0], p.act);
-                        o.y = act_apply(__uint_as_float(v[4 * j + 1]) + bs[4 * j + 1], p.act);
-                        o.z = act_apply(__uint_as_float(v[4 * j + 2]) + bs[4 * j + 2], p.act);
-                        o.w = act_apply(__uint_as_float(v[4 * j + 3]) + bs[4 * j + 3], p.act);
-                        *reinterpret_cast<float4*>(st + swz128((uint32_t)r, (uint32_t)j)) = o;
+                    for (int h = 0; h < 2; ++h) {
+                        if (h == 1 && !two) break;
+                        const int c = h ? c1 : c0;
+                        const uint32_t* v = h ? v1 : v0;
+                        if (r == 0) tma_store_wait_read<0>();  // previous store of this group has read the staging tile
+                        group_bar_sync(1 + grp);
+                        const float4* bs = reinterpret_cast<const float4*>(bias_s + c * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const float4 bv = bs[j];
+                            float4 o;
+                            o.x = activate<ACT>(__uint_as_float(v[4 * j + 0]) + bv.x, p.act);
+                            o.y = activate<ACT>(__uint_as_float(v[4 * j + 1]) + bv.y, p.act);
+                            o.z = activate<ACT>(__uint_as_float(v[4 * j + 2]) + bv.z, p.act);
+                            o.w = activate<ACT>(__uint_as_float(v[4 * j + 3]) + bv.w, p.act);
+                            *reinterpret_cast<float4*>(st + swz128((uint32_t)r, (uint32_t)j)) = o;
+                        }
+                        fence_proxy_async_smem();
+                        group_bar_sync(1 + grp);
+                        if (r == 0) {
+                            // accumulator column c*32 -> output channel: component (c*32)/Fp, filter ft*Fp + (c*32)%Fp
+                            const int col = c * 32;
+                            tma_store_3d(&tmy, st, (col / Fp) * p.F + ft * Fp + (col % Fp), t0, b);
+                            tma_store_commit();
+                        }
                     }
-                    fence_proxy_async_smem();
-                    epi_bar_sync();
-                    if (r == 0) {
-                        // accumulator column c*32 -> output channel: component (c*32)/Fp, filter ft*Fp + (c*32)%Fp
-                        const int col = c * 32;
-                        const int ch_out = (col / Fp) * p.F + ft * Fp + (col % Fp);
-                        tma_store_3d(&tmy, st, ch_out, t0, b);
-                        tma_store_commit();
-                    }
-                    sbuf ^= 1;
                 }
+                if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 4);
                 accph ^= 1;
             }
             if (r == 0) tma_store_wait_all<0>();
         }
-        __syncthreads();  // every role is done with this f-tile's weights
+        __syncthreads();  // every role is done with this f-tile's sub-filters
     }
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 2) tmem_dealloc(t_acc, 512);
+    if (warp == 3) tmem_dealloc(t_acc, 512);
+    if (tid == 0) {
+        trace(p, kTrEnd);
+        if (p.trace) p.trace[(size_t)blockIdx.x * kTraceSlots + kTrGlobalEnd] = globaltimer_ns();
+    }
 }
 
 int num_sms() {
@@ -264,7 +390,25 @@ int num_sms() {
     return n;
 }
 
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams, const float*, const float*);
+
+TcKernel pick_kernel(bool conj, int act) {
+    const int a = act == QNN_ACT_LINEAR ? kActLinear : (act == QNN_ACT_RELU ? kActRelu : kActGeneric);
+    if (conj) return a == kActLinear ? k_hamilton_tc<true, kActLinear> : a == kActRelu ? k_hamilton_tc<true, kActRelu>
+                                                                                        : k_hamilton_tc<true, kActGeneric>;
+    return a == kActLinear ? k_hamilton_tc<false, kActLinear> : a == kActRelu ? k_hamilton_tc<false, kActRelu>
+                                                                               : k_hamilton_tc<false, kActGeneric>;
+}
+
+unsigned long long* g_trace = nullptr;
+size_t g_trace_bytes = 0;
+
 }  // namespace
+
+void tc_set_trace(void* device_buffer, size_t bytes) {
+    g_trace = static_cast<unsigned long long*>(device_buffer);
+    g_trace_bytes = bytes;
+}
 
 TcPlan tc_plan(const Geom& g, int rank) {
     TcPlan pl{};
@@ -278,22 +422,27 @@ TcPlan tc_plan(const Geom& g, int rank) {
     if (g.s[2] != 1) return no("stride != 1");
     if (g.in_q % 4) return no("in_q not a multiple of 4 (TMA stride alignment)");
     if (g.F % 16) return no("filters not a multiple of 16");
-    int f_tile = g.F;
-    if (g.F > 64) {
-        f_tile = (g.F % 64 == 0) ? 64 : (g.F % 32 == 0 ? 32 : 0);
-        if (!f_tile) return no("filters > 64 and not a multiple of 32");
-    }
     const int taps = g.k[2];
     const int rows_in = kTileM + (taps - 1) * g.d[2];
     if (rows_in > 256) return no("halo exceeds the 256-row TMA box");
     if (g.out_sp[2] < 1 || g.batch < 1) return no("empty problem");
     const int in_q_pad = (g.in_q + 7) & ~7;
-    const size_t w_bytes = (size_t)taps * 4 * in_q_pad * f_tile * 4;
-    const size_t w_pad = (w_bytes + 1023) & ~size_t(1023);
     const size_t stage = ((size_t)rows_in * 128 + 1023) & ~size_t(1023);
-    const size_t fixed = 1024 /*align slack*/ + w_pad + 2 * kStagingBytes + 1024 /*bias*/ + 512 /*barriers*/;
-    if (fixed + 2 * stage > kSmemLimit) return no("sub-filters do not fit in shared memory");
-    int stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / stage);
+    // Filters per pass: the whole layer when it fits (<= 64, accumulators 4 x f_tile TMEM columns); otherwise a
+    // divisor that is a multiple of 32, so that every 32-column store chunk stays inside one output component.
+    int f_tile = 0, stages = 0;
+    size_t fixed = 0;
+    const int cand[3] = {g.F <= 64 ? g.F : 0, 64, 32};
+    for (int ci = 0; ci < 3 && !f_tile; ++ci) {
+        const int ft = cand[ci];
+        if (ft <= 0 || ft > g.F || g.F % ft || (ft != g.F && ft % 32)) continue;
+        const size_t w_pad = (((size_t)taps * 4 * in_q_pad * ft * 4) + 1023) & ~size_t(1023);
+        fixed = 1024 /*align slack*/ + w_pad + 2 * kStagingBytes + 1024 /*bias*/ + 512 /*barriers*/;
+        if (fixed + 2 * stage > kSmemLimit) continue;
+        f_tile = ft;
+        stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / stage);
+    }
+    if (!f_tile) return no("sub-filters do not fit in shared memory for any admissible filter tile");
     pl.ok = 1;
     pl.f_tile = f_tile;
     pl.n_ftiles = g.F / f_tile;
@@ -337,7 +486,6 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     p.x_stages = pl.x_stages;
     p.x_stage_bytes = (int)(((size_t)pl.rows_in * 128 + 1023) & ~size_t(1023));
     p.act = g.act;
-    p.conj_w = g.conj_w;
     p.has_bias = bias != nullptr;
     p.w_bytes = (uint32_t)((size_t)p.taps * 4 * p.in_q_pad * p.f_tile * 4);
 
@@ -362,17 +510,26 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
             return QNN_E_CUDA;
         }
     }
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        attr_err = cudaFuncSetAttribute(k_hamilton_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
-    });
-    if (attr_err != cudaSuccess) {
-        set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
-        return QNN_E_CUDA;
+    TcKernel kern = pick_kernel(g.conj_w != 0, g.act);
+    static std::mutex mu;
+    static TcKernel configured[8];
+    static int n_configured = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        bool done = false;
+        for (int i = 0; i < n_configured; ++i) done |= configured[i] == kern;
+        if (!done) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
+            if (e != cudaSuccess) {
+                set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+                return QNN_E_CUDA;
+            }
+            configured[n_configured++] = kern;
+        }
     }
     const int grid = std::min(p.n_tiles, num_sms());
-    k_hamilton_tc<<<grid, kThreads, pl.smem_bytes, st>>>(tmx, tmy, p, w, bias);
+    p.trace = (g_trace && g_trace_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace : nullptr;
+    kern<<<grid, kThreads, pl.smem_bytes, st>>>(tmx, tmy, p, w, bias);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
