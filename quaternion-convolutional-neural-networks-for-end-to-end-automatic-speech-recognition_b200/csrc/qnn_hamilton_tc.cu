@@ -6,14 +6,18 @@
 // exists: the 16 signed blocks are 16 tcgen05.mma instructions that share 4 A operands (the input components) and
 // 4 B operands (the sub-filters); the sign is the instruction descriptor's negate bit.
 //
-// One persistent CTA per SM, 512 threads, warp-specialised:
-//   warp 0       TMA producer: raw fp32 x tiles (128 rows + halo, one component, <=32 channels) -> 128B-swizzled smem ring
+// One persistent CTA per SM, 768 threads, warp-specialised:
+//   warp 0       TMA producer: raw fp32 x tiles (128 rows + halo, 32 channels) -> 128B-swizzled smem ring.  When in_q is
+//                a multiple of 8 the channel axis is walked flat (a 32-channel box may span two components, no padding);
+//                otherwise per component with the out-of-range tail zero-filled by TMA
 //   warps 4-7    converters  : smem -> registers, round-to-nearest tf32 (the tensor core would truncate), tcgen05.st into
-//                              a ring of A-operand slots in tensor memory; the tap shift is a row offset in this read
+//                              a ring of A-operand slots in tensor memory; the tap shift is a row offset in this read;
+//                              all taps of a stage are converted as one batch (one tcgen05.wait::st per batch)
 //   warps 1,2    MMA issuers : warp 1 feeds accumulators y_r,y_i, warp 2 feeds y_j,y_k; per slot <=4 k-steps x 2 blocks,
 //                              A from TMEM, B = sub-filter block resident in smem (K-major, no swizzle)
-//   warps 8-15   epilogue    : first pack + round the sub-filters into smem (overlapping the first x loads), then per
-//                              tile tcgen05.ld -> +bias -> activation -> swizzled staging -> TMA store (clips ragged tiles)
+//   warps 8-23   epilogue    : first pack + round the sub-filters into smem (overlapping the first x loads); per tile all
+//                              16 warps pull the accumulators into registers at once (TMEM is free again after two
+//                              tcgen05.ld), then +bias -> activation -> swizzled staging -> TMA store (clips ragged tiles)
 //   warp 3       owns the TMEM allocation
 // TMEM columns: [0,256) four fp32 accumulators y_r|y_i|y_j|y_k (<= 64 filters per pass), [256,512) eight 32-column A slots.
 #include <algorithm>
@@ -27,21 +31,30 @@ namespace {
 using namespace ptx;
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 512;
+constexpr int kThreads = 768;
+constexpr int kEpiThreads = 512;             // warps 8..23
 constexpr int kASlots = 8;
 constexpr int kASlotCols = 32;
 constexpr int kAccCols = 256;
 constexpr int kMaxXStages = 4;
+constexpr int kMaxTapBatch = 4;              // taps converted per tcgen05.wait::st
 constexpr int kStagingBytes = kTileM * 128;  // one [128 x 32] fp32 store tile
 constexpr uint32_t kSmemLimit = 232448;      // 227 KB opt-in maximum per CTA
-constexpr int kPackThreads = 256;            // the epilogue warps
+// register budget: 768 x 80 = 61440 at launch = 128 x kRegsWg0 + 128 x kRegsWg1 + 512 x kRegsEpi
+constexpr int kRegsWg0 = 32, kRegsWg1 = 32, kRegsEpi = 104;
+static_assert(128 * kRegsWg0 + 128 * kRegsWg1 + 512 * kRegsEpi <= 768 * 80, "register pool");
 
 // bit (a*4+b) set when block (input component a -> output component b) enters negated: conv table, SURVEY 3.2.
 // The dense layer uses the transposed table (bit b*4+a), SURVEY 3.3.
 constexpr uint32_t kNegConv = (1u << 4) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 12) | (1u << 14);
-__host__ __device__ constexpr bool block_negated(int a, int b, bool conj) {
-    return ((kNegConv >> (conj ? (b * 4 + a) : (a * 4 + b))) & 1u) != 0;
+constexpr uint32_t transpose_bits(uint32_t m) {
+    uint32_t t = 0;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b)
+            if ((m >> (a * 4 + b)) & 1u) t |= 1u << (b * 4 + a);
+    return t;
 }
+constexpr uint32_t kNegDense = transpose_bits(kNegConv);
 
 enum { kActLinear = 0, kActRelu = 1, kActGeneric = 2 };
 
@@ -55,7 +68,11 @@ struct TcParams {
     unsigned long long* trace;
     int n_tiles, tiles_per_seq;
     int taps, dil, pad_lo;
-    int in_q, in_q_pad, n_chunks;
+    int in_q, in_q_pad;
+    int flat;      // 1: stages walk the flat 4*in_q channel axis (in_q % 8 == 0); 0: per component, padded to 8
+    int n_stages;  // x stages (TMA boxes) per tile
+    int n_chunks;  // padded mode: 32-channel chunks per component
+    int m8;        // flat mode: k-steps (8 channels) per component = in_q / 8
     int F, f_tile, n_ftiles;
     int rows_in, x_stages, x_stage_bytes;
     int act, has_bias;
@@ -78,7 +95,33 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
     return t;
 }
 
-__device__ __forceinline__ void group_bar_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+// Register re-balancing between warpgroups (each of the four warps of a warpgroup must execute it)
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// k-steps (8 channels each) held by x stage s
+__device__ __forceinline__ int stage_ksteps(const TcParams& p, int s) {
+    if (p.flat) return 4;
+    const int ch = s % p.n_chunks;
+    return min(32, p.in_q_pad - ch * 32) >> 3;
+}
+// input component and first quaternion channel of k-step ks of stage s
+__device__ __forceinline__ void kstep_coords(const TcParams& p, int s, int ks, int& a, int& q0) {
+    if (p.flat) {
+        const int kk = s * 4 + ks;
+        a = kk / p.m8;
+        q0 = (kk - a * p.m8) << 3;
+    } else {
+        a = s / p.n_chunks;
+        q0 = (s % p.n_chunks) * 32 + ks * 8;
+    }
+}
 
 // D[tmem] (+)= A[tmem] * B[smem]; descriptor passed as two 32-bit halves
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
@@ -95,49 +138,51 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_
         : "memory");
 }
 
-// All MMAs of input component A for this issuer's two output components (B0, B0+1), every chunk and tap.
-template <int A, int B0, bool CONJ>
-__device__ __forceinline__ void issue_component(const TcParams& p, Barriers* bars, bool elected, uint32_t t_acc,
-                                                uint32_t t_a, uint32_t w_lo, uint32_t desc_hi, uint32_t idesc_pos,
-                                                uint32_t idesc_neg, uint32_t& as, uint32_t& aph, uint32_t& accumulate) {
-    const int Fp = p.f_tile, KQ = p.in_q_pad >> 2;
-    const uint32_t sub_stride = (uint32_t)KQ * Fp;  // descriptor-lo units (16 B) between sub-filters
-    const uint32_t tap_stride = 4u * sub_stride;
-    for (int ch = 0; ch < p.n_chunks; ++ch) {
-        const int ksteps = min(32, p.in_q_pad - ch * 32) >> 3;
-        for (int tap = 0; tap < p.taps; ++tap) {
-            mbar_wait(&bars->a_full[as], aph);
-            tc_fence_after_sync();
-            if (A == 0 && B0 == 0 && ch == 0 && tap == 0 && accumulate == 0 && elected) trace(p, kTrFirstA);
-            if (elected) {
-                const uint32_t base = w_lo + tap * tap_stride + (uint32_t)(ch * 8) * Fp;
-                const uint32_t a_col = t_a + as * kASlotCols;
-                for (int ks = 0; ks < ksteps; ++ks) {
-                    const uint32_t kofs = base + (uint32_t)(ks * 2) * Fp;
-#pragma unroll
-                    for (int bb = 0; bb < 2; ++bb) {
-                        constexpr int dummy = 0;
-                        (void)dummy;
-                        const int b = B0 + bb;
-                        const int c = A ^ b;  // sub-filter index: IDX[a][b] = a xor b
-                        mma_ts(t_acc + b * Fp, a_col + ks * 8, kofs + c * sub_stride, desc_hi,
-                               block_negated(A, b, CONJ) ? idesc_neg : idesc_pos, accumulate);
-                    }
-                    accumulate = 1;
-                }
-                mma_commit(&bars->a_empty[as]);  // one of the two arrivals that free the slot
-            }
-            __syncwarp();
-            if (++as == kASlots) { as = 0; aph ^= 1; }
-        }
-    }
-}
-
 template <int ACT>
 __device__ __forceinline__ float activate(float v, int act_rt) {
     if (ACT == kActLinear) return v;
     if (ACT == kActRelu) return fmaxf(v, 0.f);
     return act_apply(v, act_rt);
+}
+
+// bias + activation on 32 accumulator columns of this thread's row, written to the swizzled staging tile
+template <int ACT>
+__device__ __forceinline__ void stage_chunk(const uint32_t (&v)[32], const float* bias32, uint8_t* st, int r, int act_rt) {
+    const float4* bs = reinterpret_cast<const float4*>(bias32);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float4 bv = bs[j];
+        float4 o;
+        o.x = activate<ACT>(__uint_as_float(v[4 * j + 0]) + bv.x, act_rt);
+        o.y = activate<ACT>(__uint_as_float(v[4 * j + 1]) + bv.y, act_rt);
+        o.z = activate<ACT>(__uint_as_float(v[4 * j + 2]) + bv.z, act_rt);
+        o.w = activate<ACT>(__uint_as_float(v[4 * j + 3]) + bv.w, act_rt);
+        *reinterpret_cast<float4*>(st + swz128((uint32_t)r, (uint32_t)j)) = o;
+    }
+}
+
+// One turn on a staging tile shared by the two 128-thread groups of a pair: the group whose turn it is writes its
+// chunk (bias + activation), both groups meet, its thread 0 issues the TMA store and waits until the tile has been read.
+template <int ACT>
+__device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn, int which, int pair, int turn, int r,
+                                          int n_out, int Fp, int ft, int t0, int b, const TcParams& p,
+                                          const float* bias_s, uint8_t* st, const CUtensorMap* tmy) {
+    const int c_act = pair + 2 * act_turn + 4 * which;  // 32-column chunk handled in this phase on this staging tile
+    if (c_act >= n_out) return;                        // uniform across the pair
+    const bool mine = turn == act_turn;
+    if (mine) {
+        stage_chunk<ACT>(v, bias_s + c_act * 32, st, r, p.act);
+        fence_proxy_async_smem();
+    }
+    named_bar_sync(5 + pair, 256);
+    if (mine && r == 0) {
+        // accumulator column c*32 -> output channel: component (c*32)/Fp, filter ft*Fp + (c*32)%Fp
+        const int col = c_act * 32;
+        tma_store_3d(tmy, st, (col / Fp) * p.F + ft * Fp + (col % Fp), t0, b);
+        tma_store_commit();
+        tma_store_wait_read<0>();  // the staging tile may now be overwritten by the partner group
+    }
+    named_bar_sync(5 + pair, 256);
 }
 
 template <bool CONJ, int ACT>
@@ -148,7 +193,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* w_s = smem;                                               // resident sub-filters of the current f-tile
     uint8_t* x_s = w_s + ((p.w_bytes + 1023u) & ~1023u);               // x ring
-    uint8_t* y_s = x_s + (size_t)p.x_stages * p.x_stage_bytes;         // 2 staging tiles (one per epilogue group)
+    uint8_t* y_s = x_s + (size_t)p.x_stages * p.x_stage_bytes;         // 2 staging tiles (one per epilogue group pair)
     float* bias_s = reinterpret_cast<float*>(y_s + 2 * kStagingBytes); // 4 * f_tile floats
     Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(bias_s) + 1024);
 
@@ -175,8 +220,8 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             mbar_init(&bars->a_empty[i], 2);
         }
         mbar_init(&bars->acc_full, 2);
-        mbar_init(&bars->acc_empty, 256);
-        mbar_init(&bars->w_ready, kPackThreads);
+        mbar_init(&bars->acc_empty, kEpiThreads);
+        mbar_init(&bars->w_ready, kEpiThreads);
         fence_mbar_init();
     }
     if (warp == 3) {
@@ -193,33 +238,45 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     // pipeline state persists across tiles and f-tile passes
     uint32_t xs = 0, xph = 0, as = 0, aph = 0, accph = 0;
 
-    for (int ft = 0; ft < p.n_ftiles; ++ft) {
+    // 768 threads x 80 registers are granted at launch.  The epilogue warpgroups (2..5) hold 64 accumulator values per
+    // thread and grow to 104; the producer / issuer / converter warpgroups (0, 1) shrink to 32.
+    // (setmaxnreg sits INSIDE each role branch: ptxas takes the minimum of the values that reach a join point.)
+
+    if (warp < 4) {
+      reg_dealloc<kRegsWg0>();
+      for (int ft = 0; ft < p.n_ftiles; ++ft) {
         if (warp == 0) {
             // =========================== TMA producer ===========================
             if (elect_one()) {
                 bool first = ft == 0;
                 for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                     const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
-                    for (int a = 0; a < 4; ++a)
-                        for (int ch = 0; ch < p.n_chunks; ++ch) {
-                            mbar_wait(&bars->x_empty[xs], xph ^ 1);
-                            mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)p.rows_in * 128u);
-                            tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], ch * 32, a,
+                    for (int s = 0; s < p.n_stages; ++s) {
+                        mbar_wait(&bars->x_empty[xs], xph ^ 1);
+                        mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)p.rows_in * 128u);
+                        uint8_t* dst = x_s + (size_t)xs * p.x_stage_bytes;
+                        if (p.flat)
+                            tma_load_3d(dst, &tmx, &bars->x_full[xs], s * 32, t0 - p.pad_lo, b);
+                        else
+                            tma_load_4d(dst, &tmx, &bars->x_full[xs], (s % p.n_chunks) * 32, s / p.n_chunks,
                                         t0 - p.pad_lo, b);
-                            if (first) { trace(p, kTrFirstTma); first = false; }
-                            if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
-                        }
+                        if (first) { trace(p, kTrFirstTma); first = false; }
+                        if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
+                    }
                 }
                 trace(p, kTrTmaDone);
             }
         } else if (warp == 1 || warp == 2) {
             // =========================== MMA issuers (whole warp runs the loops, one lane issues) ===========================
             const bool elected = elect_one();
+            const int b0 = warp == 1 ? 0 : 2;  // this issuer's two output components
             const uint32_t idesc_pos = idesc_tf32(kTileM, Fp, false, false);
             const uint32_t idesc_neg = idesc_tf32(kTileM, Fp, false, true);
-            const uint32_t lbo = (uint32_t)Fp * 16u;
-            const uint64_t d0 = smem_desc_kmajor_noswz(smem_u32(w_s), lbo, 128);
+            const uint64_t d0 = smem_desc_kmajor_noswz(smem_u32(w_s), (uint32_t)Fp * 16u, 128);
             const uint32_t w_lo = (uint32_t)d0, desc_hi = (uint32_t)(d0 >> 32);
+            const uint32_t sub_stride = (uint32_t)KQ * Fp;  // descriptor-lo units (16 B) between sub-filters
+            const uint32_t tap_stride = 4u * sub_stride;
+            constexpr uint32_t neg_table = CONJ ? kNegDense : kNegConv;
             mbar_wait(&bars->w_ready, ft & 1);  // this pass' sub-filters are packed and visible to the async proxy
             if (warp == 1 && elected && ft == 0) trace(p, kTrWReady);
             int tcount = 0;
@@ -228,36 +285,61 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 tc_fence_after_sync();
                 if (warp == 1 && elected && ft == 0) trace(p, kTrTile0 + 5 * tcount);
                 uint32_t accumulate = 0;
-                if (warp == 1) {
-                    issue_component<0, 0, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
-                    issue_component<1, 0, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
-                    issue_component<2, 0, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
-                    issue_component<3, 0, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
-                } else {
-                    issue_component<0, 2, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
-                    issue_component<1, 2, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
-                    issue_component<2, 2, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
-                    issue_component<3, 2, CONJ>(p, bars, elected, t_acc, t_a, w_lo, desc_hi, idesc_pos, idesc_neg, as, aph, accumulate);
+                for (int s = 0; s < p.n_stages; ++s) {
+                    const int nks = stage_ksteps(p, s);
+                    for (int tap = 0; tap < p.taps; ++tap) {
+                        mbar_wait(&bars->a_full[as], aph);
+                        tc_fence_after_sync();
+                        if (elected) {
+                            if (warp == 1 && ft == 0 && tcount == 0 && s == 0 && tap == 0) trace(p, kTrFirstA);
+                            const uint32_t a_col = t_a + as * kASlotCols;
+                            const uint32_t tap_lo = w_lo + tap * tap_stride;
+                            for (int ks = 0; ks < nks; ++ks) {
+                                int a, q0;
+                                kstep_coords(p, s, ks, a, q0);
+                                const uint32_t k_lo = tap_lo + (uint32_t)(q0 >> 2) * Fp;
+#pragma unroll
+                                for (int bb = 0; bb < 2; ++bb) {
+                                    const int b = b0 + bb;
+                                    const int c = a ^ b;  // sub-filter index: IDX[a][b] = a xor b
+                                    mma_ts(t_acc + b * Fp, a_col + ks * 8, k_lo + c * sub_stride, desc_hi,
+                                           ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos, accumulate);
+                                }
+                                accumulate = 1;
+                            }
+                            mma_commit(&bars->a_empty[as]);  // one of the two arrivals that free the slot
+                        }
+                        __syncwarp();
+                        if (++as == kASlots) { as = 0; aph ^= 1; }
+                    }
                 }
                 if (elected) mma_commit(&bars->acc_full);
                 if (warp == 1 && elected && ft == 0) trace(p, kTrTile0 + 5 * tcount + 1);
                 __syncwarp();
                 accph ^= 1;
             }
-        } else if (warp >= 4 && warp < 8) {
+        }
+        __syncthreads();  // every role is done with this f-tile's sub-filters
+      }
+    } else if (warp < 8) {
+      reg_dealloc<kRegsWg1>();
+      for (int ft = 0; ft < p.n_ftiles; ++ft) {
+        {
             // =========================== converters: smem fp32 -> tf32(rn) -> TMEM A slots ===========================
             const int r = tid - 128;
             const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                for (int a = 0; a < 4; ++a)
-                    for (int ch = 0; ch < p.n_chunks; ++ch) {
-                        const int kc = min(32, p.in_q_pad - ch * 32);
-                        mbar_wait(&bars->x_full[xs], xph);
-                        if (r == 0 && a == 0 && ch == 0 && tile == (int)blockIdx.x && ft == 0) trace(p, kTrFirstX);
-                        const uint8_t* xb = x_s + (size_t)xs * p.x_stage_bytes;
-                        for (int tap = 0; tap < p.taps; ++tap) {
-                            const uint32_t row = (uint32_t)(r + tap * p.dil);
-                            mbar_wait(&bars->a_empty[as], aph ^ 1);
+                for (int s = 0; s < p.n_stages; ++s) {
+                    const int kc = stage_ksteps(p, s) << 3;
+                    mbar_wait(&bars->x_full[xs], xph);
+                    if (r == 0 && s == 0 && tile == (int)blockIdx.x && ft == 0) trace(p, kTrFirstX);
+                    const uint8_t* xb = x_s + (size_t)xs * p.x_stage_bytes;
+                    for (int tap0 = 0; tap0 < p.taps; tap0 += kMaxTapBatch) {
+                        const int nb = min(kMaxTapBatch, p.taps - tap0);
+                        uint32_t as_b = as, aph_b = aph;
+                        for (int tb = 0; tb < nb; ++tb) {
+                            const uint32_t row = (uint32_t)(r + (tap0 + tb) * p.dil);
+                            mbar_wait(&bars->a_empty[as_b], aph_b ^ 1);
                             tc_fence_after_sync();
                             for (int k0 = 0; k0 < kc; k0 += 8) {
                                 const float4 v0 = *reinterpret_cast<const float4*>(xb + swz128(row, k0 >> 2));
@@ -265,109 +347,103 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                                 const uint32_t u[8] = {f32_to_tf32_rn(v0.x), f32_to_tf32_rn(v0.y), f32_to_tf32_rn(v0.z),
                                                        f32_to_tf32_rn(v0.w), f32_to_tf32_rn(v1.x), f32_to_tf32_rn(v1.y),
                                                        f32_to_tf32_rn(v1.z), f32_to_tf32_rn(v1.w)};
-                                tmem_st8(t_a + lane_base + as * kASlotCols + k0, u);
+                                tmem_st8(t_a + lane_base + as_b * kASlotCols + k0, u);
                             }
-                            tmem_wait_st();
-                            tc_fence_before_sync();
+                            if (++as_b == kASlots) { as_b = 0; aph_b ^= 1; }
+                        }
+                        tmem_wait_st();  // one wait for the whole batch of taps
+                        tc_fence_before_sync();
+                        for (int tb = 0; tb < nb; ++tb) {
                             mbar_arrive(&bars->a_full[as]);
                             if (++as == kASlots) { as = 0; aph ^= 1; }
                         }
-                        mbar_arrive(&bars->x_empty[xs]);
-                        if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
                     }
+                    mbar_arrive(&bars->x_empty[xs]);
+                    if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
+                }
             }
-        } else if (warp >= 8) {
+        }
+        __syncthreads();  // every role is done with this f-tile's sub-filters
+      }
+    } else {
+      reg_alloc<kRegsEpi>();
+      for (int ft = 0; ft < p.n_ftiles; ++ft) {
+        {
             // =========================== packers, then epilogue ===========================
-            const int e = tid - 256;  // 0..255
+            const int e = tid - 256;  // 0..511
             {
                 // stored [tap][q][c*F + f] -> smem [(tap*4+c)][q/4][f][q%4] (K-major core matrices), rounded to tf32.
-                // One item = 4 consecutive q of one (tap, c, f): 4 coalesced loads, one 16-byte shared store.
-                const int items = p.taps * 4 * KQ * Fp;
-                for (int i0 = e; i0 < items; i0 += 4 * kPackThreads) {
-                    float v[4][4];
-                    uint32_t off[4];
+                // A warp takes one (tap, c, q/4) row at a time: 4 coalesced loads and one 16-byte shared store per lane
+                // and filter; two rows (16 loads per lane) are in flight per iteration.
+                const int lane = e & 31, pw = e >> 5;
+                const int rows = p.taps * 4 * KQ;
+                for (int row0 = pw; row0 < rows; row0 += 32) {
+                    float v[2][2][4];
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const int i = i0 + u * kPackThreads;
-                        const int f = i % Fp, q4 = (i / Fp) % KQ, c = (i / (Fp * KQ)) & 3, tap = i / (Fp * KQ * 4);
-                        off[u] = (uint32_t)i << 4;  // item index == 16-byte slot index in the packed image
-                        const bool in = i < items;
-                        const float* src = w + ((size_t)(in ? tap : 0) * p.in_q + q4 * 4) * 4 * p.F + c * p.F + ft * Fp + f;
+                    for (int u = 0; u < 2; ++u) {
+                        const int row = row0 + u * 16;
+                        const int q4 = row % KQ, c = (row / KQ) & 3, tap = row / (4 * KQ);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            v[u][j] = (in && q4 * 4 + j < p.in_q) ? __ldg(src + (size_t)j * 4 * p.F) : 0.f;
+                        for (int h = 0; h < 2; ++h) {
+                            const int f = lane + h * 32;
+                            const bool in = row < rows && f < Fp;
+                            const float* src = w + ((size_t)(in ? tap : 0) * p.in_q + q4 * 4) * 4 * p.F + c * p.F + ft * Fp + f;
+#pragma unroll
+                            for (int j = 0; j < 4; ++j)
+                                v[u][h][j] = (in && q4 * 4 + j < p.in_q) ? __ldg(src + (size_t)j * 4 * p.F) : 0.f;
+                        }
                     }
 #pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (i0 + u * kPackThreads < items)
-                            *reinterpret_cast<uint4*>(w_s + off[u]) =
-                                make_uint4(f32_to_tf32_rn(v[u][0]), f32_to_tf32_rn(v[u][1]), f32_to_tf32_rn(v[u][2]),
-                                           f32_to_tf32_rn(v[u][3]));
+                    for (int u = 0; u < 2; ++u)
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            const int row = row0 + u * 16, f = lane + h * 32;
+                            if (row < rows && f < Fp)
+                                *reinterpret_cast<uint4*>(w_s + (((size_t)row * Fp + f) << 4)) =
+                                    make_uint4(f32_to_tf32_rn(v[u][h][0]), f32_to_tf32_rn(v[u][h][1]),
+                                               f32_to_tf32_rn(v[u][h][2]), f32_to_tf32_rn(v[u][h][3]));
+                        }
                 }
-                for (int i = e; i < 4 * Fp; i += kPackThreads)
+                for (int i = e; i < 4 * Fp; i += kEpiThreads)
                     bias_s[i] = p.has_bias ? __ldg(bias + (i / Fp) * p.F + ft * Fp + (i % Fp)) : 0.f;
                 fence_proxy_async_smem();  // generic-proxy writes above are read by the tensor core (async proxy)
                 mbar_arrive(&bars->w_ready);
-                asm volatile("bar.sync 3, 256;" ::: "memory");  // bias_s visible to every epilogue thread
+                named_bar_sync(9, kEpiThreads);  // bias_s visible to every epilogue thread
                 if (e == 0 && ft == 0) trace(p, kTrPacked);
             }
-            const int grp = e >> 7;        // epilogue group: 0 handles even 32-column chunks, 1 the odd ones
-            const int r = e & 127;         // accumulator row == TMEM lane
+            // 4 groups of 128 threads (one warp per TMEM lane quadrant); group g owns 32-column chunks g and g+4.
+            // Groups g and g+2 share staging tile (g & 1) and take turns on it in lock step (256-thread named barrier).
+            const int grp = e >> 7, r = e & 127;
+            const int pair = grp & 1, turn = grp >> 1;
             const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
-            const int n_pairs = (4 * Fp) >> 6;  // 32-column chunks per group
-            uint8_t* st = y_s + grp * kStagingBytes;
+            const int n_out = (4 * Fp) >> 5;  // 32-column chunks per tile: 2, 4, 6 or 8
+            uint8_t* st = y_s + pair * kStagingBytes;
             int tcount = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
                 const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
                 mbar_wait(&bars->acc_full, accph);
                 tc_fence_after_sync();
                 if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 2);
-                for (int i0 = 0; i0 < n_pairs; i0 += 2) {
-                    const bool two = i0 + 1 < n_pairs;
-                    const int c0 = (i0 * 2) + grp, c1 = c0 + 2;
-                    uint32_t v0[32], v1[32];
-                    tmem_ld32(t_acc + lane_base + c0 * 32, v0);
-                    if (two) tmem_ld32(t_acc + lane_base + c1 * 32, v1);
-                    tmem_wait_ld();
-                    if (i0 + 2 >= n_pairs) {  // this thread's share of the accumulators is in registers
-                        tc_fence_before_sync();
-                        mbar_arrive(&bars->acc_empty);
-                        if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 3);
-                    }
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        if (h == 1 && !two) break;
-                        const int c = h ? c1 : c0;
-                        const uint32_t* v = h ? v1 : v0;
-                        if (r == 0) tma_store_wait_read<0>();  // previous store of this group has read the staging tile
-                        group_bar_sync(1 + grp);
-                        const float4* bs = reinterpret_cast<const float4*>(bias_s + c * 32);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const float4 bv = bs[j];
-                            float4 o;
-                            o.x = activate<ACT>(__uint_as_float(v[4 * j + 0]) + bv.x, p.act);
-                            o.y = activate<ACT>(__uint_as_float(v[4 * j + 1]) + bv.y, p.act);
-                            o.z = activate<ACT>(__uint_as_float(v[4 * j + 2]) + bv.z, p.act);
-                            o.w = activate<ACT>(__uint_as_float(v[4 * j + 3]) + bv.w, p.act);
-                            *reinterpret_cast<float4*>(st + swz128((uint32_t)r, (uint32_t)j)) = o;
-                        }
-                        fence_proxy_async_smem();
-                        group_bar_sync(1 + grp);
-                        if (r == 0) {
-                            // accumulator column c*32 -> output channel: component (c*32)/Fp, filter ft*Fp + (c*32)%Fp
-                            const int col = c * 32;
-                            tma_store_3d(&tmy, st, (col / Fp) * p.F + ft * Fp + (col % Fp), t0, b);
-                            tma_store_commit();
-                        }
-                    }
-                }
+                // unconditional loads (clamped to a valid chunk) keep both register arrays out of local memory
+                uint32_t v0[32], v1[32];
+                tmem_ld32(t_acc + lane_base + min(grp, n_out - 1) * 32, v0);
+                tmem_ld32(t_acc + lane_base + min(grp + 4, n_out - 1) * 32, v1);
+                tmem_wait_ld();
+                tc_fence_before_sync();
+                mbar_arrive(&bars->acc_empty);  // accumulators are in registers: the next tile's MMAs may start
+                if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 3);
+                // four lock-step phases on this pair's staging tile: (turn 0, chunk set 0), (1, 0), (0, 1), (1, 1)
+                epi_phase<ACT>(v0, 0, 0, pair, turn, r, n_out, Fp, ft, t0, b, p, bias_s, st, &tmy);
+                epi_phase<ACT>(v0, 1, 0, pair, turn, r, n_out, Fp, ft, t0, b, p, bias_s, st, &tmy);
+                epi_phase<ACT>(v1, 0, 1, pair, turn, r, n_out, Fp, ft, t0, b, p, bias_s, st, &tmy);
+                epi_phase<ACT>(v1, 1, 1, pair, turn, r, n_out, Fp, ft, t0, b, p, bias_s, st, &tmy);
                 if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 4);
                 accph ^= 1;
             }
             if (r == 0) tma_store_wait_all<0>();
         }
         __syncthreads();  // every role is done with this f-tile's sub-filters
+      }
     }
 
     tc_fence_before_sync();
@@ -478,7 +554,10 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     p.pad_lo = g.pad_lo[2];
     p.in_q = g.in_q;
     p.in_q_pad = pl.in_q_pad;
+    p.flat = (g.in_q % 8 == 0) ? 1 : 0;
     p.n_chunks = (pl.in_q_pad + 31) / 32;
+    p.m8 = g.in_q / 8;
+    p.n_stages = p.flat ? g.in_q / 8 : 4 * p.n_chunks;
     p.F = g.F;
     p.f_tile = pl.f_tile;
     p.n_ftiles = pl.n_ftiles;
@@ -490,7 +569,16 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     p.w_bytes = (uint32_t)((size_t)p.taps * 4 * p.in_q_pad * p.f_tile * 4);
 
     CUtensorMap tmx, tmy;
-    {
+    if (p.flat) {
+        const uint64_t dims[3] = {(uint64_t)g.in_q * 4, (uint64_t)L, (uint64_t)g.batch};
+        const uint64_t str[2] = {(uint64_t)g.in_q * 16, (uint64_t)L * g.in_q * 16};
+        const uint32_t box[3] = {32, (uint32_t)pl.rows_in, 1};
+        int e = make_tmap_f32(&tmx, x, 3, dims, str, box, true);
+        if (e) {
+            set_error("cuTensorMapEncodeTiled(x) failed (%d)", e);
+            return QNN_E_CUDA;
+        }
+    } else {
         const uint64_t dims[4] = {(uint64_t)g.in_q, 4, (uint64_t)L, (uint64_t)g.batch};
         const uint64_t str[3] = {(uint64_t)g.in_q * 4, (uint64_t)g.in_q * 16, (uint64_t)L * g.in_q * 16};
         const uint32_t box[4] = {32, 1, (uint32_t)pl.rows_in, 1};
