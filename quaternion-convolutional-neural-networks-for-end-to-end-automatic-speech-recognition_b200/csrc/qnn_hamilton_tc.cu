@@ -7,18 +7,20 @@
 // 4 B operands (the sub-filters); the sign is the instruction descriptor's negate bit.
 //
 // One persistent CTA per SM, 768 threads, warp-specialised:
-//   warp 0       TMA producer: raw fp32 x tiles (128 rows + halo, 32 channels) -> 128B-swizzled smem ring.  When in_q is
+//   warp 17      TMA producer: raw fp32 x tiles (128 rows + halo, 32 channels) -> 128B-swizzled smem ring.  When in_q is
 //                a multiple of 8 the channel axis is walked flat (a 32-channel box may span two components, no padding);
 //                otherwise per component with the out-of-range tail zero-filled by TMA
-//   warps 4-7    converters  : smem -> registers, round-to-nearest tf32 (the tensor core would truncate), tcgen05.st into
+//   warps 20-23  converters  : smem -> registers, round-to-nearest tf32 (the tensor core would truncate), tcgen05.st into
 //                              a ring of A-operand slots in tensor memory; the tap shift is a row offset in this read;
 //                              all taps of a stage are converted as one batch (one tcgen05.wait::st per batch)
-//   warps 1,2    MMA issuers : warp 1 feeds accumulators y_r,y_i, warp 2 feeds y_j,y_k; per slot <=4 k-steps x 2 blocks,
+//   warps 18,19  MMA issuers : warp 18 feeds accumulators y_r,y_i, warp 19 feeds y_j,y_k; per slot <=4 k-steps x 2 blocks,
 //                              A from TMEM, B = sub-filter block resident in smem (K-major, no swizzle)
-//   warps 8-23   epilogue    : first pack + round the sub-filters into smem (overlapping the first x loads); per tile all
+//   warps 0-15   epilogue    : first pack + round the sub-filters into smem (overlapping the first x loads); per tile all
 //                              16 warps pull the accumulators into registers at once (TMEM is free again after two
 //                              tcgen05.ld), then +bias -> activation -> swizzled staging -> TMA store (clips ragged tiles)
-//   warp 3       owns the TMEM allocation
+//   warp 16      owns the TMEM allocation
+// The latency-critical roles sit on the HIGHEST warp ids: the SM's issue arbiter favours high warp ids, and the 16
+// epilogue warps spend most of their time polling an mbarrier (with a nanosleep back-off so they do not steal issue slots).
 // TMEM columns: [0,256) four fp32 accumulators y_r|y_i|y_j|y_k (<= 64 filters per pass), [256,512) eight 32-column A slots.
 #include <algorithm>
 #include <mutex>
@@ -32,12 +34,13 @@ using namespace ptx;
 
 constexpr int kTileM = 128;
 constexpr int kThreads = 768;
-constexpr int kEpiThreads = 512;             // warps 8..23
+constexpr int kEpiThreads = 512;             // warps 0..15
 constexpr int kASlots = 8;
 constexpr int kASlotCols = 32;
 constexpr int kAccCols = 256;
 constexpr int kMaxXStages = 4;
 constexpr int kMaxTapBatch = 4;              // taps converted per tcgen05.wait::st
+constexpr int kPackBatch = 12;               // sub-filter items (4 loads each) in flight per packer thread
 constexpr int kStagingBytes = kTileM * 128;  // one [128 x 32] fp32 store tile
 constexpr uint32_t kSmemLimit = 232448;      // 227 KB opt-in maximum per CTA
 // register budget: 768 x 80 = 61440 at launch = 128 x kRegsWg0 + 128 x kRegsWg1 + 512 x kRegsEpi
@@ -57,12 +60,15 @@ constexpr uint32_t transpose_bits(uint32_t m) {
 constexpr uint32_t kNegDense = transpose_bits(kNegConv);
 
 enum { kActLinear = 0, kActRelu = 1, kActGeneric = 2 };
+enum { kWarpAlloc = 16, kWarpProducer = 17, kWarpIssuer0 = 18, kWarpIssuer1 = 19, kWarpConv0 = 20 };
 
 // Optional per-CTA event trace (diagnostics, qnn_debug_trace): 64 clock64() slots per CTA, see tools/tc_trace.py
-constexpr int kTraceSlots = 64;
+constexpr int kTraceSlots = 256;  // 0..63 coarse events; 64.. detailed events of the CTA's second tile
 enum { kTrStart = 0, kTrSetup = 1, kTrPacked = 2, kTrFirstTma = 3, kTrTmaDone = 4, kTrFirstX = 5, kTrWReady = 6,
        kTrFirstA = 7, kTrTile0 = 8 /* + 5 * tile: acc_empty passed, acc_full committed, epilogue got acc, TMEM released,
-                                     stores issued */, kTrEnd = 58, kTrGlobalStart = 59, kTrGlobalEnd = 60, kTrSm = 61 };
+                                     stores issued */, kTrEnd = 58, kTrGlobalStart = 59, kTrGlobalEnd = 60, kTrSm = 61,
+       kTrConv = 64 /* + 8*stage: x_full passed, a_empty passed (tap 0..3), wait::st done, arrived */,
+       kTrIssue = 128 /* + 2*slot: a_full passed, committed */, kTrProd = 192 /* + 2*stage: x_empty passed, issued */ };
 
 struct TcParams {
     unsigned long long* trace;
@@ -77,6 +83,7 @@ struct TcParams {
     int rows_in, x_stages, x_stage_bytes;
     int act, has_bias;
     uint32_t w_bytes;
+    uint32_t magic_fp, magic_kq;  // floor(2^32 / d) + 1: exact n / d by __umulhi for n < 2^16
 };
 
 struct __align__(8) Barriers {
@@ -105,23 +112,32 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// k-steps (8 channels each) held by x stage s
-__device__ __forceinline__ int stage_ksteps(const TcParams& p, int s) {
-    if (p.flat) return 4;
-    const int ch = s % p.n_chunks;
-    return min(32, p.in_q_pad - ch * 32) >> 3;
-}
-// input component and first quaternion channel of k-step ks of stage s
-__device__ __forceinline__ void kstep_coords(const TcParams& p, int s, int ks, int& a, int& q0) {
-    if (p.flat) {
-        const int kk = s * 4 + ks;
-        a = kk / p.m8;
-        q0 = (kk - a * p.m8) << 3;
-    } else {
-        a = s / p.n_chunks;
-        q0 = (s % p.n_chunks) * 32 + ks * 8;
+// Walks the x stages of a tile without integer division: for every stage the number of k-steps (8 channels each)
+// and, per k-step, the input component `a` and the first quaternion channel `q0` it covers.
+struct StageWalker {
+    int a, j;  // flat: component and k-step index inside it;  padded: component and 32-channel chunk inside it
+    __device__ __forceinline__ void reset() { a = 0; j = 0; }
+    // fills ka/kq for the current stage, returns its k-step count and advances to the next stage
+    __device__ __forceinline__ int next(const TcParams& p, int (&ka)[4], int (&kq)[4]) {
+        if (p.flat) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks) {
+                ka[ks] = a;
+                kq[ks] = j << 3;
+                if (++j == p.m8) { j = 0; ++a; }
+            }
+            return 4;
+        }
+        const int nks = min(32, p.in_q_pad - j * 32) >> 3;
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks) {
+            ka[ks] = a;
+            kq[ks] = j * 32 + ks * 8;
+        }
+        if (++j == p.n_chunks) { j = 0; ++a; }
+        return nks;
     }
-}
+};
 
 // D[tmem] (+)= A[tmem] * B[smem]; descriptor passed as two 32-bit halves
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
@@ -201,7 +217,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
     const int Fp = p.f_tile, KQ = p.in_q_pad >> 2;
 
-    if (tid == 0) {
+    if (tid == kWarpProducer * 32) {
         trace(p, kTrStart);
         if (p.trace) {
             p.trace[(size_t)blockIdx.x * kTraceSlots + kTrGlobalStart] = globaltimer_ns();
@@ -224,7 +240,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         mbar_init(&bars->w_ready, kEpiThreads);
         fence_mbar_init();
     }
-    if (warp == 3) {
+    if (warp == kWarpAlloc) {
         tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
@@ -233,7 +249,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     tc_fence_after_sync();
     const uint32_t t_acc = bars->tmem_base;
     const uint32_t t_a = t_acc + kAccCols;
-    if (tid == 0) trace(p, kTrSetup);
+    if (tid == kWarpProducer * 32) trace(p, kTrSetup);
 
     // pipeline state persists across tiles and f-tile passes
     uint32_t xs = 0, xph = 0, as = 0, aph = 0, accph = 0;
@@ -242,34 +258,39 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     // thread and grow to 104; the producer / issuer / converter warpgroups (0, 1) shrink to 32.
     // (setmaxnreg sits INSIDE each role branch: ptxas takes the minimum of the values that reach a join point.)
 
-    if (warp < 4) {
+    if (warp >= kWarpAlloc && warp < kWarpConv0) {
       reg_dealloc<kRegsWg0>();
       for (int ft = 0; ft < p.n_ftiles; ++ft) {
-        if (warp == 0) {
+        if (warp == kWarpProducer) {
             // =========================== TMA producer ===========================
             if (elect_one()) {
                 bool first = ft == 0;
                 for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                     const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
+                    const bool detail = ft == 0 && tile == (int)(blockIdx.x + gridDim.x);
+                    int pa = 0, pch = 0;  // padded mode: component / chunk of the current stage
                     for (int s = 0; s < p.n_stages; ++s) {
                         mbar_wait(&bars->x_empty[xs], xph ^ 1);
+                        if (detail && s < 16) trace(p, kTrProd + 2 * s);
                         mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)p.rows_in * 128u);
                         uint8_t* dst = x_s + (size_t)xs * p.x_stage_bytes;
                         if (p.flat)
                             tma_load_3d(dst, &tmx, &bars->x_full[xs], s * 32, t0 - p.pad_lo, b);
-                        else
-                            tma_load_4d(dst, &tmx, &bars->x_full[xs], (s % p.n_chunks) * 32, s / p.n_chunks,
-                                        t0 - p.pad_lo, b);
+                        else {
+                            tma_load_4d(dst, &tmx, &bars->x_full[xs], pch * 32, pa, t0 - p.pad_lo, b);
+                            if (++pch == p.n_chunks) { pch = 0; ++pa; }
+                        }
                         if (first) { trace(p, kTrFirstTma); first = false; }
+                        if (detail && s < 16) trace(p, kTrProd + 2 * s + 1);
                         if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
                     }
                 }
                 trace(p, kTrTmaDone);
             }
-        } else if (warp == 1 || warp == 2) {
+        } else if (warp == kWarpIssuer0 || warp == kWarpIssuer1) {
             // =========================== MMA issuers (whole warp runs the loops, one lane issues) ===========================
             const bool elected = elect_one();
-            const int b0 = warp == 1 ? 0 : 2;  // this issuer's two output components
+            const int b0 = warp == kWarpIssuer0 ? 0 : 2;  // this issuer's two output components
             const uint32_t idesc_pos = idesc_tf32(kTileM, Fp, false, false);
             const uint32_t idesc_neg = idesc_tf32(kTileM, Fp, false, true);
             const uint64_t d0 = smem_desc_kmajor_noswz(smem_u32(w_s), (uint32_t)Fp * 16u, 128);
@@ -278,26 +299,33 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             const uint32_t tap_stride = 4u * sub_stride;
             constexpr uint32_t neg_table = CONJ ? kNegDense : kNegConv;
             mbar_wait(&bars->w_ready, ft & 1);  // this pass' sub-filters are packed and visible to the async proxy
-            if (warp == 1 && elected && ft == 0) trace(p, kTrWReady);
+            if (warp == kWarpIssuer0 && elected && ft == 0) trace(p, kTrWReady);
             int tcount = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
                 mbar_wait(&bars->acc_empty, accph ^ 1);
                 tc_fence_after_sync();
-                if (warp == 1 && elected && ft == 0) trace(p, kTrTile0 + 5 * tcount);
+                if (warp == kWarpIssuer0 && elected && ft == 0) trace(p, kTrTile0 + 5 * tcount);
                 uint32_t accumulate = 0;
+                const bool detail = warp == kWarpIssuer0 && elected && ft == 0 && tcount == 1;
+                int slot_i = 0;
+                StageWalker walk;
+                walk.reset();
                 for (int s = 0; s < p.n_stages; ++s) {
-                    const int nks = stage_ksteps(p, s);
-                    for (int tap = 0; tap < p.taps; ++tap) {
+                    int ka[4], kq[4];
+                    const int nks = walk.next(p, ka, kq);
+                    for (int tap = 0; tap < p.taps; ++tap, ++slot_i) {
                         mbar_wait(&bars->a_full[as], aph);
                         tc_fence_after_sync();
+                        if (detail && slot_i < 32) trace(p, kTrIssue + 2 * slot_i);
                         if (elected) {
-                            if (warp == 1 && ft == 0 && tcount == 0 && s == 0 && tap == 0) trace(p, kTrFirstA);
+                            if (warp == kWarpIssuer0 && ft == 0 && tcount == 0 && s == 0 && tap == 0) trace(p, kTrFirstA);
                             const uint32_t a_col = t_a + as * kASlotCols;
                             const uint32_t tap_lo = w_lo + tap * tap_stride;
-                            for (int ks = 0; ks < nks; ++ks) {
-                                int a, q0;
-                                kstep_coords(p, s, ks, a, q0);
-                                const uint32_t k_lo = tap_lo + (uint32_t)(q0 >> 2) * Fp;
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {
+                                if (ks >= nks) break;
+                                const int a = ka[ks];
+                                const uint32_t k_lo = tap_lo + (uint32_t)(kq[ks] >> 2) * Fp;
 #pragma unroll
                                 for (int bb = 0; bb < 2; ++bb) {
                                     const int b = b0 + bb;
@@ -308,30 +336,38 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                                 accumulate = 1;
                             }
                             mma_commit(&bars->a_empty[as]);  // one of the two arrivals that free the slot
+                            if (detail && slot_i < 32) trace(p, kTrIssue + 2 * slot_i + 1);
                         }
                         __syncwarp();
                         if (++as == kASlots) { as = 0; aph ^= 1; }
                     }
                 }
                 if (elected) mma_commit(&bars->acc_full);
-                if (warp == 1 && elected && ft == 0) trace(p, kTrTile0 + 5 * tcount + 1);
+                if (warp == kWarpIssuer0 && elected && ft == 0) trace(p, kTrTile0 + 5 * tcount + 1);
                 __syncwarp();
                 accph ^= 1;
             }
         }
         __syncthreads();  // every role is done with this f-tile's sub-filters
       }
-    } else if (warp < 8) {
+    } else if (warp >= kWarpConv0) {
       reg_dealloc<kRegsWg1>();
       for (int ft = 0; ft < p.n_ftiles; ++ft) {
         {
             // =========================== converters: smem fp32 -> tf32(rn) -> TMEM A slots ===========================
-            const int r = tid - 128;
+            const int r = tid - kWarpConv0 * 32;
             const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+                const bool detail = r == 0 && ft == 0 && tile == (int)(blockIdx.x + gridDim.x);
+                int cch = 0;  // padded mode: chunk inside the component
                 for (int s = 0; s < p.n_stages; ++s) {
-                    const int kc = stage_ksteps(p, s) << 3;
+                    int kc = 32;
+                    if (!p.flat) {
+                        kc = min(32, p.in_q_pad - cch * 32);
+                        if (++cch == p.n_chunks) cch = 0;
+                    }
                     mbar_wait(&bars->x_full[xs], xph);
+                    if (detail && s < 8) trace(p, kTrConv + 8 * s);
                     if (r == 0 && s == 0 && tile == (int)blockIdx.x && ft == 0) trace(p, kTrFirstX);
                     const uint8_t* xb = x_s + (size_t)xs * p.x_stage_bytes;
                     for (int tap0 = 0; tap0 < p.taps; tap0 += kMaxTapBatch) {
@@ -341,6 +377,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                             const uint32_t row = (uint32_t)(r + (tap0 + tb) * p.dil);
                             mbar_wait(&bars->a_empty[as_b], aph_b ^ 1);
                             tc_fence_after_sync();
+                            if (detail && s < 8 && tap0 == 0) trace(p, kTrConv + 8 * s + 1 + tb);
                             for (int k0 = 0; k0 < kc; k0 += 8) {
                                 const float4 v0 = *reinterpret_cast<const float4*>(xb + swz128(row, k0 >> 2));
                                 const float4 v1 = *reinterpret_cast<const float4*>(xb + swz128(row, (k0 >> 2) + 1));
@@ -352,11 +389,13 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                             if (++as_b == kASlots) { as_b = 0; aph_b ^= 1; }
                         }
                         tmem_wait_st();  // one wait for the whole batch of taps
+                        if (detail && s < 8 && tap0 == 0) trace(p, kTrConv + 8 * s + 5);
                         tc_fence_before_sync();
                         for (int tb = 0; tb < nb; ++tb) {
                             mbar_arrive(&bars->a_full[as]);
                             if (++as == kASlots) { as = 0; aph ^= 1; }
                         }
+                        if (detail && s < 8 && tap0 == 0) trace(p, kTrConv + 8 * s + 6);
                     }
                     mbar_arrive(&bars->x_empty[xs]);
                     if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
@@ -370,39 +409,37 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
       for (int ft = 0; ft < p.n_ftiles; ++ft) {
         {
             // =========================== packers, then epilogue ===========================
-            const int e = tid - 256;  // 0..511
+            const int e = tid;  // 0..511
             {
                 // stored [tap][q][c*F + f] -> smem [(tap*4+c)][q/4][f][q%4] (K-major core matrices), rounded to tf32.
-                // A warp takes one (tap, c, q/4) row at a time: 4 coalesced loads and one 16-byte shared store per lane
-                // and filter; two rows (16 loads per lane) are in flight per iteration.
-                const int lane = e & 31, pw = e >> 5;
-                const int rows = p.taps * 4 * KQ;
-                for (int row0 = pw; row0 < rows; row0 += 32) {
-                    float v[2][2][4];
+                // One item = the 4 consecutive q of one (tap, c, q/4, f): four coalesced 4-byte loads, one 16-byte shared
+                // store; item index == 16-byte slot index of the packed image.  All loads of a pass (up to 48 per
+                // thread) are issued before the first use, so a pass costs one memory round trip.
+                const int items = p.taps * 4 * KQ * Fp;
+                for (int base = 0; base < items; base += kEpiThreads * kPackBatch) {
+                    float v[kPackBatch][4];
 #pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int row = row0 + u * 16;
-                        const int q4 = row % KQ, c = (row / KQ) & 3, tap = row / (4 * KQ);
+                    for (int u = 0; u < kPackBatch; ++u) {
+                        const int i = base + e + u * kEpiThreads;
+                        const bool in = i < items;
+                        const uint32_t rowi = __umulhi((uint32_t)i, p.magic_fp);        // i / Fp
+                        const uint32_t f = (uint32_t)i - rowi * Fp;
+                        const uint32_t tc = __umulhi(rowi, p.magic_kq);                 // rowi / KQ = tap * 4 + c
+                        const uint32_t q4 = rowi - tc * KQ;
+                        const float* src = w + ((size_t)(in ? (tc >> 2) : 0) * p.in_q + q4 * 4) * 4 * p.F + (tc & 3) * p.F +
+                                           ft * Fp + f;
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int f = lane + h * 32;
-                            const bool in = row < rows && f < Fp;
-                            const float* src = w + ((size_t)(in ? tap : 0) * p.in_q + q4 * 4) * 4 * p.F + c * p.F + ft * Fp + f;
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                v[u][h][j] = (in && q4 * 4 + j < p.in_q) ? __ldg(src + (size_t)j * 4 * p.F) : 0.f;
-                        }
+                        for (int j = 0; j < 4; ++j)
+                            v[u][j] = (in && (int)(q4 * 4 + j) < p.in_q) ? __ldg(src + (size_t)j * 4 * p.F) : 0.f;
                     }
 #pragma unroll
-                    for (int u = 0; u < 2; ++u)
-#pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            const int row = row0 + u * 16, f = lane + h * 32;
-                            if (row < rows && f < Fp)
-                                *reinterpret_cast<uint4*>(w_s + (((size_t)row * Fp + f) << 4)) =
-                                    make_uint4(f32_to_tf32_rn(v[u][h][0]), f32_to_tf32_rn(v[u][h][1]),
-                                               f32_to_tf32_rn(v[u][h][2]), f32_to_tf32_rn(v[u][h][3]));
-                        }
+                    for (int u = 0; u < kPackBatch; ++u) {
+                        const int i = base + e + u * kEpiThreads;
+                        if (i < items)
+                            *reinterpret_cast<uint4*>(w_s + ((size_t)i << 4)) =
+                                make_uint4(f32_to_tf32_rn(v[u][0]), f32_to_tf32_rn(v[u][1]), f32_to_tf32_rn(v[u][2]),
+                                           f32_to_tf32_rn(v[u][3]));
+                    }
                 }
                 for (int i = e; i < 4 * Fp; i += kEpiThreads)
                     bias_s[i] = p.has_bias ? __ldg(bias + (i / Fp) * p.F + ft * Fp + (i % Fp)) : 0.f;
@@ -421,7 +458,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             int tcount = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
                 const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
-                mbar_wait(&bars->acc_full, accph);
+                mbar_wait_sleep(&bars->acc_full, accph);  // long wait: back off, leave the issue slots to the other roles
                 tc_fence_after_sync();
                 if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 2);
                 // unconditional loads (clamped to a valid chunk) keep both register arrays out of local memory
@@ -448,8 +485,8 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
 
     tc_fence_before_sync();
     __syncthreads();
-    if (warp == 3) tmem_dealloc(t_acc, 512);
-    if (tid == 0) {
+    if (warp == kWarpAlloc) tmem_dealloc(t_acc, 512);
+    if (tid == kWarpProducer * 32) {
         trace(p, kTrEnd);
         if (p.trace) p.trace[(size_t)blockIdx.x * kTraceSlots + kTrGlobalEnd] = globaltimer_ns();
     }
@@ -567,6 +604,8 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     p.act = g.act;
     p.has_bias = bias != nullptr;
     p.w_bytes = (uint32_t)((size_t)p.taps * 4 * p.in_q_pad * p.f_tile * 4);
+    p.magic_fp = (uint32_t)((1ull << 32) / (uint32_t)p.f_tile) + 1;
+    p.magic_kq = (uint32_t)((1ull << 32) / (uint32_t)(p.in_q_pad / 4)) + 1;
 
     CUtensorMap tmx, tmy;
     if (p.flat) {
