@@ -142,7 +142,8 @@ int run_forward(const Geom& g, int rank, int math, int algo, const float* x, con
         }
         return general_forward(g, x, w, bias, y, st);
     }
-    const bool aligned = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+    const bool aligned =
+        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) == 0;
     if (algo == QNN_ALGO_TENSOR) return tc_forward(g, rank, x, w, bias, y, st);
     if (algo != QNN_ALGO_AUTO) {
         set_error("unknown algo %d", algo);
@@ -175,10 +176,32 @@ Scratch g_scratch;
 
 size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
+// Copy engines run next to the SMs and PCIe is full duplex: the units (samples for a convolution, rows for a dense
+// layer) are cut into chunks and pipelined over three streams -- H2D of chunk i+1, kernel of chunk i and D2H of chunk
+// i-1 overlap -- so the call costs about max(H2D, D2H) instead of their sum.
+struct HostPipe {
+    cudaStream_t in = nullptr, out = nullptr;
+    cudaEvent_t ev_in[16] = {}, ev_k[16] = {}, ev_start = nullptr;
+    bool ok = false;
+    bool init() {
+        if (ok) return true;
+        if (cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking) != cudaSuccess) return false;
+        if (cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking) != cudaSuccess) return false;
+        for (int i = 0; i < 16; ++i) {
+            if (cudaEventCreateWithFlags(&ev_in[i], cudaEventDisableTiming) != cudaSuccess) return false;
+            if (cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming) != cudaSuccess) return false;
+        }
+        if (cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming) != cudaSuccess) return false;
+        ok = true;
+        return true;
+    }
+};
+HostPipe g_pipe;
+
 int forward_host(const Geom& g, int rank, int math, int algo, size_t nx, size_t nw, size_t nb, size_t ny,
                  const float* xh, const float* wh, const float* bh, float* yh, cudaStream_t st) {
+    if (ny == 0) return QNN_OK;
     if (!xh || !wh || !yh) {
-        if (ny == 0) return QNN_OK;
         set_error("host x, kernel and y must not be NULL");
         return QNN_E_INVALID;
     }
@@ -189,13 +212,47 @@ int forward_host(const Geom& g, int rank, int math, int algo, size_t nx, size_t 
     char* base = static_cast<char*>(g_scratch.ptr);
     float *xd = (float*)(base + ox), *wd = (float*)(base + ow), *bd = bh ? (float*)(base + ob) : nullptr,
           *yd = (float*)(base + oy);
+    // units that can be cut independently: samples (conv) or rows (dense: batch == 1, rows live in in_sp[2])
+    const bool dense = g.conj_w && g.batch == 1 && g.k[2] == 1;
+    const long long units = dense ? g.in_sp[2] : g.batch;
+    const size_t x_unit = nx / (size_t)units, y_unit = ny / (size_t)units;
+    int chunks = 1;
+    if ((nx + ny) * 4 >= (size_t)8 << 20 && units >= 8 && g_pipe.init()) chunks = units >= 64 ? 8 : 4;
     cudaError_t e;
-    if ((e = cudaMemcpyAsync(xd, xh, nx * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) goto fail;
     if ((e = cudaMemcpyAsync(wd, wh, nw * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) goto fail;
     if (bh && (e = cudaMemcpyAsync(bd, bh, nb * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) goto fail;
-    rc = run_forward(g, rank, math, algo, xd, wd, bd, yd, st);
-    if (rc) return rc;
-    if ((e = cudaMemcpyAsync(yh, yd, ny * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto fail;
+    if (chunks == 1) {
+        if ((e = cudaMemcpyAsync(xd, xh, nx * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) goto fail;
+        rc = run_forward(g, rank, math, algo, xd, wd, bd, yd, st);
+        if (rc) return rc;
+        if ((e = cudaMemcpyAsync(yh, yd, ny * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto fail;
+        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) goto fail;
+        return QNN_OK;
+    }
+    // the copy streams must not run ahead of work already queued on the caller's stream (scratch reuse)
+    if ((e = cudaEventRecord(g_pipe.ev_start, st)) != cudaSuccess) goto fail;
+    if ((e = cudaStreamWaitEvent(g_pipe.in, g_pipe.ev_start, 0)) != cudaSuccess) goto fail;
+    if ((e = cudaStreamWaitEvent(g_pipe.out, g_pipe.ev_start, 0)) != cudaSuccess) goto fail;
+    for (int c = 0; c < chunks; ++c) {
+        const long long u0 = units * c / chunks, u1 = units * (c + 1) / chunks;
+        if (u1 == u0) continue;
+        Geom gc = g;
+        if (dense)
+            gc.in_sp[2] = gc.out_sp[2] = (int)(u1 - u0);
+        else
+            gc.batch = (int)(u1 - u0);
+        if ((e = cudaMemcpyAsync(xd + u0 * x_unit, xh + u0 * x_unit, (size_t)(u1 - u0) * x_unit * 4,
+                                 cudaMemcpyHostToDevice, g_pipe.in)) != cudaSuccess) goto fail;
+        if ((e = cudaEventRecord(g_pipe.ev_in[c], g_pipe.in)) != cudaSuccess) goto fail;
+        if ((e = cudaStreamWaitEvent(st, g_pipe.ev_in[c], 0)) != cudaSuccess) goto fail;
+        rc = run_forward(gc, rank, math, algo, xd + u0 * x_unit, wd, bd, yd + u0 * y_unit, st);
+        if (rc) return rc;
+        if ((e = cudaEventRecord(g_pipe.ev_k[c], st)) != cudaSuccess) goto fail;
+        if ((e = cudaStreamWaitEvent(g_pipe.out, g_pipe.ev_k[c], 0)) != cudaSuccess) goto fail;
+        if ((e = cudaMemcpyAsync(yh + u0 * y_unit, yd + u0 * y_unit, (size_t)(u1 - u0) * y_unit * 4,
+                                 cudaMemcpyDeviceToHost, g_pipe.out)) != cudaSuccess) goto fail;
+    }
+    if ((e = cudaStreamSynchronize(g_pipe.out)) != cudaSuccess) goto fail;
     if ((e = cudaStreamSynchronize(st)) != cudaSuccess) goto fail;
     return QNN_OK;
 fail:

@@ -6,11 +6,11 @@
 // exists: the 16 signed blocks are 16 tcgen05.mma instructions that share 4 A operands (the input components) and
 // 4 B operands (the sub-filters); the sign is the instruction descriptor's negate bit.
 //
-// One persistent CTA per SM, 768 threads, warp-specialised:
+// One persistent CTA per SM, 896 threads, warp-specialised:
 //   warp 17      TMA producer: raw fp32 x tiles (128 rows + halo, 32 channels) -> 128B-swizzled smem ring.  When in_q is
 //                a multiple of 8 the channel axis is walked flat (a 32-channel box may span two components, no padding);
 //                otherwise per component with the out-of-range tail zero-filled by TMA
-//   warps 20-23  converters  : smem -> registers, round-to-nearest tf32 (the tensor core would truncate), tcgen05.st into
+//   warps 20-27  converters  : two groups of four warps that take alternate x stages; smem -> registers, round-to-nearest tf32 (the tensor core would truncate), tcgen05.st into
 //                              a ring of A-operand slots in tensor memory; the tap shift is a row offset in this read;
 //                              all taps of a stage are converted as one batch (one tcgen05.wait::st per batch)
 //   warps 18,19  MMA issuers : warp 18 feeds accumulators y_r,y_i, warp 19 feeds y_j,y_k; per slot <=4 k-steps x 2 blocks,
@@ -33,19 +33,19 @@ namespace {
 using namespace ptx;
 
 constexpr int kTileM = 128;
-constexpr int kThreads = 768;
+constexpr int kThreads = 896;
 constexpr int kEpiThreads = 512;             // warps 0..15
 constexpr int kASlots = 8;
 constexpr int kASlotCols = 32;
 constexpr int kAccCols = 256;
 constexpr int kMaxXStages = 4;
 constexpr int kMaxTapBatch = 4;              // taps converted per tcgen05.wait::st
-constexpr int kPackBatch = 12;               // sub-filter items (4 loads each) in flight per packer thread
+constexpr int kPackBatch = 4;                // 4x4 sub-filter blocks (4 x 16-byte loads each) in flight per packer thread
 constexpr int kStagingBytes = kTileM * 128;  // one [128 x 32] fp32 store tile
 constexpr uint32_t kSmemLimit = 232448;      // 227 KB opt-in maximum per CTA
-// register budget: 768 x 80 = 61440 at launch = 128 x kRegsWg0 + 128 x kRegsWg1 + 512 x kRegsEpi
-constexpr int kRegsWg0 = 32, kRegsWg1 = 32, kRegsEpi = 104;
-static_assert(128 * kRegsWg0 + 128 * kRegsWg1 + 512 * kRegsEpi <= 768 * 80, "register pool");
+// register budget: 896 x 72 = 64512 at launch = 128 x kRegsWg0 + 256 x kRegsWg1 + 512 x kRegsEpi
+constexpr int kRegsWg0 = 40, kRegsWg1 = 40, kRegsEpi = 96;
+static_assert(128 * kRegsWg0 + 256 * kRegsWg1 + 512 * kRegsEpi <= 896 * 72, "register pool");
 
 // bit (a*4+b) set when block (input component a -> output component b) enters negated: conv table, SURVEY 3.2.
 // The dense layer uses the transposed table (bit b*4+a), SURVEY 3.3.
@@ -83,7 +83,7 @@ struct TcParams {
     int rows_in, x_stages, x_stage_bytes;
     int act, has_bias;
     uint32_t w_bytes;
-    uint32_t magic_fp, magic_kq;  // floor(2^32 / d) + 1: exact n / d by __umulhi for n < 2^16
+    uint32_t magic_f4, magic_kq;  // floor(2^32 / d) + 1: exact n / d by __umulhi for n < 2^16
 };
 
 struct __align__(8) Barriers {
@@ -254,8 +254,8 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     // pipeline state persists across tiles and f-tile passes
     uint32_t xs = 0, xph = 0, as = 0, aph = 0, accph = 0;
 
-    // 768 threads x 80 registers are granted at launch.  The epilogue warpgroups (2..5) hold 64 accumulator values per
-    // thread and grow to 104; the producer / issuer / converter warpgroups (0, 1) shrink to 32.
+    // 896 threads x 72 registers are granted at launch.  The epilogue warpgroups hold 64 accumulator values per thread
+    // and grow to 96; the producer / issuer / converter warpgroups shrink to 40.
     // (setmaxnreg sits INSIDE each role branch: ptxas takes the minimum of the values that reach a join point.)
 
     if (warp >= kWarpAlloc && warp < kWarpConv0) {
@@ -355,20 +355,31 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
       for (int ft = 0; ft < p.n_ftiles; ++ft) {
         {
             // =========================== converters: smem fp32 -> tf32(rn) -> TMEM A slots ===========================
-            const int r = tid - kWarpConv0 * 32;
+            // Two groups of 128 threads take alternate x stages, so one group's tcgen05.wait::st overlaps the other's
+            // loads.  Rounding to nearest tf32 is "add half an ulp, let the tensor core truncate": one integer add per
+            // element (an infinite input becomes NaN; finite inputs round exactly like cvt.rna).
+            const int cgrp = (tid - kWarpConv0 * 32) >> 7;
+            const int r = (tid - kWarpConv0 * 32) & 127;
             const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
+            uint32_t gs = 0;  // running stage counter: stage parity selects the group
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 const bool detail = r == 0 && ft == 0 && tile == (int)(blockIdx.x + gridDim.x);
                 int cch = 0;  // padded mode: chunk inside the component
-                for (int s = 0; s < p.n_stages; ++s) {
+                for (int s = 0; s < p.n_stages; ++s, ++gs) {
                     int kc = 32;
                     if (!p.flat) {
                         kc = min(32, p.in_q_pad - cch * 32);
                         if (++cch == p.n_chunks) cch = 0;
                     }
+                    if ((int)(gs & 1) != cgrp) {  // the other group's stage: just advance the ring positions
+                        if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
+                        as += p.taps;
+                        while (as >= kASlots) { as -= kASlots; aph ^= 1; }
+                        continue;
+                    }
                     mbar_wait(&bars->x_full[xs], xph);
                     if (detail && s < 8) trace(p, kTrConv + 8 * s);
-                    if (r == 0 && s == 0 && tile == (int)blockIdx.x && ft == 0) trace(p, kTrFirstX);
+                    if (r == 0 && cgrp == 0 && s == 0 && tile == (int)blockIdx.x && ft == 0) trace(p, kTrFirstX);
                     const uint8_t* xb = x_s + (size_t)xs * p.x_stage_bytes;
                     for (int tap0 = 0; tap0 < p.taps; tap0 += kMaxTapBatch) {
                         const int nb = min(kMaxTapBatch, p.taps - tap0);
@@ -379,11 +390,10 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                             tc_fence_after_sync();
                             if (detail && s < 8 && tap0 == 0) trace(p, kTrConv + 8 * s + 1 + tb);
                             for (int k0 = 0; k0 < kc; k0 += 8) {
-                                const float4 v0 = *reinterpret_cast<const float4*>(xb + swz128(row, k0 >> 2));
-                                const float4 v1 = *reinterpret_cast<const float4*>(xb + swz128(row, (k0 >> 2) + 1));
-                                const uint32_t u[8] = {f32_to_tf32_rn(v0.x), f32_to_tf32_rn(v0.y), f32_to_tf32_rn(v0.z),
-                                                       f32_to_tf32_rn(v0.w), f32_to_tf32_rn(v1.x), f32_to_tf32_rn(v1.y),
-                                                       f32_to_tf32_rn(v1.z), f32_to_tf32_rn(v1.w)};
+                                const uint4 v0 = *reinterpret_cast<const uint4*>(xb + swz128(row, k0 >> 2));
+                                const uint4 v1 = *reinterpret_cast<const uint4*>(xb + swz128(row, (k0 >> 2) + 1));
+                                const uint32_t u[8] = {v0.x + 0x1000u, v0.y + 0x1000u, v0.z + 0x1000u, v0.w + 0x1000u,
+                                                       v1.x + 0x1000u, v1.y + 0x1000u, v1.z + 0x1000u, v1.w + 0x1000u};
                                 tmem_st8(t_a + lane_base + as_b * kASlotCols + k0, u);
                             }
                             if (++as_b == kASlots) { as_b = 0; aph_b ^= 1; }
@@ -412,33 +422,43 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             const int e = tid;  // 0..511
             {
                 // stored [tap][q][c*F + f] -> smem [(tap*4+c)][q/4][f][q%4] (K-major core matrices), rounded to tf32.
-                // One item = the 4 consecutive q of one (tap, c, q/4, f): four coalesced 4-byte loads, one 16-byte shared
-                // store; item index == 16-byte slot index of the packed image.  All loads of a pass (up to 48 per
-                // thread) are issued before the first use, so a pass costs one memory round trip.
-                const int items = p.taps * 4 * KQ * Fp;
-                for (int base = 0; base < items; base += kEpiThreads * kPackBatch) {
-                    float v[kPackBatch][4];
+                // A thread takes 4 (q) x 4 (f) blocks: four 16-byte loads (one per q row, coalesced along f), a register
+                // transpose, four 16-byte shared stores (one per f).  All loads of a pass (up to 16 per thread) are
+                // issued before the first use, so a pass costs one memory round trip.
+                const int nf4 = Fp >> 2;
+                const int blocks = p.taps * 4 * KQ * nf4;
+                for (int base = 0; base < blocks; base += kEpiThreads * kPackBatch) {
+                    float4 m[kPackBatch][4];
 #pragma unroll
                     for (int u = 0; u < kPackBatch; ++u) {
-                        const int i = base + e + u * kEpiThreads;
-                        const bool in = i < items;
-                        const uint32_t rowi = __umulhi((uint32_t)i, p.magic_fp);        // i / Fp
-                        const uint32_t f = (uint32_t)i - rowi * Fp;
+                        const int bi = base + e + u * kEpiThreads;
+                        const bool in = bi < blocks;
+                        const uint32_t rowi = __umulhi((uint32_t)bi, p.magic_f4);       // bi / nf4 = (tap*4+c)*KQ + q4
+                        const uint32_t f4 = (uint32_t)bi - rowi * nf4;
                         const uint32_t tc = __umulhi(rowi, p.magic_kq);                 // rowi / KQ = tap * 4 + c
                         const uint32_t q4 = rowi - tc * KQ;
                         const float* src = w + ((size_t)(in ? (tc >> 2) : 0) * p.in_q + q4 * 4) * 4 * p.F + (tc & 3) * p.F +
-                                           ft * Fp + f;
+                                           ft * Fp + f4 * 4;
 #pragma unroll
                         for (int j = 0; j < 4; ++j)
-                            v[u][j] = (in && (int)(q4 * 4 + j) < p.in_q) ? __ldg(src + (size_t)j * 4 * p.F) : 0.f;
+                            m[u][j] = (in && (int)(q4 * 4 + j) < p.in_q)
+                                          ? __ldg(reinterpret_cast<const float4*>(src + (size_t)j * 4 * p.F))
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
                     }
 #pragma unroll
                     for (int u = 0; u < kPackBatch; ++u) {
-                        const int i = base + e + u * kEpiThreads;
-                        if (i < items)
-                            *reinterpret_cast<uint4*>(w_s + ((size_t)i << 4)) =
-                                make_uint4(f32_to_tf32_rn(v[u][0]), f32_to_tf32_rn(v[u][1]), f32_to_tf32_rn(v[u][2]),
-                                           f32_to_tf32_rn(v[u][3]));
+                        const int bi = base + e + u * kEpiThreads;
+                        if (bi < blocks) {
+                            uint4* dst = reinterpret_cast<uint4*>(w_s + ((size_t)bi << 6));  // 4 consecutive 16-byte slots
+                            dst[0] = make_uint4(f32_to_tf32_rn(m[u][0].x), f32_to_tf32_rn(m[u][1].x),
+                                                f32_to_tf32_rn(m[u][2].x), f32_to_tf32_rn(m[u][3].x));
+                            dst[1] = make_uint4(f32_to_tf32_rn(m[u][0].y), f32_to_tf32_rn(m[u][1].y),
+                                                f32_to_tf32_rn(m[u][2].y), f32_to_tf32_rn(m[u][3].y));
+                            dst[2] = make_uint4(f32_to_tf32_rn(m[u][0].z), f32_to_tf32_rn(m[u][1].z),
+                                                f32_to_tf32_rn(m[u][2].z), f32_to_tf32_rn(m[u][3].z));
+                            dst[3] = make_uint4(f32_to_tf32_rn(m[u][0].w), f32_to_tf32_rn(m[u][1].w),
+                                                f32_to_tf32_rn(m[u][2].w), f32_to_tf32_rn(m[u][3].w));
+                        }
                     }
                 }
                 for (int i = e; i < 4 * Fp; i += kEpiThreads)
@@ -573,8 +593,8 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
         set_error("tensor-core kernel does not take this shape: %s", pl.why);
         return QNN_E_UNSUPPORTED;
     }
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) {
-        set_error("tensor-core kernel needs 16-byte aligned x and y");
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) {
+        set_error("tensor-core kernel needs 16-byte aligned x, kernel and y");
         return QNN_E_UNSUPPORTED;
     }
     const int L = g.in_sp[2], Lo = g.out_sp[2];
@@ -604,7 +624,7 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     p.act = g.act;
     p.has_bias = bias != nullptr;
     p.w_bytes = (uint32_t)((size_t)p.taps * 4 * p.in_q_pad * p.f_tile * 4);
-    p.magic_fp = (uint32_t)((1ull << 32) / (uint32_t)p.f_tile) + 1;
+    p.magic_f4 = (uint32_t)((1ull << 32) / (uint32_t)(p.f_tile / 4)) + 1;
     p.magic_kq = (uint32_t)((1ull << 32) / (uint32_t)(p.in_q_pad / 4)) + 1;
 
     CUtensorMap tmx, tmy;
