@@ -8,6 +8,7 @@
 //   6  TMA 4-D load, 128-B swizzle, box wider than the tensor and negative start row (zero fill), thread un-swizzle
 //   7  TMA 3-D store from a swizzled staging tile with clipping at the tensor edge
 //   8  as 1 with N = 32 and N = 16
+//   9  tensor-pipe rate: cycles per tf32 MMA for N = 32/64/128/256, A from TMEM or smem, 1 or 4 accumulators, 1 or 2 issuers
 #define QNN_SPIN_LIMIT 20000000
 #include <cstdio>
 #include <cstdlib>
@@ -210,6 +211,51 @@ __global__ void __launch_bounds__(128) k_tma_store(const __grid_constant__ CUten
     }
 }
 
+// Issues `reps` MMAs (K = 8 each) from one or two threads and reports the SM cycles from first issue to completion.
+__global__ void __launch_bounds__(128) k_rate(int N, int a_in_tmem, int n_acc, int two_issuers, int reps, long long* out) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        tmem_alloc(&tmem_slot, 512);
+        tmem_relinquish();
+    }
+    if (tid == 0) {
+        mbar_init(&bar, two_issuers ? 2 : 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < (128 + 256) * 32 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    long long t0 = 0;
+    if ((tid == 0) || (two_issuers && tid == 32)) {
+        const uint32_t idesc = idesc_tf32(128, N, false, false);
+        const uint64_t bd = smem_desc_kmajor_noswz(smem_u32(smem) + 128 * 32, N * 16, 128);
+        const uint64_t ad = smem_desc_kmajor_noswz(smem_u32(smem), 128 * 16, 128);
+        const int my_reps = two_issuers ? reps / 2 : reps;
+        const int acc0 = (two_issuers && tid == 32) ? n_acc / 2 : 0;
+        const int my_acc = two_issuers ? max(n_acc / 2, 1) : n_acc;
+        t0 = clock64();
+        for (int i = 0; i < my_reps; ++i) {
+            const uint32_t d = tbase + ((acc0 + i % my_acc) * N) % 256;
+            if (a_in_tmem)
+                mma_tf32_ts(d, tbase + 256 + (i & 7) * 8, bd, idesc, 1);
+            else
+                mma_tf32_ss(d, ad, bd, idesc, 1);
+        }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    if (tid == 0) out[blockIdx.x] = clock64() - t0;
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
 static float frand_int() { return float((rand() % 9) - 4); }
 
 static int run_mma(int K, int N, int a_tmem, int negA, int negB, const char* name) {
@@ -394,6 +440,30 @@ int main(int argc, char** argv) {
                     }
             printf("v7 TMA 3D store (swizzled staging, clipped at T): bad=%d -> %s\n", bad, bad ? "FAIL" : "PASS");
             rc = bad != 0;
+            break;
+        }
+        case 9: {
+            CK(cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+            long long* dout;
+            CK(cudaMalloc(&dout, 148 * 8));
+            const int reps = 4096;
+            printf("v9 tensor-pipe rate (tf32, M=128, K=8 per MMA, %d MMAs): cycles per MMA  [ideal N/2]\n", reps);
+            for (int grid : {1, 148})
+                for (int N : {32, 64, 128, 256})
+                    for (int ts = 0; ts < 2; ++ts)
+                        for (int nacc : {1, 4})
+                            for (int two = 0; two < 2; ++two) {
+                                if (nacc * N > 256 && nacc > 1) continue;
+                                if (two && nacc < 2) continue;
+                                k_rate<<<grid, 128, 48 * 1024>>>(N, ts, nacc, two, reps, dout);
+                                CK(cudaDeviceSynchronize());
+                                long long h[148];
+                                CK(cudaMemcpy(h, dout, grid * 8, cudaMemcpyDeviceToHost));
+                                long long mx = 0;
+                                for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
+                                printf("  grid=%3d N=%3d A=%s acc=%d issuers=%d : %.1f cyc/MMA\n", grid, N, ts ? "tmem" : "smem",
+                                       nacc, two + 1, (double)mx / reps);
+                            }
             break;
         }
         default: printf("unknown variant\n"); rc = 3;

@@ -44,7 +44,7 @@ constexpr int kPackBatch = 4;                // 4x4 sub-filter blocks (4 x 16-by
 constexpr int kStagingBytes = kTileM * 128;  // one [128 x 32] fp32 store tile
 constexpr uint32_t kSmemLimit = 232448;      // 227 KB opt-in maximum per CTA
 // register budget: 896 x 72 = 64512 at launch = 128 x kRegsWg0 + 256 x kRegsWg1 + 512 x kRegsEpi
-constexpr int kRegsWg0 = 40, kRegsWg1 = 40, kRegsEpi = 96;
+constexpr int kRegsWg0 = 24, kRegsWg1 = 48, kRegsEpi = 96;
 static_assert(128 * kRegsWg0 + 256 * kRegsWg1 + 512 * kRegsEpi <= 896 * 72, "register pool");
 
 // bit (a*4+b) set when block (input component a -> output component b) enters negated: conv table, SURVEY 3.2.
@@ -154,6 +154,13 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_
         : "memory");
 }
 
+__device__ __forceinline__ uint32_t rn_bias(float v) { return __float_as_uint(v) + 0x1000u; }
+__device__ __forceinline__ void swap4(uint4& a, uint4& b) {
+    const uint4 t = a;
+    a = b;
+    b = t;
+}
+
 template <int ACT>
 __device__ __forceinline__ float activate(float v, int act_rt) {
     if (ACT == kActLinear) return v;
@@ -206,7 +213,9 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const TcParams p,
               const float* __restrict__ w, const float* __restrict__ bias) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment (TMA 128B swizzle) by offsetting the __shared__ array itself, so that every pointer derived
+    // from it stays in the shared address space (LDS/STS instead of generic LD/ST)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* w_s = smem;                                               // resident sub-filters of the current f-tile
     uint8_t* x_s = w_s + ((p.w_bytes + 1023u) & ~1023u);               // x ring
     uint8_t* y_s = x_s + (size_t)p.x_stages * p.x_stage_bytes;         // 2 staging tiles (one per epilogue group pair)
@@ -255,7 +264,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     uint32_t xs = 0, xph = 0, as = 0, aph = 0, accph = 0;
 
     // 896 threads x 72 registers are granted at launch.  The epilogue warpgroups hold 64 accumulator values per thread
-    // and grow to 96; the producer / issuer / converter warpgroups shrink to 40.
+    // and grow to 96; the producer / issuer warpgroup shrinks to 24, the two converter warpgroups to 48.
     // (setmaxnreg sits INSIDE each role branch: ptxas takes the minimum of the values that reach a join point.)
 
     if (warp >= kWarpAlloc && warp < kWarpConv0) {
@@ -383,20 +392,44 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     const uint8_t* xb = x_s + (size_t)xs * p.x_stage_bytes;
                     for (int tap0 = 0; tap0 < p.taps; tap0 += kMaxTapBatch) {
                         const int nb = min(kMaxTapBatch, p.taps - tap0);
+                        // all slots of the batch must be free before the first store; one fence for the batch
                         uint32_t as_b = as, aph_b = aph;
                         for (int tb = 0; tb < nb; ++tb) {
-                            const uint32_t row = (uint32_t)(r + (tap0 + tb) * p.dil);
                             mbar_wait(&bars->a_empty[as_b], aph_b ^ 1);
-                            tc_fence_after_sync();
                             if (detail && s < 8 && tap0 == 0) trace(p, kTrConv + 8 * s + 1 + tb);
-                            for (int k0 = 0; k0 < kc; k0 += 8) {
-                                const uint4 v0 = *reinterpret_cast<const uint4*>(xb + swz128(row, k0 >> 2));
-                                const uint4 v1 = *reinterpret_cast<const uint4*>(xb + swz128(row, (k0 >> 2) + 1));
-                                const uint32_t u[8] = {v0.x + 0x1000u, v0.y + 0x1000u, v0.z + 0x1000u, v0.w + 0x1000u,
-                                                       v1.x + 0x1000u, v1.y + 0x1000u, v1.z + 0x1000u, v1.w + 0x1000u};
-                                tmem_st8(t_a + lane_base + as_b * kASlotCols + k0, u);
-                            }
                             if (++as_b == kASlots) { as_b = 0; aph_b ^= 1; }
+                        }
+                        tc_fence_after_sync();
+                        as_b = as;
+                        for (int tb = 0; tb < nb; ++tb) {
+                            const uint32_t row = (uint32_t)(r + (tap0 + tb) * p.dil);
+                            const uint8_t* xrow = xb + row * 128u;
+                            const uint32_t sw = row & 7u;
+                            const uint32_t dst = t_a + lane_base + as_b * kASlotCols;
+                            if (kc == 32) {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {  // 16 columns at a time: 4 loads, 16 adds, one store
+                                    uint32_t u[16];
+#pragma unroll
+                                    for (int c4 = 0; c4 < 4; ++c4) {
+                                        const uint4 v = *reinterpret_cast<const uint4*>(xrow + (((h * 4 + c4) ^ sw) << 4));
+                                        u[4 * c4 + 0] = v.x + 0x1000u;
+                                        u[4 * c4 + 1] = v.y + 0x1000u;
+                                        u[4 * c4 + 2] = v.z + 0x1000u;
+                                        u[4 * c4 + 3] = v.w + 0x1000u;
+                                    }
+                                    tmem_st16_nc(dst + h * 16, u);
+                                }
+                            } else {
+                                for (int k0 = 0; k0 < kc; k0 += 8) {
+                                    const uint4 v0 = *reinterpret_cast<const uint4*>(xrow + ((((k0 >> 2)) ^ sw) << 4));
+                                    const uint4 v1 = *reinterpret_cast<const uint4*>(xrow + ((((k0 >> 2) + 1) ^ sw) << 4));
+                                    const uint32_t u[8] = {v0.x + 0x1000u, v0.y + 0x1000u, v0.z + 0x1000u, v0.w + 0x1000u,
+                                                           v1.x + 0x1000u, v1.y + 0x1000u, v1.z + 0x1000u, v1.w + 0x1000u};
+                                    tmem_st8_nc(dst + k0, u);
+                                }
+                            }
+                            if (++as_b == kASlots) as_b = 0;
                         }
                         tmem_wait_st();  // one wait for the whole batch of taps
                         if (detail && s < 8 && tap0 == 0) trace(p, kTrConv + 8 * s + 5);
@@ -449,15 +482,22 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     for (int u = 0; u < kPackBatch; ++u) {
                         const int bi = base + e + u * kEpiThreads;
                         if (bi < blocks) {
+                            // round to nearest tf32 as "add half an ulp" (the tensor core drops the low 13 bits)
+                            uint4 it0 = make_uint4(rn_bias(m[u][0].x), rn_bias(m[u][1].x), rn_bias(m[u][2].x), rn_bias(m[u][3].x));
+                            uint4 it1 = make_uint4(rn_bias(m[u][0].y), rn_bias(m[u][1].y), rn_bias(m[u][2].y), rn_bias(m[u][3].y));
+                            uint4 it2 = make_uint4(rn_bias(m[u][0].z), rn_bias(m[u][1].z), rn_bias(m[u][2].z), rn_bias(m[u][3].z));
+                            uint4 it3 = make_uint4(rn_bias(m[u][0].w), rn_bias(m[u][1].w), rn_bias(m[u][2].w), rn_bias(m[u][3].w));
+                            // A thread owns 64 contiguous bytes; neighbours are 64 bytes apart, so storing item k from
+                            // every thread at step k would hit the same banks 4 ways.  Thread t stores item k ^ sel at
+                            // step k (sel = (t >> 1) & 3): the 8 threads of a quarter-warp then cover all 32 banks.
+                            const uint32_t sel = ((uint32_t)e >> 1) & 3u;
+                            if (sel & 1u) { swap4(it0, it1); swap4(it2, it3); }
+                            if (sel & 2u) { swap4(it0, it2); swap4(it1, it3); }
                             uint4* dst = reinterpret_cast<uint4*>(w_s + ((size_t)bi << 6));  // 4 consecutive 16-byte slots
-                            dst[0] = make_uint4(f32_to_tf32_rn(m[u][0].x), f32_to_tf32_rn(m[u][1].x),
-                                                f32_to_tf32_rn(m[u][2].x), f32_to_tf32_rn(m[u][3].x));
-                            dst[1] = make_uint4(f32_to_tf32_rn(m[u][0].y), f32_to_tf32_rn(m[u][1].y),
-                                                f32_to_tf32_rn(m[u][2].y), f32_to_tf32_rn(m[u][3].y));
-                            dst[2] = make_uint4(f32_to_tf32_rn(m[u][0].z), f32_to_tf32_rn(m[u][1].z),
-                                                f32_to_tf32_rn(m[u][2].z), f32_to_tf32_rn(m[u][3].z));
-                            dst[3] = make_uint4(f32_to_tf32_rn(m[u][0].w), f32_to_tf32_rn(m[u][1].w),
-                                                f32_to_tf32_rn(m[u][2].w), f32_to_tf32_rn(m[u][3].w));
+                            dst[0 ^ sel] = it0;
+                            dst[1 ^ sel] = it1;
+                            dst[2 ^ sel] = it2;
+                            dst[3 ^ sel] = it3;
                         }
                     }
                 }
