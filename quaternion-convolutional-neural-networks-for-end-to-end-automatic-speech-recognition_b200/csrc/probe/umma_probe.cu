@@ -8,6 +8,7 @@
 //   6  TMA 4-D load, 128-B swizzle, box wider than the tensor and negative start row (zero fill), thread un-swizzle
 //   7  TMA 3-D store from a swizzled staging tile with clipping at the tensor edge
 //   8  as 1 with N = 32 and N = 16
+//  10  B operand MN-major with the TMA 128-byte swizzle (the layout a TMA box of the stored kernel lands in)
 //   9  tensor-pipe rate: cycles per tf32 MMA for N = 32/64/128/256, A from TMEM or smem, 1 or 4 accumulators, 1 or 2 issuers
 #define QNN_SPIN_LIMIT 20000000
 #include <cstdio>
@@ -211,8 +212,9 @@ __global__ void __launch_bounds__(128) k_tma_store(const __grid_constant__ CUten
     }
 }
 
-// Issues `reps` MMAs (K = 8 each) from one or two threads and reports the SM cycles from first issue to completion.
-__global__ void __launch_bounds__(128) k_rate(int N, int a_in_tmem, int n_acc, int two_issuers, int reps, long long* out) {
+// `n_issuers` threads (lane 0 of warps 0..n_issuers-1) each issue reps / n_issuers MMAs (K = 8 each) into their own
+// accumulator columns; reports the SM cycles from first issue to completion of everything.
+__global__ void __launch_bounds__(256) k_rate(int N, int a_in_tmem, int n_issuers, int same_acc, int reps, long long* out) {
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t bar;
     __shared__ uint32_t tmem_slot;
@@ -222,30 +224,38 @@ __global__ void __launch_bounds__(128) k_rate(int N, int a_in_tmem, int n_acc, i
         tmem_relinquish();
     }
     if (tid == 0) {
-        mbar_init(&bar, two_issuers ? 2 : 1);
+        mbar_init(&bar, n_issuers);
         fence_mbar_init();
     }
-    for (int i = tid; i < (128 + 256) * 32 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    for (int i = tid; i < (128 + 256) * 32 / 4; i += 256) reinterpret_cast<uint32_t*>(smem)[i] = 0;
     fence_proxy_async_smem();
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
     const uint32_t tbase = tmem_slot;
-    long long t0 = 0;
-    if ((tid == 0) || (two_issuers && tid == 32)) {
+    long long t0 = clock64();
+    if ((tid & 31) == 0 && warp < n_issuers) {
         const uint32_t idesc = idesc_tf32(128, N, false, false);
         const uint64_t bd = smem_desc_kmajor_noswz(smem_u32(smem) + 128 * 32, N * 16, 128);
         const uint64_t ad = smem_desc_kmajor_noswz(smem_u32(smem), 128 * 16, 128);
-        const int my_reps = two_issuers ? reps / 2 : reps;
-        const int acc0 = (two_issuers && tid == 32) ? n_acc / 2 : 0;
-        const int my_acc = two_issuers ? max(n_acc / 2, 1) : n_acc;
-        t0 = clock64();
-        for (int i = 0; i < my_reps; ++i) {
-            const uint32_t d = tbase + ((acc0 + i % my_acc) * N) % 256;
-            if (a_in_tmem)
-                mma_tf32_ts(d, tbase + 256 + (i & 7) * 8, bd, idesc, 1);
-            else
-                mma_tf32_ss(d, ad, bd, idesc, 1);
+        const int my_reps = reps / n_issuers;
+        // accumulator columns: issuers share 256 columns; with same_acc every MMA of a thread hits one accumulator,
+        // otherwise it alternates between two
+        const uint32_t d0 = tbase + (uint32_t)((warp * 2 * N) % 256);
+        const uint32_t d1 = same_acc ? d0 : tbase + (uint32_t)(((warp * 2 + 1) * N) % 256);
+        const uint32_t ta = tbase + 256;
+        for (int i = 0; i < my_reps; i += 4) {
+            if (a_in_tmem) {
+                mma_tf32_ts(d0, ta, bd, idesc, 1);
+                mma_tf32_ts(d1, ta + 8, bd, idesc, 1);
+                mma_tf32_ts(d0, ta + 16, bd, idesc, 1);
+                mma_tf32_ts(d1, ta + 24, bd, idesc, 1);
+            } else {
+                mma_tf32_ss(d0, ad, bd, idesc, 1);
+                mma_tf32_ss(d1, ad, bd, idesc, 1);
+                mma_tf32_ss(d0, ad, bd, idesc, 1);
+                mma_tf32_ss(d1, ad, bd, idesc, 1);
+            }
         }
         mma_commit(&bar);
     }
@@ -254,6 +264,107 @@ __global__ void __launch_bounds__(128) k_rate(int N, int a_in_tmem, int n_acc, i
     tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+// D[128 x N] = A[128 x K] * Bkn[K x N]; Bkn is row-major [k][n] in global (n contiguous, like the stored kernel).
+// smem image = what TMA SWIZZLE_128B would write for boxes of 32 n by K rows: panel h (n in [32h, 32h+32)) at
+// b_s + h*K*128, row k at +k*128, 16-byte chunk c at ((c ^ (k & 7)) << 4).
+__global__ void __launch_bounds__(128) k_mma_bmn(const float* __restrict__ A, const float* __restrict__ Bkn,
+                                                 float* __restrict__ D, int K, int N, int a_in_tmem) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint8_t* a_s = smem;                       // 128*K*4 (K-major no swizzle)
+    uint8_t* b_s = smem + ((128 * K * 4 + 1023) & ~1023);
+    __shared__ uint64_t bar;
+    __shared__ uint32_t tmem_slot;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) {
+        tmem_alloc(&tmem_slot, 512);
+        tmem_relinquish();
+    }
+    if (tid == 0) {
+        mbar_init(&bar, 1);
+        fence_mbar_init();
+    }
+    for (int i = tid; i < 128 * K; i += 128) {
+        int r = i / K, k = i % K;
+        *reinterpret_cast<float*>(a_s + noswz_off(r, k, 128)) = A[i];
+    }
+    for (int i = tid; i < K * N; i += 128) {
+        int k = i / N, n = i % N, h = n / 32, c = (n % 32) / 4, w4 = n % 4;
+        *reinterpret_cast<float*>(b_s + h * K * 128 + k * 128 + ((c ^ (k & 7)) << 4) + w4 * 4) = Bkn[i];
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t tbase = tmem_slot;
+    const uint32_t t_acc = tbase, t_a = tbase + 256;
+    const uint32_t lane_base = uint32_t(warp * 32) << 16;
+    if (a_in_tmem) {
+        for (int k0 = 0; k0 < K; k0 += 8) {
+            uint32_t v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = __float_as_uint(A[tid * K + k0 + j]);
+            tmem_st8(t_a + lane_base + k0, v);
+        }
+        tmem_wait_st();
+    }
+    fence_proxy_async_smem();
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    if (tid == 0) {
+        const uint32_t idesc = idesc_tf32_b_mn(128, N, false, false);
+        for (int ks = 0; ks < K / 8; ++ks) {
+            // K step ks = rows 8ks..8ks+7 of every panel: +ks*1024 bytes; panels are K*128 bytes apart
+            uint64_t bd = smem_desc_mnmajor_sw128(smem_u32(b_s) + ks * 1024, K * 128, 1024);
+            if (a_in_tmem) {
+                mma_tf32_ts(t_acc, t_a + ks * 8, bd, idesc, ks > 0);
+            } else {
+                uint64_t ad = smem_desc_kmajor_noswz(smem_u32(a_s) + ks * 2 * (128 * 16), 128 * 16, 128);
+                mma_tf32_ss(t_acc, ad, bd, idesc, ks > 0);
+            }
+        }
+        mma_commit(&bar);
+    }
+    mbar_wait(&bar, 0);
+    tc_fence_after_sync();
+    for (int c0 = 0; c0 < N; c0 += 8) {
+        uint32_t v[8];
+        tmem_ld8(t_acc + lane_base + c0, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+    }
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
+static int run_mma_bmn(int K, int N, int a_tmem) {
+    std::vector<float> A(128 * K), B(K * N), D(128 * N), R(128 * N);
+    for (auto& v : A) v = float((rand() % 9) - 4);
+    for (auto& v : B) v = float((rand() % 9) - 4);
+    for (int m = 0; m < 128; ++m)
+        for (int n = 0; n < N; ++n) {
+            float s = 0;
+            for (int k = 0; k < K; ++k) s += A[m * K + k] * B[k * N + n];
+            R[m * N + n] = s;
+        }
+    float *dA, *dB, *dD;
+    CK(cudaMalloc(&dA, A.size() * 4));
+    CK(cudaMalloc(&dB, B.size() * 4));
+    CK(cudaMalloc(&dD, D.size() * 4));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(dD, 0xff, D.size() * 4));
+    k_mma_bmn<<<1, 128, 128 * K * 4 + 1024 + K * N * 4 + 1024>>>(dA, dB, dD, K, N, a_tmem);
+    CK(cudaDeviceSynchronize());
+    CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+    int bad = 0;
+    for (size_t i = 0; i < D.size(); ++i) bad += D[i] != R[i];
+    printf("v10 B MN-major SW128: K=%d N=%d a_tmem=%d bad=%d  D[0..3]=%g %g %g %g ref %g %g %g %g -> %s\n", K, N, a_tmem,
+           bad, D[0], D[1], D[2], D[3], R[0], R[1], R[2], R[3], bad ? "FAIL" : "PASS");
+    return bad != 0;
 }
 
 static float frand_int() { return float((rand() % 9) - 4); }
@@ -442,28 +553,35 @@ int main(int argc, char** argv) {
             rc = bad != 0;
             break;
         }
+        case 10:
+            CK(cudaFuncSetAttribute(k_mma_bmn, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            rc = run_mma_bmn(8, 32, 1);
+            rc |= run_mma_bmn(8, 64, 1);
+            rc |= run_mma_bmn(40, 64, 1);
+            rc |= run_mma_bmn(40, 64, 0);
+            rc |= run_mma_bmn(16, 128, 1);
+            break;
         case 9: {
             CK(cudaFuncSetAttribute(k_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
             long long* dout;
             CK(cudaMalloc(&dout, 148 * 8));
             const int reps = 4096;
-            printf("v9 tensor-pipe rate (tf32, M=128, K=8 per MMA, %d MMAs): cycles per MMA  [ideal N/2]\n", reps);
-            for (int grid : {1, 148})
-                for (int N : {32, 64, 128, 256})
-                    for (int ts = 0; ts < 2; ++ts)
-                        for (int nacc : {1, 4})
-                            for (int two = 0; two < 2; ++two) {
-                                if (nacc * N > 256 && nacc > 1) continue;
-                                if (two && nacc < 2) continue;
-                                k_rate<<<grid, 128, 48 * 1024>>>(N, ts, nacc, two, reps, dout);
-                                CK(cudaDeviceSynchronize());
-                                long long h[148];
-                                CK(cudaMemcpy(h, dout, grid * 8, cudaMemcpyDeviceToHost));
-                                long long mx = 0;
-                                for (int i = 0; i < grid; ++i) mx = h[i] > mx ? h[i] : mx;
-                                printf("  grid=%3d N=%3d A=%s acc=%d issuers=%d : %.1f cyc/MMA\n", grid, N, ts ? "tmem" : "smem",
-                                       nacc, two + 1, (double)mx / reps);
-                            }
+            printf("v9 tensor-pipe rate (tf32, M=128, K=8 per MMA, %d MMAs in total): cycles per MMA, aggregate  [pipe floor N/2]\n", reps);
+            for (int N : {32, 64, 128, 256})
+                for (int ts = 0; ts < 2; ++ts)
+                    for (int same = 0; same < 2; ++same)
+                        for (int ni : {1, 2, 4, 8}) {
+                            if (N == 256 && !same) continue;
+                            if (N == 128 && ni > 2 && !same) continue;
+                            k_rate<<<148, 256, 48 * 1024>>>(N, ts, ni, same, reps, dout);
+                            CK(cudaDeviceSynchronize());
+                            long long h[148];
+                            CK(cudaMemcpy(h, dout, 148 * 8, cudaMemcpyDeviceToHost));
+                            long long mx = 0;
+                            for (int i = 0; i < 148; ++i) mx = h[i] > mx ? h[i] : mx;
+                            printf("  N=%3d A=%s %s issuers=%d : %.1f cyc/MMA\n", N, ts ? "tmem" : "smem",
+                                   same ? "1 acc/thread " : "2 accs/thread", ni, (double)mx / reps);
+                        }
             break;
         }
         default: printf("unknown variant\n"); rc = 3;

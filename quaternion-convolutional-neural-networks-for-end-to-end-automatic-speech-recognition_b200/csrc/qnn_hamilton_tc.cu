@@ -68,7 +68,8 @@ enum { kTrStart = 0, kTrSetup = 1, kTrPacked = 2, kTrFirstTma = 3, kTrTmaDone = 
        kTrFirstA = 7, kTrTile0 = 8 /* + 5 * tile: acc_empty passed, acc_full committed, epilogue got acc, TMEM released,
                                      stores issued */, kTrEnd = 58, kTrGlobalStart = 59, kTrGlobalEnd = 60, kTrSm = 61,
        kTrConv = 64 /* + 8*stage: x_full passed, a_empty passed (tap 0..3), wait::st done, arrived */,
-       kTrIssue = 128 /* + 2*slot: a_full passed, committed */, kTrProd = 192 /* + 2*stage: x_empty passed, issued */ };
+       kTrIssue = 128 /* + 2*slot: a_full passed, committed */, kTrProd = 192 /* + 2*stage: x_empty passed, issued */,
+       kTrPack = 240 /* loads issued, data arrived, stored, fenced+arrived */ };
 
 struct TcParams {
     unsigned long long* trace;
@@ -89,7 +90,7 @@ struct TcParams {
 struct __align__(8) Barriers {
     uint64_t x_full[kMaxXStages], x_empty[kMaxXStages];
     uint64_t a_full[kASlots], a_empty[kASlots];
-    uint64_t acc_full, acc_empty, w_ready;
+    uint64_t acc_full, acc_empty, w_raw, w_ready;
     uint32_t tmem_base;
 };
 
@@ -210,8 +211,8 @@ __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn,
 
 template <bool CONJ, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
-k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const TcParams p,
-              const float* __restrict__ w, const float* __restrict__ bias) {
+k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
+              const __grid_constant__ CUtensorMap tmw, const TcParams p, const float* __restrict__ bias) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment (TMA 128B swizzle) by offsetting the __shared__ array itself, so that every pointer derived
     // from it stays in the shared address space (LDS/STS instead of generic LD/ST)
@@ -236,6 +237,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         }
         tma_prefetch_desc(&tmx);
         tma_prefetch_desc(&tmy);
+        tma_prefetch_desc(&tmw);
         for (int i = 0; i < kMaxXStages; ++i) {
             mbar_init(&bars->x_full[i], 1);
             mbar_init(&bars->x_empty[i], 128);
@@ -246,6 +248,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         }
         mbar_init(&bars->acc_full, 2);
         mbar_init(&bars->acc_empty, kEpiThreads);
+        mbar_init(&bars->w_raw, 1);
         mbar_init(&bars->w_ready, kEpiThreads);
         fence_mbar_init();
     }
@@ -295,6 +298,15 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     }
                 }
                 trace(p, kTrTmaDone);
+            }
+        } else if (warp == kWarpAlloc) {
+            // =========================== sub-filter loader ===========================
+            // The stored sub-filters of this pass land RAW in their final region (one box per tap and component:
+            // in_q_pad rows of f_tile floats, rows beyond in_q zero-filled); the packer warps transpose in place.
+            if (elect_one()) {
+                mbar_arrive_expect_tx(&bars->w_raw, p.w_bytes);
+                for (int tc = 0; tc < p.taps * 4; ++tc)
+                    tma_load_4d(w_s + (size_t)tc * KQ * Fp * 16, &tmw, &bars->w_raw, ft * Fp, tc & 3, 0, tc >> 2);
             }
         } else if (warp == kWarpIssuer0 || warp == kWarpIssuer1) {
             // =========================== MMA issuers (whole warp runs the loops, one lane issues) ===========================
@@ -454,57 +466,52 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             // =========================== packers, then epilogue ===========================
             const int e = tid;  // 0..511
             {
-                // stored [tap][q][c*F + f] -> smem [(tap*4+c)][q/4][f][q%4] (K-major core matrices), rounded to tf32.
-                // A thread takes 4 (q) x 4 (f) blocks: four 16-byte loads (one per q row, coalesced along f), a register
-                // transpose, four 16-byte shared stores (one per f).  All loads of a pass (up to 16 per thread) are
-                // issued before the first use, so a pass costs one memory round trip.
-                const int nf4 = Fp >> 2;
-                const int blocks = p.taps * 4 * KQ * nf4;
-                for (int base = 0; base < blocks; base += kEpiThreads * kPackBatch) {
-                    float4 m[kPackBatch][4];
+                // raw [(tap*4+c)][q][f] -> K-major core matrices [(tap*4+c)][q/4][f][q%4], rounded to nearest tf32 ("add
+                // half an ulp", the tensor core drops the low 13 bits).  Every group of four q rows occupies exactly the
+                // f_tile*16 bytes its packed form needs, so a warp transposes one such region in place: all lanes read
+                // (4 rows x their one or two filters), then all lanes write their 16-byte items.
+                const int lane = e & 31, pw = e >> 5;
+                const int regions = p.taps * 4 * KQ;
+                const bool has2 = lane + 32 < Fp, has1 = lane < Fp;
+                // bias of this pass: requested before the wait so its latency hides behind the sub-filter load
+                float bias_v = 0.f;
+                if (e < 4 * Fp && p.has_bias) bias_v = __ldg(bias + (e / Fp) * p.F + ft * Fp + (e % Fp));
+                mbar_wait(&bars->w_raw, ft & 1);
+                if (e == 0 && ft == 0) trace(p, kTrPack);
+                int it_n = 0;
+                for (int reg = pw; reg < regions; reg += 32, ++it_n) {
+                    if (ft == 0 && lane == 0 && (pw == 0 || pw == 15) && it_n < 4) trace(p, kTrPack + 4 + (pw ? 4 : 0) + it_n);
+                    uint32_t v[2][2][4];
 #pragma unroll
-                    for (int u = 0; u < kPackBatch; ++u) {
-                        const int bi = base + e + u * kEpiThreads;
-                        const bool in = bi < blocks;
-                        const uint32_t rowi = __umulhi((uint32_t)bi, p.magic_f4);       // bi / nf4 = (tap*4+c)*KQ + q4
-                        const uint32_t f4 = (uint32_t)bi - rowi * nf4;
-                        const uint32_t tc = __umulhi(rowi, p.magic_kq);                 // rowi / KQ = tap * 4 + c
-                        const uint32_t q4 = rowi - tc * KQ;
-                        const float* src = w + ((size_t)(in ? (tc >> 2) : 0) * p.in_q + q4 * 4) * 4 * p.F + (tc & 3) * p.F +
-                                           ft * Fp + f4 * 4;
+                    for (int u = 0; u < 2; ++u) {
+                        const int rg = reg + 16 * u;
+                        const uint32_t* raw = reinterpret_cast<const uint32_t*>(w_s + (size_t)min(rg, regions - 1) * Fp * 16);
 #pragma unroll
-                        for (int j = 0; j < 4; ++j)
-                            m[u][j] = (in && (int)(q4 * 4 + j) < p.in_q)
-                                          ? __ldg(reinterpret_cast<const float4*>(src + (size_t)j * 4 * p.F))
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+                        for (int j = 0; j < 4; ++j) {
+                            v[u][0][j] = has1 ? raw[j * Fp + lane] : 0u;
+                            v[u][1][j] = has2 ? raw[j * Fp + lane + 32] : 0u;
+                        }
                     }
+                    __syncwarp();
 #pragma unroll
-                    for (int u = 0; u < kPackBatch; ++u) {
-                        const int bi = base + e + u * kEpiThreads;
-                        if (bi < blocks) {
-                            // round to nearest tf32 as "add half an ulp" (the tensor core drops the low 13 bits)
-                            uint4 it0 = make_uint4(rn_bias(m[u][0].x), rn_bias(m[u][1].x), rn_bias(m[u][2].x), rn_bias(m[u][3].x));
-                            uint4 it1 = make_uint4(rn_bias(m[u][0].y), rn_bias(m[u][1].y), rn_bias(m[u][2].y), rn_bias(m[u][3].y));
-                            uint4 it2 = make_uint4(rn_bias(m[u][0].z), rn_bias(m[u][1].z), rn_bias(m[u][2].z), rn_bias(m[u][3].z));
-                            uint4 it3 = make_uint4(rn_bias(m[u][0].w), rn_bias(m[u][1].w), rn_bias(m[u][2].w), rn_bias(m[u][3].w));
-                            // A thread owns 64 contiguous bytes; neighbours are 64 bytes apart, so storing item k from
-                            // every thread at step k would hit the same banks 4 ways.  Thread t stores item k ^ sel at
-                            // step k (sel = (t >> 1) & 3): the 8 threads of a quarter-warp then cover all 32 banks.
-                            const uint32_t sel = ((uint32_t)e >> 1) & 3u;
-                            if (sel & 1u) { swap4(it0, it1); swap4(it2, it3); }
-                            if (sel & 2u) { swap4(it0, it2); swap4(it1, it3); }
-                            uint4* dst = reinterpret_cast<uint4*>(w_s + ((size_t)bi << 6));  // 4 consecutive 16-byte slots
-                            dst[0 ^ sel] = it0;
-                            dst[1 ^ sel] = it1;
-                            dst[2 ^ sel] = it2;
-                            dst[3 ^ sel] = it3;
+                    for (int u = 0; u < 2; ++u) {
+                        const int rg = reg + 16 * u;
+                        if (rg < regions) {
+                            uint4* dst = reinterpret_cast<uint4*>(w_s + (size_t)rg * Fp * 16);
+                            if (has1)
+                                dst[lane] = make_uint4(v[u][0][0] + 0x1000u, v[u][0][1] + 0x1000u, v[u][0][2] + 0x1000u,
+                                                       v[u][0][3] + 0x1000u);
+                            if (has2)
+                                dst[lane + 32] = make_uint4(v[u][1][0] + 0x1000u, v[u][1][1] + 0x1000u,
+                                                            v[u][1][2] + 0x1000u, v[u][1][3] + 0x1000u);
                         }
                     }
                 }
-                for (int i = e; i < 4 * Fp; i += kEpiThreads)
-                    bias_s[i] = p.has_bias ? __ldg(bias + (i / Fp) * p.F + ft * Fp + (i % Fp)) : 0.f;
+                if (e < 4 * Fp) bias_s[e] = bias_v;  // 4 * f_tile <= 256 < kEpiThreads
+                if (e == 0 && ft == 0) trace(p, kTrPack + 2);
                 fence_proxy_async_smem();  // generic-proxy writes above are read by the tensor core (async proxy)
                 mbar_arrive(&bars->w_ready);
+                if (e == 0 && ft == 0) trace(p, kTrPack + 3);
                 named_bar_sync(9, kEpiThreads);  // bias_s visible to every epilogue thread
                 if (e == 0 && ft == 0) trace(p, kTrPacked);
             }
@@ -529,6 +536,33 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 tc_fence_before_sync();
                 mbar_arrive(&bars->acc_empty);  // accumulators are in registers: the next tile's MMAs may start
                 if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 3);
+                if (tile + (int)gridDim.x >= p.n_tiles && ft == p.n_ftiles - 1 &&
+                    (size_t)p.x_stages * p.x_stage_bytes >= 4 * (size_t)kStagingBytes) {
+                    // Last tile of this CTA: every x stage has been consumed (its MMAs are complete), so the x ring is
+                    // free and each of the four groups gets a staging tile of its own -- no turn taking in the tail.
+                    uint8_t* st_own = x_s + (size_t)grp * kStagingBytes;
+#pragma unroll
+                    for (int which = 0; which < 2; ++which) {
+                        const int c = grp + 4 * which;
+                        if (c >= n_out) break;
+                        if (which == 1 && r == 0) tma_store_wait_read<0>();
+                        named_bar_sync(1 + grp, 128);
+                        if (which == 0)
+                            stage_chunk<ACT>(v0, bias_s + c * 32, st_own, r, p.act);
+                        else
+                            stage_chunk<ACT>(v1, bias_s + c * 32, st_own, r, p.act);
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + grp, 128);
+                        if (r == 0) {
+                            const int col = c * 32;
+                            tma_store_3d(&tmy, st_own, (col / Fp) * p.F + ft * Fp + (col % Fp), t0, b);
+                            tma_store_commit();
+                        }
+                    }
+                    if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 4);
+                    accph ^= 1;
+                    continue;
+                }
                 // four lock-step phases on this pair's staging tile: (turn 0, chunk set 0), (1, 0), (0, 1), (1, 1)
                 epi_phase<ACT>(v0, 0, 0, pair, turn, r, n_out, Fp, ft, t0, b, p, bias_s, st, &tmy);
                 epi_phase<ACT>(v0, 1, 0, pair, turn, r, n_out, Fp, ft, t0, b, p, bias_s, st, &tmy);
@@ -563,7 +597,7 @@ int num_sms() {
     return n;
 }
 
-typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams, const float*, const float*);
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*);
 
 TcKernel pick_kernel(bool conj, int act) {
     const int a = act == QNN_ACT_LINEAR ? kActLinear : (act == QNN_ACT_RELU ? kActRelu : kActGeneric);
@@ -600,6 +634,7 @@ TcPlan tc_plan(const Geom& g, int rank) {
     if (rows_in > 256) return no("halo exceeds the 256-row TMA box");
     if (g.out_sp[2] < 1 || g.batch < 1) return no("empty problem");
     const int in_q_pad = (g.in_q + 7) & ~7;
+    if (in_q_pad > 256) return no("more than 256 quaternion input channels (TMA box limit of the sub-filter load)");
     const size_t stage = ((size_t)rows_in * 128 + 1023) & ~size_t(1023);
     // Filters per pass: the whole layer when it fits (<= 64, accumulators 4 x f_tile TMEM columns); otherwise a
     // divisor that is a multiple of 32, so that every 32-column store chunk stays inside one output component.
@@ -667,7 +702,18 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     p.magic_f4 = (uint32_t)((1ull << 32) / (uint32_t)(p.f_tile / 4)) + 1;
     p.magic_kq = (uint32_t)((1ull << 32) / (uint32_t)(p.in_q_pad / 4)) + 1;
 
-    CUtensorMap tmx, tmy;
+    CUtensorMap tmx, tmy, tmw;
+    {
+        // stored kernel [tap][q][c][f]: one box = (f_tile filters, one component, in_q_pad rows, one tap), no swizzle
+        const uint64_t dims[4] = {(uint64_t)g.F, 4, (uint64_t)g.in_q, (uint64_t)g.k[2]};
+        const uint64_t str[3] = {(uint64_t)g.F * 4, (uint64_t)g.F * 16, (uint64_t)g.in_q * g.F * 16};
+        const uint32_t box[4] = {(uint32_t)pl.f_tile, 1, (uint32_t)pl.in_q_pad, 1};
+        int e = make_tmap_f32(&tmw, w, 4, dims, str, box, false);
+        if (e) {
+            set_error("cuTensorMapEncodeTiled(kernel) failed (%d)", e);
+            return QNN_E_CUDA;
+        }
+    }
     if (p.flat) {
         const uint64_t dims[3] = {(uint64_t)g.in_q * 4, (uint64_t)L, (uint64_t)g.batch};
         const uint64_t str[2] = {(uint64_t)g.in_q * 16, (uint64_t)L * g.in_q * 16};
@@ -716,7 +762,7 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     }
     const int grid = std::min(p.n_tiles, num_sms());
     p.trace = (g_trace && g_trace_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace : nullptr;
-    kern<<<grid, kThreads, pl.smem_bytes, st>>>(tmx, tmy, p, w, bias);
+    kern<<<grid, kThreads, pl.smem_bytes, st>>>(tmx, tmy, tmw, p, bias);
     count_launch();
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {

@@ -114,6 +114,16 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, ui
         "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
 }
+// L2 prefetch of a box (no shared memory involved): the later load of the same box then hits L2
+__device__ __forceinline__ void tma_prefetch_3d(const void* tmap, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_4d(const void* tmap, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.prefetch.tensor.4d.L2.global.tile [%0, {%1, %2, %3, %4}];" ::"l"(tmap), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, const void* smem_src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(tmap),
                  "r"(smem_u32(smem_src)), "r"(c0), "r"(c1)
@@ -221,6 +231,23 @@ __device__ __forceinline__ uint64_t smem_desc_kmajor_noswz(uint32_t smem_addr, u
     d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= uint64_t(1) << 46;  // descriptor version for sm_100
     return d;                // layout_type (bits 61..63) = 0: no swizzle
+}
+
+// Shared-memory matrix descriptor, MN-major with the 128-byte swizzle -- the image TMA (SWIZZLE_128B) leaves for a box of
+// 32 fp32 along MN by any number of K rows: row k of a panel is 128 bytes at  panel + k*128  (16-byte chunks XORed with
+// k mod 8); panels of 32 MN-elements are `lbo_bytes` apart, groups of 8 K rows `sbo_bytes` (= 1024) apart.
+__device__ __forceinline__ uint64_t smem_desc_mnmajor_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= uint64_t((smem_addr >> 4) & 0x3FFF);
+    d |= uint64_t((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= uint64_t((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= uint64_t(1) << 46;  // descriptor version for sm_100
+    d |= uint64_t(2) << 61;  // layout_type SWIZZLE_128B
+    return d;
+}
+// idesc bit 16: B is MN-major
+__host__ __device__ constexpr uint32_t idesc_tf32_b_mn(int M, int N, bool neg_a, bool neg_b) {
+    return idesc_tf32(M, N, neg_a, neg_b) | (1u << 16);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]

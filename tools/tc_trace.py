@@ -74,5 +74,10 @@ for s_ in range(16):
         v = t[cta, 192 + 2 * s_ + j]
         if v:
             ev.append((int(v - base), "stage %d %s" % (s_, n)))
+for j, n in enumerate(["pack: raw sub-filters landed", "-", "pack: stored", "pack: fenced+arrived", "pack w0 it0", "pack w0 it1",
+                       "pack w0 it2", "pack w0 it3", "pack w15 it0", "pack w15 it1", "pack w15 it2", "pack w15 it3"]):
+    v = t[cta, 240 + j]
+    if v:
+        ev.append((int(v - base), n))
 for c, n in sorted(ev):
     print("  %8d  %s" % (c, n))
