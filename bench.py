@@ -19,6 +19,16 @@ import sys
 import threading
 import time
 
+# torchrun exports OMP_NUM_THREADS=1 to every worker; the CPU baseline / reference arm on rank 0 must see all host
+# cores, and BLAS reads these variables when NumPy is first imported -- so set them before that import.
+if int(os.environ.get("RANK", "0")) == 0:
+    try:
+        _cores = len(os.sched_getaffinity(0))
+    except Exception:
+        _cores = os.cpu_count() or 1
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = str(_cores)
+
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
@@ -113,6 +123,23 @@ def host_cores():
         return os.cpu_count() or 1
 
 
+class all_host_threads(object):
+    """The CPU arm uses every host core for its BLAS calls, also under torchrun (which exports OMP_NUM_THREADS=1)."""
+
+    def __enter__(self):
+        try:
+            from threadpoolctl import threadpool_limits
+            self._ctx = threadpool_limits(limits=host_cores())
+            self._ctx.__enter__()
+        except Exception:
+            self._ctx = None
+        return self
+
+    def __exit__(self, *a):
+        if self._ctx is not None:
+            self._ctx.__exit__(*a)
+
+
 def run_reference(args, w):
     """The reference arm: CPU restatement of complexnn/conv.py:288-345 on the box's host cores (NumPy + its BLAS threads)."""
     rank = int(os.environ.get("RANK", "0"))
@@ -121,12 +148,13 @@ def run_reference(args, w):
     rng = np.random.default_rng(0)
     sample = 32 if w["kind"] == "conv1d" else 8192
     step, q = cpu_reference_step(w, sample, rng)
-    for _ in range(max(args.warmup, 1)):
-        step()
-    t0 = time.perf_counter()
-    for _ in range(args.steps):
-        step()
-    dt = (time.perf_counter() - t0) / args.steps
+    with all_host_threads():
+        for _ in range(max(args.warmup, 1)):
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = (time.perf_counter() - t0) / args.steps
     val = q / dt
     sample_desc = "%d of %d %s per step (NumPy fp32: expand+im2col+sgemm+bias+relu)" % (
         sample, w["B"], "sequences" if w["kind"] == "conv1d" else "rows")
@@ -299,15 +327,16 @@ def run_ours(args, w):
     except Exception:
         pass
     cpu_step, cpu_q = cpu_reference_step(w, 32 if w["kind"] == "conv1d" else 8192, np.random.default_rng(0))
-    cpu_step()
-    t0 = time.perf_counter()
-    reps = 0
-    while reps < 3 or time.perf_counter() - t0 < 10.0:
+    with all_host_threads():
         cpu_step()
-        reps += 1
-        if reps >= 200:
-            break
-    cpu_val = cpu_q * reps / (time.perf_counter() - t0)
+        t0 = time.perf_counter()
+        reps = 0
+        while reps < 3 or time.perf_counter() - t0 < 10.0:
+            cpu_step()
+            reps += 1
+            if reps >= 200:
+                break
+        cpu_val = cpu_q * reps / (time.perf_counter() - t0)
 
     line = {
         "metric": METRIC, "value": world * q / t_s, "unit": "qMAC/s", "n_gpus": world, "steps": steps,
