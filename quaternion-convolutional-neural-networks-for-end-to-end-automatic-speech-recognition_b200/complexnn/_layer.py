@@ -64,6 +64,27 @@ def conv_output_length(input_length, filter_size, padding, stride, dilation=1):
     return (out + stride - 1) // stride
 
 
+class SymbolicTensor(object):
+    """Placeholder produced by `Input(...)` and by calling a layer on another placeholder (Keras functional API):
+    carries only a shape and the (layer, inputs) pair that produces it.  A `Model` replays these nodes eagerly."""
+    _keras_symbolic = True
+
+    def __init__(self, shape, node=None, dtype=None, name=None):
+        self.shape = tuple(shape)
+        self._keras_shape = self.shape
+        self._node = node
+        self.dtype = dtype or _FLOATX
+        self.name = name
+
+    def __repr__(self):
+        return "<SymbolicTensor shape=%s>" % (self.shape,)
+
+
+def is_symbolic(x):
+    return getattr(x, "_keras_symbolic", False) or (
+        isinstance(x, (list, tuple)) and len(x) > 0 and all(getattr(t, "_keras_symbolic", False) for t in x))
+
+
 class InputSpec(object):
     def __init__(self, dtype=None, shape=None, ndim=None, max_ndim=None, min_ndim=None, axes=None):
         self.dtype, self.shape, self.ndim = dtype, shape, ndim
@@ -263,6 +284,13 @@ class Variable(object):
     def mark_device_updated(self):
         self._dev_is_master = True
 
+    def parameter(self, device="cuda"):
+        """The device mirror as an autograd leaf (for an optimiser); call `mark_device_updated` after stepping it."""
+        t = self.device(device)
+        if not t.requires_grad:
+            t.requires_grad_(True)
+        return t
+
     def __array__(self, dtype=None, copy=None):
         a = self.numpy()
         return a.astype(dtype) if dtype is not None else a
@@ -329,11 +357,13 @@ class Layer(object):
             raise ValueError("Input 0 is incompatible with layer %s: expected ndim=%d, found ndim=%d"
                              % (self.name, spec.ndim, len(shape)))
         for axis, value in spec.axes.items():
-            if value is not None and shape[int(axis)] != value:
+            if value is not None and shape[int(axis)] is not None and shape[int(axis)] != value:
                 raise ValueError("Input 0 is incompatible with layer %s: expected axis %s of input shape to have value %s "
                                  "but got shape %s" % (self.name, axis, value, shape))
 
     def __call__(self, inputs, **kwargs):
+        if is_symbolic(inputs):
+            return self._symbolic_call(inputs)
         self.assert_input_compatibility(inputs)
         if not self.built:
             self.build((None,) + tuple(int(s) for s in inputs.shape[1:]))
@@ -343,6 +373,21 @@ class Layer(object):
                 self._initial_weights = None
             self.assert_input_compatibility(inputs)
         return self.call(inputs, **kwargs)
+
+    def _symbolic_call(self, inputs):
+        """Functional-API call on placeholders: build from the static shape, infer the output shape, record the node."""
+        many = isinstance(inputs, (list, tuple))
+        shapes = [tuple(t.shape) for t in inputs] if many else tuple(inputs.shape)
+        if not many:
+            self.assert_input_compatibility(inputs)
+        if not self.built:
+            self.build(shapes)
+            self.built = True
+            if self._initial_weights is not None:
+                self.set_weights(self._initial_weights)
+                self._initial_weights = None
+        out_shape = self.compute_output_shape(shapes)
+        return SymbolicTensor(out_shape, node=(self, inputs))
 
     @property
     def weights(self):

@@ -256,6 +256,11 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor prefetch) may overlap
+    // the tail of the previous kernel on this stream; nothing below reads or writes global memory before that kernel
+    // has completed and flushed.  Our own dependents may start their prologue as soon as every CTA got here.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     tc_fence_before_sync();
     __syncthreads();
     tc_fence_after_sync();
@@ -762,9 +767,19 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     }
     const int grid = std::min(p.n_tiles, num_sms());
     p.trace = (g_trace && g_trace_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace : nullptr;
-    kern<<<grid, kThreads, pl.smem_bytes, st>>>(tmx, tmy, tmw, p, bias);
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;  // PDL: see griddepcontrol.wait in the kernel
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmx, tmy, tmw, p, bias);
     count_launch();
-    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("tensor-core kernel launch failed: %s", cudaGetErrorString(e));
         return QNN_E_CUDA;
