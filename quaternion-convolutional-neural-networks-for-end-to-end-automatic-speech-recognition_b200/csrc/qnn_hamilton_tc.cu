@@ -7,18 +7,20 @@
 // 4 B operands (the sub-filters); the sign is the instruction descriptor's negate bit.
 //
 // One persistent CTA per SM, 896 threads, warp-specialised:
-//   warp 17      TMA producer: raw fp32 x tiles (128 rows + halo, 32 channels) -> 128B-swizzled smem ring.  When in_q is
-//                a multiple of 8 the channel axis is walked flat (a 32-channel box may span two components, no padding);
+//   x tiles      TMA: raw fp32 (128 rows + halo, 32 channels) -> 128B-swizzled smem ring, issued by the converter group
+//                that owns the ring slot as soon as it has consumed it (no separate producer warp).  When in_q is a
+//                multiple of 8 the channel axis is walked flat (a 32-channel box may span two components, no padding);
 //                otherwise per component with the out-of-range tail zero-filled by TMA
 //   warps 20-27  converters  : two groups of four warps that take alternate x stages; smem -> registers, round-to-nearest tf32 (the tensor core would truncate), tcgen05.st into
 //                              a ring of A-operand slots in tensor memory; the tap shift is a row offset in this read;
 //                              all taps of a stage are converted as one batch (one tcgen05.wait::st per batch)
-//   warps 18,19  MMA issuers : warp 18 feeds accumulators y_r,y_i, warp 19 feeds y_j,y_k; per slot <=4 k-steps x 2 blocks,
-//                              A from TMEM, B = sub-filter block resident in smem (K-major, no swizzle)
+//   warps 16-19  MMA issuers : one warp per output component (y_r, y_i, y_j, y_k): a single thread sustains only one
+//                              tcgen05.mma per ~117 cycles, four issuers reach ~38 (measured; floor 32 at N = 64);
+//                              A from TMEM, B = sub-filter block resident in smem (K-major, no swizzle).  Warp 16 also
+//                              owns the TMEM allocation and issues the sub-filter TMA loads of each pass
 //   warps 0-15   epilogue    : first pack + round the sub-filters into smem (overlapping the first x loads); per tile all
 //                              16 warps pull the accumulators into registers at once (TMEM is free again after two
 //                              tcgen05.ld), then +bias -> activation -> swizzled staging -> TMA store (clips ragged tiles)
-//   warp 16      owns the TMEM allocation
 // The latency-critical roles sit on the HIGHEST warp ids: the SM's issue arbiter favours high warp ids, and the 16
 // epilogue warps spend most of their time polling an mbarrier (with a nanosleep back-off so they do not steal issue slots).
 // TMEM columns: [0,256) four fp32 accumulators y_r|y_i|y_j|y_k (<= 64 filters per pass), [256,512) eight 32-column A slots.
@@ -60,7 +62,7 @@ constexpr uint32_t transpose_bits(uint32_t m) {
 constexpr uint32_t kNegDense = transpose_bits(kNegConv);
 
 enum { kActLinear = 0, kActRelu = 1, kActGeneric = 2 };
-enum { kWarpAlloc = 16, kWarpProducer = 17, kWarpIssuer0 = 18, kWarpIssuer1 = 19, kWarpConv0 = 20 };
+enum { kWarpAlloc = 16, kWarpIssuer0 = 16, kWarpConv0 = 20 };
 
 // Optional per-CTA event trace (diagnostics, qnn_debug_trace): 64 clock64() slots per CTA, see tools/tc_trace.py
 constexpr int kTraceSlots = 256;  // 0..63 coarse events; 64.. detailed events of the CTA's second tile
@@ -88,7 +90,7 @@ struct TcParams {
 };
 
 struct __align__(8) Barriers {
-    uint64_t x_full[kMaxXStages], x_empty[kMaxXStages];
+    uint64_t x_full[kMaxXStages];
     uint64_t a_full[kASlots], a_empty[kASlots];
     uint64_t acc_full, acc_empty, w_raw, w_ready;
     uint32_t tmem_base;
@@ -227,7 +229,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
     const int Fp = p.f_tile, KQ = p.in_q_pad >> 2;
 
-    if (tid == kWarpProducer * 32) {
+    if (tid == kWarpAlloc * 32) {
         trace(p, kTrStart);
         if (p.trace) {
             p.trace[(size_t)blockIdx.x * kTraceSlots + kTrGlobalStart] = globaltimer_ns();
@@ -240,13 +242,12 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         tma_prefetch_desc(&tmw);
         for (int i = 0; i < kMaxXStages; ++i) {
             mbar_init(&bars->x_full[i], 1);
-            mbar_init(&bars->x_empty[i], 128);
         }
         for (int i = 0; i < kASlots; ++i) {
             mbar_init(&bars->a_full[i], 128);
-            mbar_init(&bars->a_empty[i], 2);
+            mbar_init(&bars->a_empty[i], 4);
         }
-        mbar_init(&bars->acc_full, 2);
+        mbar_init(&bars->acc_full, 4);
         mbar_init(&bars->acc_empty, kEpiThreads);
         mbar_init(&bars->w_raw, 1);
         mbar_init(&bars->w_ready, kEpiThreads);
@@ -266,7 +267,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     tc_fence_after_sync();
     const uint32_t t_acc = bars->tmem_base;
     const uint32_t t_a = t_acc + kAccCols;
-    if (tid == kWarpProducer * 32) trace(p, kTrSetup);
+    if (tid == kWarpAlloc * 32) trace(p, kTrSetup);
 
     // pipeline state persists across tiles and f-tile passes
     uint32_t xs = 0, xph = 0, as = 0, aph = 0, accph = 0;
@@ -278,45 +279,18 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     if (warp >= kWarpAlloc && warp < kWarpConv0) {
       reg_dealloc<kRegsWg0>();
       for (int ft = 0; ft < p.n_ftiles; ++ft) {
-        if (warp == kWarpProducer) {
-            // =========================== TMA producer ===========================
-            if (elect_one()) {
-                bool first = ft == 0;
-                for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                    const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
-                    const bool detail = ft == 0 && tile == (int)(blockIdx.x + gridDim.x);
-                    int pa = 0, pch = 0;  // padded mode: component / chunk of the current stage
-                    for (int s = 0; s < p.n_stages; ++s) {
-                        mbar_wait(&bars->x_empty[xs], xph ^ 1);
-                        if (detail && s < 16) trace(p, kTrProd + 2 * s);
-                        mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)p.rows_in * 128u);
-                        uint8_t* dst = x_s + (size_t)xs * p.x_stage_bytes;
-                        if (p.flat)
-                            tma_load_3d(dst, &tmx, &bars->x_full[xs], s * 32, t0 - p.pad_lo, b);
-                        else {
-                            tma_load_4d(dst, &tmx, &bars->x_full[xs], pch * 32, pa, t0 - p.pad_lo, b);
-                            if (++pch == p.n_chunks) { pch = 0; ++pa; }
-                        }
-                        if (first) { trace(p, kTrFirstTma); first = false; }
-                        if (detail && s < 16) trace(p, kTrProd + 2 * s + 1);
-                        if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
-                    }
-                }
-                trace(p, kTrTmaDone);
-            }
-        } else if (warp == kWarpAlloc) {
-            // =========================== sub-filter loader ===========================
-            // The stored sub-filters of this pass land RAW in their final region (one box per tap and component:
-            // in_q_pad rows of f_tile floats, rows beyond in_q zero-filled); the packer warps transpose in place.
-            if (elect_one()) {
+        {
+            // =========================== MMA issuers (whole warp runs the loops, one lane issues) ===========================
+            const bool elected = elect_one();
+            const int b = warp - kWarpIssuer0;  // this issuer's output component
+            if (warp == kWarpAlloc && elected) {
+                // The stored sub-filters of this pass land RAW in their final region (one box per tap and component:
+                // in_q_pad rows of f_tile floats, rows beyond in_q zero-filled); the packer warps transpose in place.
                 mbar_arrive_expect_tx(&bars->w_raw, p.w_bytes);
                 for (int tc = 0; tc < p.taps * 4; ++tc)
                     tma_load_4d(w_s + (size_t)tc * KQ * Fp * 16, &tmw, &bars->w_raw, ft * Fp, tc & 3, 0, tc >> 2);
             }
-        } else if (warp == kWarpIssuer0 || warp == kWarpIssuer1) {
-            // =========================== MMA issuers (whole warp runs the loops, one lane issues) ===========================
-            const bool elected = elect_one();
-            const int b0 = warp == kWarpIssuer0 ? 0 : 2;  // this issuer's two output components
+            __syncwarp();
             const uint32_t idesc_pos = idesc_tf32(kTileM, Fp, false, false);
             const uint32_t idesc_neg = idesc_tf32(kTileM, Fp, false, true);
             const uint64_t d0 = smem_desc_kmajor_noswz(smem_u32(w_s), (uint32_t)Fp * 16u, 128);
@@ -352,16 +326,12 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                                 if (ks >= nks) break;
                                 const int a = ka[ks];
                                 const uint32_t k_lo = tap_lo + (uint32_t)(kq[ks] >> 2) * Fp;
-#pragma unroll
-                                for (int bb = 0; bb < 2; ++bb) {
-                                    const int b = b0 + bb;
-                                    const int c = a ^ b;  // sub-filter index: IDX[a][b] = a xor b
-                                    mma_ts(t_acc + b * Fp, a_col + ks * 8, k_lo + c * sub_stride, desc_hi,
-                                           ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos, accumulate);
-                                }
+                                const int c = a ^ b;  // sub-filter index: IDX[a][b] = a xor b
+                                mma_ts(t_acc + b * Fp, a_col + ks * 8, k_lo + c * sub_stride, desc_hi,
+                                       ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos, accumulate);
                                 accumulate = 1;
                             }
-                            mma_commit(&bars->a_empty[as]);  // one of the two arrivals that free the slot
+                            mma_commit(&bars->a_empty[as]);  // one of the four arrivals that free the slot
                             if (detail && slot_i < 32) trace(p, kTrIssue + 2 * slot_i + 1);
                         }
                         __syncwarp();
@@ -382,22 +352,45 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         {
             // =========================== converters: smem fp32 -> tf32(rn) -> TMEM A slots ===========================
             // Two groups of 128 threads take alternate x stages, so one group's tcgen05.wait::st overlaps the other's
-            // loads.  Rounding to nearest tf32 is "add half an ulp, let the tensor core truncate": one integer add per
-            // element (an infinite input becomes NaN; finite inputs round exactly like cvt.rna).
+            // loads.  A group owns the ring slots of its parity: once its 128 threads are done with a slot, its thread 0
+            // issues the TMA load of the stage that comes x_stages later into the same slot (no producer warp, no
+            // "slot empty" barrier).  Rounding to nearest tf32 is "add half an ulp, let the tensor core truncate": one
+            // integer add per element (an infinite input becomes NaN; finite inputs round exactly like cvt.rna).
             const int cgrp = (tid - kWarpConv0 * 32) >> 7;
             const int r = (tid - kWarpConv0 * 32) & 127;
             const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
-            uint32_t gs = 0;  // running stage counter: stage parity selects the group
+            const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+            const int total_stages = my_tiles * p.n_stages;  // of this CTA in this pass
+            // issue the x load of this pass' stage number `i` (counted over this CTA's tiles) into ring slot `slot`
+            auto issue_stage = [&](int i, uint32_t slot) {
+                const int j = i / p.n_stages, s = i - j * p.n_stages;
+                const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+                const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
+                mbar_arrive_expect_tx(&bars->x_full[slot], (uint32_t)p.rows_in * 128u);
+                uint8_t* dst = x_s + (size_t)slot * p.x_stage_bytes;
+                if (p.flat)
+                    tma_load_3d(dst, &tmx, &bars->x_full[slot], s * 32, t0 - p.pad_lo, b);
+                else
+                    tma_load_4d(dst, &tmx, &bars->x_full[slot], (s % p.n_chunks) * 32, s / p.n_chunks, t0 - p.pad_lo, b);
+            };
+            if (r == 0) {  // prologue: fill this group's slots (x_stages is even; every pass starts at an even stage)
+                uint32_t slot = xs + cgrp;
+                for (int i = cgrp; i < p.x_stages && i < total_stages; i += 2, slot += 2) {
+                    issue_stage(i, slot >= (uint32_t)p.x_stages ? slot - p.x_stages : slot);
+                    if (ft == 0 && i == 0) trace(p, kTrFirstTma);
+                }
+            }
+            int stage_i = 0;  // stage number inside this pass
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 const bool detail = r == 0 && ft == 0 && tile == (int)(blockIdx.x + gridDim.x);
                 int cch = 0;  // padded mode: chunk inside the component
-                for (int s = 0; s < p.n_stages; ++s, ++gs) {
+                for (int s = 0; s < p.n_stages; ++s, ++stage_i) {
                     int kc = 32;
                     if (!p.flat) {
                         kc = min(32, p.in_q_pad - cch * 32);
                         if (++cch == p.n_chunks) cch = 0;
                     }
-                    if ((int)(gs & 1) != cgrp) {  // the other group's stage: just advance the ring positions
+                    if ((stage_i & 1) != cgrp) {  // the other group's stage: just advance the ring positions
                         if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
                         as += p.taps;
                         while (as >= kASlots) { as -= kASlots; aph ^= 1; }
@@ -405,7 +398,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     }
                     mbar_wait(&bars->x_full[xs], xph);
                     if (detail && s < 8) trace(p, kTrConv + 8 * s);
-                    if (r == 0 && cgrp == 0 && s == 0 && tile == (int)blockIdx.x && ft == 0) trace(p, kTrFirstX);
+                    if (r == 0 && stage_i == 0 && ft == 0) trace(p, kTrFirstX);
                     const uint8_t* xb = x_s + (size_t)xs * p.x_stage_bytes;
                     for (int tap0 = 0; tap0 < p.taps; tap0 += kMaxTapBatch) {
                         const int nb = min(kMaxTapBatch, p.taps - tap0);
@@ -457,7 +450,9 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                         }
                         if (detail && s < 8 && tap0 == 0) trace(p, kTrConv + 8 * s + 6);
                     }
-                    mbar_arrive(&bars->x_empty[xs]);
+                    // every thread of the group is done reading the slot -> refill it with the stage x_stages ahead
+                    named_bar_sync(10 + cgrp, 128);
+                    if (r == 0 && stage_i + p.x_stages < total_stages) issue_stage(stage_i + p.x_stages, xs);
                     if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
                 }
             }
@@ -543,24 +538,29 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 3);
                 if (tile + (int)gridDim.x >= p.n_tiles && ft == p.n_ftiles - 1 &&
                     (size_t)p.x_stages * p.x_stage_bytes >= 4 * (size_t)kStagingBytes) {
-                    // Last tile of this CTA: every x stage has been consumed (its MMAs are complete), so the x ring is
-                    // free and each of the four groups gets a staging tile of its own -- no turn taking in the tail.
-                    uint8_t* st_own = x_s + (size_t)grp * kStagingBytes;
+                    // Last tile of this CTA in the last pass: every x stage has been consumed and every MMA has read its
+                    // sub-filters, so the x ring and the sub-filter region are free: each group gets two private staging
+                    // tiles (no turn taking, no wait between its two chunks).
+                    uint8_t* st_own[2] = {x_s + (size_t)grp * kStagingBytes, w_s + (size_t)grp * kStagingBytes};
+                    const bool w_region_ok = p.w_bytes >= 4u * kStagingBytes;
 #pragma unroll
                     for (int which = 0; which < 2; ++which) {
                         const int c = grp + 4 * which;
                         if (c >= n_out) break;
-                        if (which == 1 && r == 0) tma_store_wait_read<0>();
-                        named_bar_sync(1 + grp, 128);
+                        uint8_t* sto = (which == 1 && w_region_ok) ? st_own[1] : st_own[0];
+                        if (which == 1 && !w_region_ok) {
+                            if (r == 0) tma_store_wait_read<0>();
+                            named_bar_sync(1 + grp, 128);
+                        }
                         if (which == 0)
-                            stage_chunk<ACT>(v0, bias_s + c * 32, st_own, r, p.act);
+                            stage_chunk<ACT>(v0, bias_s + c * 32, sto, r, p.act);
                         else
-                            stage_chunk<ACT>(v1, bias_s + c * 32, st_own, r, p.act);
+                            stage_chunk<ACT>(v1, bias_s + c * 32, sto, r, p.act);
                         fence_proxy_async_smem();
                         named_bar_sync(1 + grp, 128);
                         if (r == 0) {
                             const int col = c * 32;
-                            tma_store_3d(&tmy, st_own, (col / Fp) * p.F + ft * Fp + (col % Fp), t0, b);
+                            tma_store_3d(&tmy, sto, (col / Fp) * p.F + ft * Fp + (col % Fp), t0, b);
                             tma_store_commit();
                         }
                     }
@@ -576,7 +576,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 4);
                 accph ^= 1;
             }
-            if (r == 0) tma_store_wait_all<0>();
+            if (r == 0) tma_store_wait_read<0>();  // smem may be released; completion of the writes is the kernel's end
         }
         __syncthreads();  // every role is done with this f-tile's sub-filters
       }
@@ -585,7 +585,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     tc_fence_before_sync();
     __syncthreads();
     if (warp == kWarpAlloc) tmem_dealloc(t_acc, 512);
-    if (tid == kWarpProducer * 32) {
+    if (tid == kWarpAlloc * 32) {
         trace(p, kTrEnd);
         if (p.trace) p.trace[(size_t)blockIdx.x * kTraceSlots + kTrGlobalEnd] = globaltimer_ns();
     }
@@ -653,7 +653,7 @@ TcPlan tc_plan(const Geom& g, int rank) {
         fixed = 1024 /*align slack*/ + w_pad + 2 * kStagingBytes + 1024 /*bias*/ + 512 /*barriers*/;
         if (fixed + 2 * stage > kSmemLimit) continue;
         f_tile = ft;
-        stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / stage);
+        stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / stage) & ~1;  // even: 2 or 4 (slot ownership)
     }
     if (!f_tile) return no("sub-filters do not fit in shared memory for any admissible filter tile");
     pl.ok = 1;

@@ -385,3 +385,63 @@ def test_empty_batch_and_short_sequences(cnn):
     assert tuple(y.shape) == (2, 0, 64)
     d = cnn.QuaternionDense(64)
     assert tuple(d(torch.zeros((0, 16), device="cuda")).shape) == (0, 64)
+
+
+def test_baseline_config3_stack_vs_oracle(cnn):
+    """BASELINE.json configs[2] (as worded): 3 x QuaternionConv1D(64, 3, same, relu) + 2 x QuaternionDense(256, relu) on
+    TIMIT-shaped input [B, T, 4*41]; the first layer (in_q = 41) runs on the general kernel, the rest on tensor cores.
+    Checked layer by layer against the oracle fed with the GPU's own previous activations (so errors do not compound
+    through relu masks) and end to end in the Frobenius norm."""
+    rng = np.random.default_rng(5)
+    np.random.seed(5)
+    B, T = 16, 256
+    x = rng.normal(size=(B, T, 164)).astype(np.float32)
+    layers = [cnn.QuaternionConv1D(64, 3, padding="same", activation="relu") for _ in range(3)]
+    dense = [cnn.QuaternionDense(256, activation="relu") for _ in range(2)]
+    h = dev(x)
+    ref_chain = x
+    for i, layer in enumerate(layers):
+        hin = h.cpu().numpy()
+        h = layer(h)
+        k, b = layer.get_weights()
+        ref = O.qconv_forward(hin, k, b, 64, 1, "same", "channels_last", 1, "relu")
+        bound = O.qconv_abs_bound(hin, k, 64, 1, "same")
+        check_tf32(h.cpu().numpy(), ref, bound, "conv layer %d" % i)
+        ref_chain = O.qconv_forward(ref_chain, k, b, 64, 1, "same", "channels_last", 1, "relu")
+    h = h.reshape(B * T, 256)
+    ref_chain = ref_chain.reshape(B * T, 256)
+    for i, layer in enumerate(dense):
+        hin = h.cpu().numpy()
+        h = layer(h)
+        k, b = layer.get_weights()
+        check_tf32(h.cpu().numpy(), O.qdense_forward(hin, k, b, 256, "relu"), O.qdense_abs_bound(hin, k, 256),
+                   "dense layer %d" % i)
+        ref_chain = O.qdense_forward(ref_chain, k, b, 256, "relu")
+    assert errs(h.cpu().numpy(), ref_chain)[1] <= 2e-3, "5-layer chain, Frobenius"
+
+
+def test_baseline_config5_conv2d_slice_and_properties(cnn):
+    """BASELINE.json configs[4]: QuaternionConv2D(128, 3x3, same) on channels_first [B, 4*64, 128, 128] (general kernel
+    this round).  Oracle parity on a B=1 slice of reduced height; at the full spatial size size-independent properties:
+    batch-shard bit-equality and linearity."""
+    rng = np.random.default_rng(6)
+    np.random.seed(6)
+    layer = cnn.QuaternionConv2D(128, (3, 3), padding="same", data_format="channels_first", activation="relu")
+    xs = rng.normal(size=(1, 256, 12, 128)).astype(np.float32)
+    y = layer(dev(xs))
+    k, b = layer.get_weights()
+    assert k.shape == (3, 3, 64, 512)
+    ref = O.qconv_forward(xs, k, b, 128, (1, 1), "same", "channels_first", (1, 1), "relu")
+    check(y.cpu().numpy(), ref, FP32_TOL, "cfg5 slice")
+    x = torch.randn(4, 256, 128, 128, device="cuda")
+    yf = layer(x)
+    assert tuple(yf.shape) == (4, 512, 128, 128)
+    assert torch.equal(layer(x[2:].contiguous()), yf[2:])
+    lin = cnn.QuaternionConv2D(128, (3, 3), padding="same", data_format="channels_first", use_bias=False)
+    lin.build((None, 256, 128, 128))
+    lin.built = True
+    lin.set_weights([k])
+    x2 = torch.randn(2, 256, 128, 128, device="cuda")
+    lhs = lin(1.5 * x[:2] - 0.25 * x2)
+    rhs = 1.5 * lin(x[:2].contiguous()) - 0.25 * lin(x2)
+    assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-4
