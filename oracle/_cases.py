@@ -22,6 +22,11 @@ CONV_CASES = [
     ("c2_same_d2", 2, (1, 9, 8, 4), 2, (3, 2), dict(padding="same", dilation_rate=(2, 2), activation="relu")),
     ("c3_same", 3, (1, 4, 5, 6, 4), 2, (2, 3, 3), dict(padding="same", activation="relu")),
     ("c3_cf_valid_s2", 3, (1, 8, 5, 6, 7), 2, (2, 2, 3), dict(padding="valid", strides=(1, 2, 2), data_format="channels_first")),
+    # shapes the channels_first tensor-core kernel takes (in_q % 8 == 0, filters % 32 == 0, stride 1, row length % 4 == 0)
+    ("c2_tc_cf_same_33", 2, (2, 32, 6, 132), 32, (3, 3), dict(padding="same", data_format="channels_first", activation="relu")),
+    ("c2_tc_cf_valid_35_d21", 2, (1, 64, 9, 64), 64, (3, 5), dict(padding="valid", dilation_rate=(2, 1), data_format="channels_first")),
+    ("c1_tc_cf_tanh", 1, (2, 32, 200), 32, 3, dict(padding="same", data_format="channels_first", activation="tanh")),
+    ("c2_tc_cf_timit_35", 2, (1, 32, 41, 64), 32, (3, 5), dict(padding="same", data_format="channels_first", use_bias=False)),
 ]
 
 DENSE_CASES = [

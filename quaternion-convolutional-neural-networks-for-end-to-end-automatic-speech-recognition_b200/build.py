@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libqnn_b200.so")
-SOURCES = ["qnn_api.cu", "qnn_general.cu", "qnn_hamilton_tc.cu"]
+SOURCES = ["qnn_api.cu", "qnn_general.cu", "qnn_hamilton_tc.cu", "qnn_hamilton_tc2d.cu"]
 HEADERS = ["qnn_common.h", "qnn_ptx.cuh", "qnn_tmap.h", os.path.join("..", "..", "include", "qnn.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "--use_fast_math",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]
@@ -24,13 +24,16 @@ def build(force=False, verbose=False):
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    flags = list(NVCC_FLAGS)
+    if os.environ.get("QNN_SPIN_LIMIT"):  # debug builds: bounded mbarrier waits that trap instead of hanging the GPU
+        flags.append("-DQNN_SPIN_LIMIT=" + os.environ["QNN_SPIN_LIMIT"])
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     objs = []
     procs = []
     for s in SOURCES:
         o = os.path.join(HERE, "lib", s.replace(".cu", ".o"))
         objs.append(o)
-        cmd = [nvcc] + NVCC_FLAGS + ["-c", os.path.join(CSRC, s), "-o", o]
+        cmd = [nvcc] + flags + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     for cmd, p in procs:
         out, _ = p.communicate()

@@ -144,12 +144,14 @@ int run_forward(const Geom& g, int rank, int math, int algo, const float* x, con
     }
     const bool aligned =
         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) == 0;
-    if (algo == QNN_ALGO_TENSOR) return tc_forward(g, rank, x, w, bias, y, st);
+    if (algo == QNN_ALGO_TENSOR)
+        return g.channels_first ? tc2d_forward(g, rank, x, w, bias, y, st) : tc_forward(g, rank, x, w, bias, y, st);
     if (algo != QNN_ALGO_AUTO) {
         set_error("unknown algo %d", algo);
         return QNN_E_INVALID;
     }
     if (aligned && tc_plan(g, rank).ok) return tc_forward(g, rank, x, w, bias, y, st);
+    if (aligned && tc2d_plan(g, rank).ok) return tc2d_forward(g, rank, x, w, bias, y, st);
     return general_forward(g, x, w, bias, y, st);
 }
 
@@ -336,7 +338,7 @@ int qnn_conv_uses_tensor_cores(const qnn_conv_desc* d) {
     Geom g;
     if (build_geom(d, &g)) return 0;
     if (d->algo == QNN_ALGO_GENERAL || d->math != QNN_MATH_TF32) return 0;
-    return tc_plan(g, d->rank).ok;
+    return tc_plan(g, d->rank).ok || tc2d_plan(g, d->rank).ok;
 }
 
 int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units) {
@@ -420,6 +422,7 @@ int qnn_dense_forward_host(int64_t rows, int32_t in_q, int32_t q_units, const fl
 
 int qnn_debug_trace(void* device_buffer, size_t bytes) {
     tc_set_trace(device_buffer, bytes);
+    tc2d_set_trace(device_buffer, bytes);
     return QNN_OK;
 }
 

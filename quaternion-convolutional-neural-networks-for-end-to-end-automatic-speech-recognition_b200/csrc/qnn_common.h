@@ -44,6 +44,20 @@ TcPlan tc_plan(const Geom& g, int rank);
 void tc_set_trace(void* device_buffer, size_t bytes);
 int tc_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
 
+// tensor-core kernel for channels_first tensors (rank 1 / 2, stride 1): streamed sub-filters, transposing converters
+struct Tc2dPlan {
+    int ok;
+    int f_tile, n_ftiles;
+    int wbox;        // x box per channel: one row of 128 + halo positions (rounded up to 4)
+    int xshift;      // columns the box starts left of the first tap (16-byte alignment of the TMA start)
+    int x_stages;
+    size_t x_stage_bytes, smem_bytes;
+    const char* why;
+};
+Tc2dPlan tc2d_plan(const Geom& g, int rank);
+void tc2d_set_trace(void* device_buffer, size_t bytes);
+int tc2d_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+
 }  // namespace qnn
 
 // ---------------------------------------------------------------------------------------------------------------------

@@ -1,0 +1,629 @@
+// Fused Hamilton convolution for channels_first tensors on the 5th-generation tensor cores (sm_100a only):
+// QuaternionConv2D (and Conv1D) with data_format='channels_first', stride 1 -- BASELINE configs[4],
+// models/interspeech_model.py:60-61,97 in the reference.
+//
+// Problem: x[nb, 4*in_q, H, W], stored un-expanded kernel w[KH, KW, in_q, 4F], y[nb, 4F, Ho, Wo] =
+// act(bias + sum_tap sum_a sum_b +-x_a(h + kh*dh - ph, w + kw*dw - pw) . f_{a^b}[tap]).  As in qnn_hamilton_tc.cu the
+// 4in_q x 4F real weight of complexnn/conv.py:327-331 never exists: 16 signed tcgen05.mma per k-step share four A
+// operands (input components) and four B operands (sub-filters), sign = negate-B bit of the instruction descriptor.
+//
+// What differs from the channels_last kernel:
+//   * positions are the CONTIGUOUS axis of x and y.  One tile = 128 consecutive output columns of one output row.
+//     An x stage is a 4-D TMA box (W: 128 + halo, one input row = one kernel row kh, 8 quaternion channels, the 4
+//     components of a sample) landing as [channel][w]; a converter thread owns one position and walks the channels (conflict-free
+//     4-byte shared loads), so the transpose to "position = TMEM lane, channel = TMEM column" costs nothing extra.
+//     Rows / columns outside the image are TMA zero fill = the convolution's zero padding.
+//   * a whole layer's sub-filters (cfg 5: 1.18 MB) do not fit in shared memory, so they are STREAMED: a tiny
+//     pre-pass (k_pack_w2d) re-orders the stored kernel into the K-major core-matrix image the MMA wants, rounded
+//     to nearest tf32, one 8 KB block per (filter tile, 8-channel chunk, tap); the main kernel pulls a block with one
+//     cp.async.bulk into the B slot that pairs with the A slot of the same (chunk, tap).  A and B rings share their
+//     index and their "empty" barrier (the same 16 MMAs consume both).
+//   * the k loop is chunk-major: a stage holds all FOUR components of 8 quaternion channels, so one 8 KB sub-filter
+//     block feeds 16 MMAs (every (a, b) pair) and is read from L2 exactly once per tile.
+//   * the epilogue transposes back through a [32 channels][128 positions] staging tile and TMA-stores it (4-D box),
+//     which also clips ragged tiles.
+// Work item = (tile, filter tile of <= 64 filters); persistent CTAs stride over the items.
+// Warp roles and the TMEM plan are those of qnn_hamilton_tc.cu: warps 0-15 epilogue, 16-19 MMA issuers (one per output
+// component), 20-27 converters (two groups on alternate stages), 28 / 29 producers (x stages / sub-filter blocks); TMEM [0,256) accumulators, [256,512) eight A slots.
+#include <algorithm>
+#include <mutex>
+#include "qnn_common.h"
+#include "qnn_ptx.cuh"
+#include "qnn_tmap.h"
+
+namespace qnn {
+namespace {
+using namespace ptx;
+
+constexpr int kTileM = 128;
+constexpr int kThreads = 1024;
+constexpr int kEpiThreads = 512;
+constexpr int kSlots = 8;
+constexpr int kSlotCols = 32;
+constexpr int kAccCols = 256;
+constexpr int kMaxXStages = 6;
+constexpr int kMaxTapBatch = 4;
+constexpr int kStagingBytes = 32 * kTileM * 4;  // [32 channels][128 positions] fp32
+constexpr uint32_t kSmemLimit = 232448;
+// register budget: 1024 x 64 at launch = 2 x 128 x kRegsWg0 (issuers, producers) + 256 x kRegsWg1 (converters) + 512 x kRegsEpi
+constexpr int kRegsWg0 = 24, kRegsWg1 = 40, kRegsEpi = 96;
+static_assert(256 * kRegsWg0 + 256 * kRegsWg1 + 512 * kRegsEpi <= 1024 * 64, "register pool");
+
+constexpr uint32_t kNegConv = (1u << 4) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 12) | (1u << 14);
+constexpr uint32_t transpose_bits(uint32_t m) {
+    uint32_t t = 0;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b)
+            if ((m >> (a * 4 + b)) & 1u) t |= 1u << (b * 4 + a);
+    return t;
+}
+constexpr uint32_t kNegDense = transpose_bits(kNegConv);
+
+enum { kActLinear = 0, kActRelu = 1, kActGeneric = 2 };
+enum { kWarpAlloc = 16, kWarpIssuer0 = 16, kWarpConv0 = 20, kWarpProd0 = 28 /* 28: x TMA, 29: sub-filter blocks */ };
+
+// Optional per-CTA event trace (qnn_debug_trace, tools/tc2d_trace.py): clock64() slots per CTA
+constexpr int kTraceSlots = 256;
+enum { kTrStart = 0, kTrSetup = 1, kTrEnd = 2, kTrItem = 8 /* + 4*item: mma acc_empty passed, mma committed, epilogue got
+       acc, epilogue stored */, kTrIssue = 64 /* + 2*slot of the CTA's second item: a_full passed, b_full passed */,
+       kTrConv = 160 /* + 4*k, k-th own stage of converter group 0 in the second item: x_full passed, a_empty passed,
+                        stores issued, slot released */ };
+
+struct P2 {
+    unsigned long long* trace;
+    int n_items, n_ftiles;
+    int tiles_w, Ho;
+    int KH, KW, taps, dh, dw, pad_h, pad_w;
+    int n_qc;      // 8-channel chunks per item
+    int n_stages;  // x stages per item = n_qc * KH: one kernel row of one chunk each
+    int F, f_tile;
+    int wbox;        // x box: one row of wbox positions per channel
+    int xshift;      // the box starts xshift (0..3) columns left of the first tap: its start must be 16-byte aligned
+    int x_stages, x_stage_bytes;
+    int act, has_bias;
+    uint32_t b_blk_bytes;  // 4 sub-filters x 2 k-groups x f_tile x 16 B
+};
+
+struct __align__(8) Bars {
+    uint64_t x_full[kMaxXStages], x_empty[kMaxXStages];
+    uint64_t a_full[kSlots], b_full[kSlots], a_empty[kSlots];
+    uint64_t acc_full, acc_empty;
+    uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void trace(const P2& p, int slot) {
+    if (p.trace && slot < kTraceSlots) p.trace[(size_t)blockIdx.x * kTraceSlots + slot] = (unsigned long long)clock64();
+}
+
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
+                                       uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 d;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// plain (1-D) bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+template <int ACT>
+__device__ __forceinline__ float activate(float v, int act_rt) {
+    if (ACT == kActLinear) return v;
+    if (ACT == kActRelu) return fmaxf(v, 0.f);
+    return act_apply(v, act_rt);
+}
+
+// bias + activation on 32 accumulator columns (= 32 output channels) of this thread's position, written transposed
+// into the [32][128] staging tile (consecutive threads -> consecutive words: conflict-free)
+template <int ACT>
+__device__ __forceinline__ void stage_chunk_t(const uint32_t (&v)[32], const float* bias32, float* st, int r, int act_rt) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) st[j * kTileM + r] = activate<ACT>(__uint_as_float(v[j]) + bias32[j], act_rt);
+}
+
+struct ItemPos {
+    int ft, b, ho, w0;
+};
+__device__ __forceinline__ ItemPos item_pos(const P2& p, int item) {
+    ItemPos ip;
+    const int tile = item / p.n_ftiles;
+    ip.ft = item - tile * p.n_ftiles;
+    const int wt = tile % p.tiles_w, t2 = tile / p.tiles_w;
+    ip.ho = t2 % p.Ho;
+    ip.b = t2 / p.Ho;
+    ip.w0 = wt * kTileM;
+    return ip;
+}
+
+template <int ACT>
+__device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn, int which, int pair, int turn, int r,
+                                          int n_out, int Fp, const ItemPos& ip, const P2& p, const float* bias_s,
+                                          float* st, const CUtensorMap* tmy) {
+    const int c_act = pair + 2 * act_turn + 4 * which;  // 32-column chunk handled in this phase on this staging tile
+    if (c_act >= n_out) return;                        // uniform across the pair
+    const int col = c_act * 32;
+    const int ch0 = (col / Fp) * p.F + ip.ft * Fp + (col % Fp);  // first of 32 consecutive output channels
+    const bool mine = turn == act_turn;
+    if (mine) {
+        stage_chunk_t<ACT>(v, bias_s + ch0, st, r, p.act);
+        fence_proxy_async_smem();
+    }
+    named_bar_sync(5 + pair, 256);
+    if (mine && r == 0) {
+        tma_store_4d(tmy, st, ip.w0, ip.ho, ch0, ip.b);
+        tma_store_commit();
+        tma_store_wait_read<0>();  // the staging tile may now be overwritten by the partner group
+    }
+    named_bar_sync(5 + pair, 256);
+}
+
+template <bool CONJ, int ACT>
+__global__ void __launch_bounds__(kThreads, 1)
+k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const P2 p,
+                const float* __restrict__ wp, const float* __restrict__ bias) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_s = smem;                                             // kSlots sub-filter blocks
+    uint8_t* x_s = b_s + (size_t)kSlots * p.b_blk_bytes;             // x ring (b_blk_bytes is a multiple of 1024)
+    uint8_t* y_s = x_s + (size_t)p.x_stages * p.x_stage_bytes;       // 2 staging tiles
+    float* bias_s = reinterpret_cast<float*>(y_s + 2 * kStagingBytes);  // 4F floats
+    Bars* bars = reinterpret_cast<Bars*>(reinterpret_cast<uint8_t*>(bias_s) + (((size_t)p.F * 16 + 1023) & ~size_t(1023)));
+
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int Fp = p.f_tile;
+
+    if (tid == kWarpAlloc * 32) {
+        trace(p, kTrStart);
+        tma_prefetch_desc(&tmx);
+        tma_prefetch_desc(&tmy);
+        for (int i = 0; i < kMaxXStages; ++i) {
+            mbar_init(&bars->x_full[i], 1);
+            mbar_init(&bars->x_empty[i], 128);
+        }
+        for (int i = 0; i < kSlots; ++i) {
+            mbar_init(&bars->a_full[i], 128);
+            mbar_init(&bars->b_full[i], 1);
+            mbar_init(&bars->a_empty[i], 4);
+        }
+        mbar_init(&bars->acc_full, 4);
+        mbar_init(&bars->acc_empty, kEpiThreads);
+        fence_mbar_init();
+    }
+    if (warp == kWarpAlloc) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    // Programmatic dependent launch: the prologue above may overlap the tail of the previous kernel on the stream (the
+    // sub-filter pre-pass); nothing below touches global memory before that kernel has completed and flushed.
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t t_acc = bars->tmem_base;
+    const uint32_t t_a = t_acc + kAccCols;
+    if (tid == kWarpAlloc * 32) trace(p, kTrSetup);
+
+    uint32_t as = 0, aph = 0, accph = 0;
+
+    if (warp >= kWarpAlloc && warp < kWarpConv0) {
+        // =========================== MMA issuers (whole warp runs the loops, one lane issues) ===========================
+        reg_dealloc<kRegsWg0>();
+        const bool elected = elect_one();
+        const int b = warp - kWarpIssuer0;  // this issuer's output component
+        const uint32_t idesc_pos = idesc_tf32(kTileM, Fp, false, false);
+        const uint32_t idesc_neg = idesc_tf32(kTileM, Fp, false, true);
+        const uint64_t d0 = smem_desc_kmajor_noswz(smem_u32(b_s), (uint32_t)Fp * 16u, 128);
+        const uint32_t w_lo = (uint32_t)d0, desc_hi = (uint32_t)(d0 >> 32);
+        const uint32_t sub_stride = 2u * Fp;             // descriptor-lo units (16 B) between sub-filters of a block
+        const uint32_t slot_stride = p.b_blk_bytes >> 4;  // ... between B slots
+        constexpr uint32_t neg_table = CONJ ? kNegDense : kNegConv;
+        const int slots_per_item = p.n_stages * p.KW;
+        int icount = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
+            mbar_wait(&bars->acc_empty, accph ^ 1);
+            tc_fence_after_sync();
+            const bool tr = b == 0 && elected && icount < 12;
+            if (tr) trace(p, kTrItem + 4 * icount);
+            uint32_t accumulate = 0;
+            for (int i = 0; i < slots_per_item; ++i) {
+                mbar_wait(&bars->a_full[as], aph);
+                if (tr && icount == 1 && i < 48) trace(p, kTrIssue + 2 * i);
+                mbar_wait(&bars->b_full[as], aph);
+                if (tr && icount == 1 && i < 48) trace(p, kTrIssue + 2 * i + 1);
+                tc_fence_after_sync();
+                if (elected) {
+                    const uint32_t a_col = t_a + as * kSlotCols;
+                    const uint32_t blk_lo = w_lo + as * slot_stride;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int c = a ^ b;  // sub-filter index: IDX[a][b] = a xor b
+                        mma_ts(t_acc + b * Fp, a_col + a * 8, blk_lo + c * sub_stride, desc_hi,
+                               ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos, accumulate);
+                        accumulate = 1;
+                    }
+                    mma_commit(&bars->a_empty[as]);  // one of the four arrivals that free the A and the B slot
+                }
+                __syncwarp();
+                if (++as == kSlots) { as = 0; aph ^= 1; }
+            }
+            if (elected) mma_commit(&bars->acc_full);
+            if (tr) trace(p, kTrItem + 4 * icount + 1);
+            __syncwarp();
+            accph ^= 1;
+        }
+    } else if (warp >= kWarpProd0) {
+        // =========================== producers: warp 28 x stages (TMA), warp 29 sub-filter blocks (bulk copies) ===========================
+        reg_dealloc<kRegsWg0>();
+        if (warp == kWarpProd0 && elect_one()) {
+            uint32_t xs = 0, xph = 0;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const ItemPos ip = item_pos(p, item);
+                const int cx = ip.w0 - p.pad_w - p.xshift, cy = ip.ho - p.pad_h, cb = 4 * ip.b;
+                for (int qc = 0; qc < p.n_qc; ++qc)
+                    for (int kh = 0; kh < p.KH; ++kh) {
+                        mbar_wait(&bars->x_empty[xs], xph ^ 1);
+                        mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)(32 * p.wbox * 4));
+                        tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], cx, cy + kh * p.dh, qc * 8, cb);
+                        if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
+                    }
+            }
+        } else if (warp == kWarpProd0 + 1 && elect_one()) {
+            // block (ft, stage s, kw) of the packed sub-filters goes into the B slot paired with the A slot of (s, kw)
+            const size_t blk_floats = p.b_blk_bytes >> 2;
+            const int slots_per_item = p.n_stages * p.KW;
+            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+                const float* src = wp + (size_t)(item % p.n_ftiles) * slots_per_item * blk_floats;
+                for (int i = 0; i < slots_per_item; ++i, src += blk_floats) {
+                    mbar_wait(&bars->a_empty[as], aph ^ 1);
+                    mbar_arrive_expect_tx(&bars->b_full[as], p.b_blk_bytes);
+                    bulk_load(b_s + (size_t)as * p.b_blk_bytes, src, p.b_blk_bytes, &bars->b_full[as]);
+                    if (++as == kSlots) { as = 0; aph ^= 1; }
+                }
+            }
+        }
+    } else if (warp >= kWarpConv0) {
+        // =========================== converters: smem fp32 [channel][w] -> tf32(rn) -> TMEM A slots ===========================
+        // Two groups of 128 threads take alternate x stages; a thread owns one position (TMEM lane) and walks the 32
+        // channels of the stage (conflict-free 4-byte loads).  Rounding to nearest tf32 = add half an ulp, the tensor
+        // core truncates.
+        reg_dealloc<kRegsWg1>();
+        const int cgrp = (tid - kWarpConv0 * 32) >> 7;
+        const int r = (tid - kWarpConv0 * 32) & 127;
+        const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
+        const int ch_stride = p.wbox;  // floats between channels of a stage
+        int stage_i = 0;
+        uint32_t xs = 0, xph = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+            const bool tr = cgrp == 0 && r == 0 && item == (int)(blockIdx.x + gridDim.x);
+            for (int s = 0; s < p.n_stages; ++s, ++stage_i) {
+                if ((stage_i & 1) != cgrp) {  // the other group's stage: just advance the ring positions
+                    if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
+                    as += p.KW;
+                    while (as >= kSlots) { as -= kSlots; aph ^= 1; }
+                    continue;
+                }
+                mbar_wait(&bars->x_full[xs], xph);
+                if (tr && s < 48) trace(p, kTrConv + 4 * (s >> 1));
+                const float* xb = reinterpret_cast<const float*>(x_s + (size_t)xs * p.x_stage_bytes) + r + p.xshift;
+                for (int tap0 = 0; tap0 < p.KW; tap0 += kMaxTapBatch) {
+                    const int nb = min(kMaxTapBatch, p.KW - tap0);
+                    uint32_t as_b = as, aph_b = aph;
+                    for (int tb = 0; tb < nb; ++tb) {
+                        mbar_wait(&bars->a_empty[as_b], aph_b ^ 1);
+                        if (++as_b == kSlots) { as_b = 0; aph_b ^= 1; }
+                    }
+                    tc_fence_after_sync();
+                    if (tr && s < 48 && tap0 == 0) trace(p, kTrConv + 4 * (s >> 1) + 1);
+                    as_b = as;
+                    for (int tb = 0; tb < nb; ++tb) {
+                        const float* xt = xb + (tap0 + tb) * p.dw;
+                        const uint32_t dst = t_a + lane_base + as_b * kSlotCols;
+#pragma unroll
+                        for (int h = 0; h < 2; ++h) {
+                            uint32_t u[16];
+#pragma unroll
+                            for (int c = 0; c < 16; ++c)
+                                u[c] = __float_as_uint(xt[(h * 16 + c) * ch_stride]) + 0x1000u;  // round to nearest tf32
+                            tmem_st16_nc(dst + h * 16, u);
+                        }
+                        if (++as_b == kSlots) as_b = 0;
+                    }
+                    if (tr && s < 48 && tap0 == 0) trace(p, kTrConv + 4 * (s >> 1) + 2);
+                    tmem_wait_st();
+                    tc_fence_before_sync();
+                    for (int tb = 0; tb < nb; ++tb) {
+                        mbar_arrive(&bars->a_full[as]);
+                        if (++as == kSlots) { as = 0; aph ^= 1; }
+                    }
+                }
+                mbar_arrive(&bars->x_empty[xs]);  // this thread is done reading the x slot
+                if (tr && s < 48) trace(p, kTrConv + 4 * (s >> 1) + 3);
+                if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
+            }
+        }
+    } else {
+        // =========================== epilogue ===========================
+        reg_alloc<kRegsEpi>();
+        const int e = tid;  // 0..511
+        for (int i = e; i < 4 * p.F; i += kEpiThreads) bias_s[i] = p.has_bias ? __ldg(bias + i) : 0.f;
+        named_bar_sync(9, kEpiThreads);
+        const int grp = e >> 7, r = e & 127;
+        const int pair = grp & 1, turn = grp >> 1;
+        const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
+        const int n_out = (4 * Fp) >> 5;  // 32-column chunks per item: 4 or 8
+        float* st = reinterpret_cast<float*>(y_s + pair * kStagingBytes);
+        int icount = 0;
+        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
+            const ItemPos ip = item_pos(p, item);
+            mbar_wait_sleep(&bars->acc_full, accph);
+            tc_fence_after_sync();
+            if (e == 0 && icount < 12) trace(p, kTrItem + 4 * icount + 2);
+            uint32_t v0[32], v1[32];
+            tmem_ld32(t_acc + lane_base + min(grp, n_out - 1) * 32, v0);
+            tmem_ld32(t_acc + lane_base + min(grp + 4, n_out - 1) * 32, v1);
+            tmem_wait_ld();
+            tc_fence_before_sync();
+            mbar_arrive(&bars->acc_empty);  // accumulators are in registers: the next item's MMAs may start
+            epi_phase<ACT>(v0, 0, 0, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
+            epi_phase<ACT>(v0, 1, 0, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
+            epi_phase<ACT>(v1, 0, 1, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
+            epi_phase<ACT>(v1, 1, 1, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
+            if (e == 0 && icount < 12) trace(p, kTrItem + 4 * icount + 3);
+            accph ^= 1;
+        }
+        if (r == 0) tma_store_wait_read<0>();
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kWarpAlloc) tmem_dealloc(t_acc, 512);
+    if (tid == kWarpAlloc * 32) trace(p, kTrEnd);
+}
+
+// Stored kernel [tap][q][c][F]  ->  wp[ft][qc][tap][c][kg][f][q%4]  (q = qc*8 + kg*4 + q%4), rounded to nearest tf32:
+// the K-major, un-swizzled core-matrix image of each (filter tile, 8-channel chunk, tap) block, contiguous.
+__global__ void __launch_bounds__(256) k_pack_w2d(const float* __restrict__ w, float4* __restrict__ wp, int taps, int Q,
+                                                  int F, int Fp) {
+    const int n_qc = Q >> 3, n_ft = F / Fp;
+    const int total = n_ft * n_qc * taps * 4 * 2 * Fp;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int t = i;
+        const int f = t % Fp;
+        t /= Fp;
+        const int kg = t & 1;
+        t >>= 1;
+        const int c = t & 3;
+        t >>= 2;
+        const int tap = t % taps;
+        t /= taps;
+        const int qc = t % n_qc, ft = t / n_qc;
+        const float* src = w + ((size_t)(tap * Q + qc * 8 + kg * 4) * 4 + c) * F + ft * Fp + f;
+        const size_t qs = (size_t)4 * F;
+        float4 o;
+        o.x = __uint_as_float(__float_as_uint(__ldg(src)) + 0x1000u);
+        o.y = __uint_as_float(__float_as_uint(__ldg(src + qs)) + 0x1000u);
+        o.z = __uint_as_float(__float_as_uint(__ldg(src + 2 * qs)) + 0x1000u);
+        o.w = __uint_as_float(__float_as_uint(__ldg(src + 3 * qs)) + 0x1000u);
+        wp[i] = o;
+    }
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+typedef void (*Tc2dKernel)(const CUtensorMap, const CUtensorMap, const P2, const float*, const float*);
+
+unsigned long long* g_trace2d = nullptr;
+size_t g_trace2d_bytes = 0;
+
+Tc2dKernel pick_kernel(int act) {
+    const int a = act == QNN_ACT_LINEAR ? kActLinear : (act == QNN_ACT_RELU ? kActRelu : kActGeneric);
+    return a == kActLinear ? k_hamilton_tc2d<false, kActLinear>
+                           : a == kActRelu ? k_hamilton_tc2d<false, kActRelu> : k_hamilton_tc2d<false, kActGeneric>;
+}
+
+}  // namespace
+
+void tc2d_set_trace(void* device_buffer, size_t bytes) {
+    g_trace2d = static_cast<unsigned long long*>(device_buffer);
+    g_trace2d_bytes = bytes;
+}
+
+Tc2dPlan tc2d_plan(const Geom& g, int rank) {
+    Tc2dPlan pl{};
+    pl.ok = 0;
+    auto no = [&](const char* why) {
+        pl.why = why;
+        return pl;
+    };
+    if (!g.channels_first) return no("channels_last layout");
+    if (rank > 2) return no("rank 3");
+    if (g.conj_w) return no("dense table");
+    if (g.s[1] != 1 || g.s[2] != 1) return no("stride != 1");
+    if (g.in_q % 8) return no("in_q not a multiple of 8");
+    if (g.F % 32) return no("filters not a multiple of 32");
+    if (g.in_sp[2] % 4 || g.out_sp[2] % 4) return no("row length not a multiple of 4 (TMA stride alignment)");
+    if (g.out_sp[2] < 1 || g.out_sp[1] < 1 || g.batch < 1) return no("empty problem");
+    // un-swizzled TMA boxes must start on a 16-byte boundary of the innermost axis (measured: an odd start column is an
+    // illegal instruction, profiles/r01_tma_box_probe.log), so the box starts up to 3 columns early
+    const int xshift = (4 - (g.pad_lo[2] & 3)) & 3;
+    const int wbox = (kTileM + (g.k[2] - 1) * g.d[2] + xshift + 3) & ~3;
+    if (wbox > 256) return no("halo exceeds the 256-element TMA box");
+    const int f_tile = g.F % 64 == 0 ? 64 : 32;
+    const size_t blk = (size_t)32 * f_tile * 4;
+    const size_t stage = ((size_t)32 * wbox * 4 + 1023) & ~size_t(1023);
+    const size_t fixed = 1024 + kSlots * blk + 2 * kStagingBytes + (((size_t)g.F * 16 + 1023) & ~size_t(1023)) + 512;
+    if (fixed + 2 * stage > kSmemLimit) return no("x stages do not fit in shared memory");
+    pl.ok = 1;
+    pl.f_tile = f_tile;
+    pl.n_ftiles = g.F / f_tile;
+    pl.wbox = wbox;
+    pl.xshift = xshift;
+    pl.x_stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / stage);
+    pl.x_stage_bytes = stage;
+    pl.smem_bytes = fixed + (size_t)pl.x_stages * stage;
+    pl.why = "";
+    return pl;
+}
+
+int tc2d_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
+    const Tc2dPlan pl = tc2d_plan(g, rank);
+    if (!pl.ok) {
+        set_error("channels_first tensor-core kernel does not take this shape: %s", pl.why);
+        return QNN_E_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) {
+        set_error("tensor-core kernel needs 16-byte aligned x, kernel and y");
+        return QNN_E_UNSUPPORTED;
+    }
+    const int H = g.in_sp[1], W = g.in_sp[2], Ho = g.out_sp[1], Wo = g.out_sp[2], Q = g.in_q, F = g.F;
+    P2 p{};
+    p.tiles_w = (Wo + kTileM - 1) / kTileM;
+    p.Ho = Ho;
+    p.n_ftiles = pl.n_ftiles;
+    const long long ni = (long long)g.batch * Ho * p.tiles_w * pl.n_ftiles;
+    if (ni > 0x7fffffffLL / 64) {
+        set_error("too many tiles");
+        return QNN_E_UNSUPPORTED;
+    }
+    p.n_items = (int)ni;
+    p.KH = g.k[1];
+    p.KW = g.k[2];
+    p.taps = g.k[1] * g.k[2];
+    p.dh = g.d[1];
+    p.dw = g.d[2];
+    p.pad_h = g.pad_lo[1];
+    p.pad_w = g.pad_lo[2];
+    p.n_qc = Q / 8;
+    p.n_stages = p.n_qc * p.KH;
+    p.F = F;
+    p.f_tile = pl.f_tile;
+    p.wbox = pl.wbox;
+    p.xshift = pl.xshift;
+    p.x_stages = pl.x_stages;
+    p.x_stage_bytes = (int)pl.x_stage_bytes;
+    p.act = g.act;
+    p.has_bias = bias != nullptr;
+    p.b_blk_bytes = (uint32_t)(32 * pl.f_tile * 4);
+
+    CUtensorMap tmx, tmy;
+    {
+        // x[nb][4][Q][H][W] seen as [nb*4][Q][H][W]: box = (wbox positions, 1 row, 8 quaternion channels, the 4
+        // components of one sample), no swizzle
+        const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)Q, (uint64_t)4 * g.batch};
+        const uint64_t str[3] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)Q * H * W * 4};
+        const uint32_t box[4] = {(uint32_t)pl.wbox, 1, 8, 4};
+        int e = make_tmap_f32(&tmx, x, 4, dims, str, box, false);
+        if (e) {
+            set_error("cuTensorMapEncodeTiled(x, channels_first) failed (%d)", e);
+            return QNN_E_CUDA;
+        }
+    }
+    {
+        // y[nb][4F][Ho][Wo]: box = (128 positions, 1 row, 32 channels, 1 sample)
+        const uint64_t dims[4] = {(uint64_t)Wo, (uint64_t)Ho, (uint64_t)4 * F, (uint64_t)g.batch};
+        const uint64_t str[3] = {(uint64_t)Wo * 4, (uint64_t)Ho * Wo * 4, (uint64_t)4 * F * Ho * Wo * 4};
+        const uint32_t box[4] = {(uint32_t)kTileM, 1, 32, 1};
+        int e = make_tmap_f32(&tmy, y, 4, dims, str, box, false);
+        if (e) {
+            set_error("cuTensorMapEncodeTiled(y, channels_first) failed (%d)", e);
+            return QNN_E_CUDA;
+        }
+    }
+    Tc2dKernel kern = pick_kernel(g.act);
+    static std::mutex mu;
+    static Tc2dKernel configured[4];
+    static int n_configured = 0;
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        bool done = false;
+        for (int i = 0; i < n_configured; ++i) done |= configured[i] == kern;
+        if (!done) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
+            if (e != cudaSuccess) {
+                set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+                return QNN_E_CUDA;
+            }
+            configured[n_configured++] = kern;
+        }
+    }
+    // sub-filter pre-pass into a stream-ordered scratch (same size as the stored kernel; freed after the main kernel).
+    // The device's default pool keeps freed blocks (release threshold raised once), so steady-state calls do not go
+    // back to the OS allocator.
+    {
+        static std::once_flag once;
+        std::call_once(once, [] {
+            int dev = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = 64ull << 20;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+        });
+    }
+    const size_t wp_bytes = (size_t)p.taps * Q * 4 * F * sizeof(float);
+    float* wp = nullptr;
+    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&wp), wp_bytes, st);
+    if (e != cudaSuccess) {
+        set_error("stream-ordered scratch allocation of %zu bytes failed: %s", wp_bytes, cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    {
+        const int total = pl.n_ftiles * p.n_qc * p.taps * 8 * pl.f_tile;
+        k_pack_w2d<<<std::min((total + 255) / 256, 4 * num_sms()), 256, 0, st>>>(w, reinterpret_cast<float4*>(wp), p.taps, Q,
+                                                                              F, pl.f_tile);
+        count_launch();
+    }
+    const int grid = std::min(p.n_items, num_sms());
+    p.trace = (g_trace2d && g_trace2d_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace2d : nullptr;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, tmx, tmy, p, (const float*)wp, bias);
+    count_launch();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    cudaFreeAsync(wp, st);
+    if (e != cudaSuccess) {
+        set_error("channels_first tensor-core kernel launch failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    return QNN_OK;
+}
+
+}  // namespace qnn

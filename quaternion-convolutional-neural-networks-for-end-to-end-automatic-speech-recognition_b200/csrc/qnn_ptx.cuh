@@ -58,8 +58,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 #if QNN_SPIN_LIMIT
     for (uint64_t i = 0; i < (uint64_t)QNN_SPIN_LIMIT; ++i)
         if (mbar_try_wait(bar, parity)) return;
-    printf("mbar_wait overrun: block %d thread %d bar %p parity %u\n", blockIdx.x, threadIdx.x, bar, parity);
-    __trap();
+    __trap();  // no printf here: a call would need more registers than the setmaxnreg-shrunk roles own
 #else
     while (!mbar_try_wait(bar, parity)) {
     }
@@ -68,7 +67,15 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // Polling with back-off for waits that are expected to be long (keeps the warp off the issue slots).
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
+#if QNN_SPIN_LIMIT
+    for (uint64_t i = 0; i < (uint64_t)QNN_SPIN_LIMIT / 16; ++i) {
+        if (mbar_try_wait(bar, parity)) return;
+        __nanosleep(128);
+    }
+    __trap();
+#else
     while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+#endif
 }
 
 // ------------------------------------------------------------------ proxies / fences

@@ -92,7 +92,7 @@ def test_conv_forward_vs_reference_golden(cnn, golden, monkeypatch, case, algo):
     layer.set_weights(weights)
     y = layer(x)
     assert y.is_cuda and y.dtype == torch.float32
-    if algo == "auto" and name.startswith("c1_tc_"):
+    if algo == "auto" and "_tc_" in name:
         k = conv_kwargs(rank, kw)
         bound = O.qconv_abs_bound(g[name + ".x"], g[name + ".kernel"], filters, k["strides"], k["padding"],
                                   k["data_format"], k["dilation_rate"])
@@ -420,19 +420,70 @@ def test_baseline_config3_stack_vs_oracle(cnn):
     assert errs(h.cpu().numpy(), ref_chain)[1] <= 2e-3, "5-layer chain, Frobenius"
 
 
+def _tc_cf_shapes():
+    """Seeded random channels_first problems (rank 1 and 2) that the channels_first tensor-core kernel takes."""
+    from complexnn import _native
+    lib = _native.lib()
+    rng = np.random.default_rng(7)
+    out = []
+    while len(out) < 20:
+        rank = int(rng.choice([1, 2, 2, 2]))
+        in_q = int(rng.choice([8, 16, 24, 40]))
+        F = int(rng.choice([32, 64, 96, 128]))
+        k = tuple(int(v) for v in rng.integers(1, 5, size=rank))
+        d = tuple(int(v) for v in rng.integers(1, 3, size=rank))
+        pad = str(rng.choice(["same", "valid"]))
+        W = int(rng.choice([4, 40, 64, 128, 132, 200, 260]))
+        sp = (W,) if rank == 1 else (int(rng.choice([1, 3, 7, 12])), W)
+        if pad == "valid":
+            sp = tuple(max(n, (kk - 1) * dd + 2) for n, kk, dd in zip(sp, k, d))
+        B = int(rng.integers(1, 4))
+        act, use_bias = str(rng.choice(["relu", "linear", "tanh"])), bool(rng.integers(0, 2))
+        desc = _native.make_conv_desc(rank, B, sp, in_q, F, k, (1,) * rank, d, pad, "channels_first", act)
+        if lib.qnn_conv_uses_tensor_cores(ctypes.byref(desc)) == 1:
+            out.append((B, sp, in_q, F, k, d, pad, act, use_bias))
+    return out
+
+
+@pytest.mark.parametrize("shape", _tc_cf_shapes(), ids=lambda s: "B%d_%s_q%d_F%d_k%s_d%s_%s_%s_b%d" % s)
+def test_tensor_core_channels_first_random_shapes_vs_oracle(cnn, native_lib, shape):
+    from complexnn import _ops
+    from complexnn._layer import Variable
+    B, sp, in_q, F, k, d, pad, act, use_bias = shape
+    rank = len(sp)
+    rng = np.random.default_rng(abs(hash(shape)) % (2 ** 31))
+    x = rng.normal(size=(B, 4 * in_q) + sp).astype(np.float32)
+    kern = (rng.normal(size=k + (in_q, 4 * F)) / np.sqrt(4 * in_q * np.prod(k))).astype(np.float32)
+    bias = rng.normal(0, 0.1, size=4 * F).astype(np.float32) if use_bias else None
+    ones = (1,) * rank
+    y = _ops.conv_forward(dev(x), Variable(kern), Variable(bias) if use_bias else None, F, k, ones, pad,
+                          "channels_first", d, act, math="tf32", algo="tensor")
+    ref = O.qconv_forward(x, kern, bias, F, ones, pad, "channels_first", d, act)
+    check_tf32(y.cpu().numpy(), ref, O.qconv_abs_bound(x, kern, F, ones, pad, "channels_first", d), str(shape))
+    yg = _ops.conv_forward(dev(x), Variable(kern), Variable(bias) if use_bias else None, F, k, ones, pad,
+                           "channels_first", d, act, math="fp32", algo="general")
+    check(yg.cpu().numpy(), ref, FP32_TOL, "general " + str(shape))
+
+
 def test_baseline_config5_conv2d_slice_and_properties(cnn):
-    """BASELINE.json configs[4]: QuaternionConv2D(128, 3x3, same) on channels_first [B, 4*64, 128, 128] (general kernel
-    this round).  Oracle parity on a B=1 slice of reduced height; at the full spatial size size-independent properties:
-    batch-shard bit-equality and linearity."""
+    """BASELINE.json configs[4]: QuaternionConv2D(128, 3x3, same) on channels_first [B, 4*64, 128, 128] on the
+    channels_first tensor-core kernel (one weight pre-pass + one fused launch).  Oracle parity on a B=1 slice of reduced
+    height; at the full spatial size size-independent properties: batch-shard bit-equality and linearity."""
+    from complexnn import _native
     rng = np.random.default_rng(6)
     np.random.seed(6)
     layer = cnn.QuaternionConv2D(128, (3, 3), padding="same", data_format="channels_first", activation="relu")
     xs = rng.normal(size=(1, 256, 12, 128)).astype(np.float32)
+    n0 = _native.launch_count()
     y = layer(dev(xs))
+    assert _native.launch_count() == n0 + 2            # sub-filter pre-pass + the fused kernel
     k, b = layer.get_weights()
     assert k.shape == (3, 3, 64, 512)
+    layer.set_weights([k, rng.normal(0, 0.1, 512).astype(np.float32)])
+    k, b = layer.get_weights()
+    y = layer(dev(xs))
     ref = O.qconv_forward(xs, k, b, 128, (1, 1), "same", "channels_first", (1, 1), "relu")
-    check(y.cpu().numpy(), ref, FP32_TOL, "cfg5 slice")
+    check_tf32(y.cpu().numpy(), ref, O.qconv_abs_bound(xs, k, 128, (1, 1), "same", "channels_first", (1, 1)), "cfg5 slice")
     x = torch.randn(4, 256, 128, 128, device="cuda")
     yf = layer(x)
     assert tuple(yf.shape) == (4, 512, 128, 128)
@@ -444,4 +495,12 @@ def test_baseline_config5_conv2d_slice_and_properties(cnn):
     x2 = torch.randn(2, 256, 128, 128, device="cuda")
     lhs = lin(1.5 * x[:2] - 0.25 * x2)
     rhs = 1.5 * lin(x[:2].contiguous()) - 0.25 * lin(x2)
-    assert float((lhs - rhs).abs().max() / rhs.abs().max()) < 1e-4
+    assert float((lhs - rhs).norm() / rhs.norm()) < 2 * TF32_TOL
+    # and the general kernel agrees with the tensor-core kernel on the same full-size samples
+    import os
+    os.environ["QNN_ALGO"], os.environ["QNN_MATH"] = "general", "fp32"
+    try:
+        yg = layer(x[:1].contiguous())
+    finally:
+        del os.environ["QNN_ALGO"], os.environ["QNN_MATH"]
+    assert float((yg - yf[:1]).norm() / yg.norm()) < TF32_TOL

@@ -239,7 +239,13 @@ def test_abi_argument_errors_and_kernel_selection(native_lib):
     s2 = _native.make_conv_desc(1, 8, (64,), 40, 64, (3,), (2,), (1,), "same", "channels_last", "relu")
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(s2)) == 0
     cf = _native.make_conv_desc(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")
-    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cf)) == 0
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cf)) == 1          # channels_first tensor-core kernel
+    cfg5 = _native.make_conv_desc(2, 128, (128, 128), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cfg5)) == 1        # BASELINE config 5
+    cf_odd = _native.make_conv_desc(2, 8, (16, 18), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cf_odd)) == 0      # row length % 4 != 0 -> general kernel
+    cl2 = _native.make_conv_desc(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_last", "relu")
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cl2)) == 0         # channels_last rank 2 -> general kernel
     assert native_lib.qnn_allreduce_f32(None, 4, None) == -6                  # QNN_E_STATE: no communicator yet
     assert native_lib.qnn_comm_init(2, 2, None) == -1
 
