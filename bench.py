@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Headline benchmark: quaternion-MACs/s of the fused Hamilton conv forward (BASELINE.json configs[1]).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|dense]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload cfg2|dense|cfg5]
 
 A step = one QuaternionConv1D forward (64 filters, kernel 3, stride 1, `same`, bias, relu) over a synthetic
 x[256, 256, 160] fp32 batch -- one launch of the fused tensor-core kernel through the layer API / C ABI.
@@ -44,6 +44,9 @@ WORKLOADS = {
                  desc="QuaternionConv1D fwd x[256,256,4x40] 64 filters k=3 same relu (BASELINE configs[1])"),
     "dense": dict(kind="dense", B=65536, T=1, in_q=40, F=64, k=1,
                   desc="QuaternionDense fwd x[65536,160] -> 256 relu (north-star dense shape)"),
+    # BASELINE configs[4] (not the headline line; run with --workload cfg5): T = H*W positions, k = 3*3 taps
+    "cfg5": dict(kind="conv2d", B=128, T=128 * 128, H=128, W=128, in_q=64, F=128, k=9,
+                 desc="QuaternionConv2D fwd x[128,4x64,128,128] channels_first 128 filters k=3x3 same relu (BASELINE configs[4])"),
 }
 
 
@@ -59,9 +62,10 @@ def alg_bytes(w):
 def peaks():
     try:
         m = json.load(open(os.path.join(REPO, "MEASURED_PEAKS.json")))
-        return dict(hbm_gbs=float(m["hbm_gbs"]), bf16=float(m["bf16_tflops"]), src="measured (MEASURED_PEAKS.json)")
+        return dict(hbm_gbs=float(m["hbm_gbs"]), bf16=float(m["bf16_tflops"]),
+                    bf16_sustained=float(m.get("bf16_tflops_sustained", m["bf16_tflops"])), src="measured (MEASURED_PEAKS.json)")
     except Exception:
-        return dict(hbm_gbs=6650.0, bf16=1590.0, src="fallback (B200_PROFILING.md)")
+        return dict(hbm_gbs=6650.0, bf16=1590.0, bf16_sustained=1590.0, src="fallback (B200_PROFILING.md)")
 
 
 class ClockSampler(threading.Thread):
@@ -136,10 +140,24 @@ def cpu_reference_step(w, sample_batch, rng):
         kern = (rng.normal(size=(w["k"], w["in_q"], 4 * w["F"])) * 0.05).astype(np.float32)
         bias = rng.normal(0, 0.1, 4 * w["F"]).astype(np.float32)
         return (lambda: O.qconv1d_forward_f32(x, kern, bias, w["F"], "same", True)), qmacs(w, sample_batch)
+    if w["kind"] == "conv2d":
+        x = rng.normal(size=(sample_batch, 4 * w["in_q"], w["H"], w["W"])).astype(np.float32)
+        kern = (rng.normal(size=(3, 3, w["in_q"], 4 * w["F"])) * 0.05).astype(np.float32)
+        bias = rng.normal(0, 0.1, 4 * w["F"]).astype(np.float32)
+        return (lambda: O.qconv2d_forward_f32(x, kern, bias, w["F"], True)), qmacs(w, sample_batch)
     x = rng.normal(size=(sample_batch, 4 * w["in_q"])).astype(np.float32)
     kern = (rng.normal(size=(w["in_q"], 4 * w["F"])) * 0.05).astype(np.float32)
     bias = rng.normal(0, 0.1, 4 * w["F"]).astype(np.float32)
     return (lambda: O.qdense_forward_f32(x, kern, bias, 4 * w["F"], True)), qmacs(w, sample_batch)
+
+
+def cpu_sample(w):
+    """Units of the workload one CPU-arm step processes (a bounded sample: the whole job would take minutes)."""
+    return {"conv1d": 32, "conv2d": 1, "dense": 8192}[w["kind"]]
+
+
+def unit_name(w):
+    return {"conv1d": "sequences", "conv2d": "images", "dense": "rows"}[w["kind"]]
 
 
 def host_cores():
@@ -172,7 +190,7 @@ def run_reference(args, w):
     if rank != 0:
         return 0
     rng = np.random.default_rng(0)
-    sample = 32 if w["kind"] == "conv1d" else 8192
+    sample = cpu_sample(w)
     step, q = cpu_reference_step(w, sample, rng)
     with all_host_threads():
         for _ in range(max(args.warmup, 1)):
@@ -182,8 +200,7 @@ def run_reference(args, w):
             step()
         dt = (time.perf_counter() - t0) / args.steps
     val = q / dt
-    sample_desc = "%d of %d %s per step (NumPy fp32: expand+im2col+sgemm+bias+relu)" % (
-        sample, w["B"], "sequences" if w["kind"] == "conv1d" else "rows")
+    sample_desc = "%d of %d %s per step (NumPy fp32: expand+im2col+sgemm+bias+relu)" % (sample, w["B"], unit_name(w))
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": "qMAC/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -224,6 +241,9 @@ def run_ours(args, w):
     if w["kind"] == "conv1d":
         layer = complexnn.QuaternionConv1D(w["F"], w["k"], padding="same", activation="relu")
         in_shape = (w["B"], w["T"], 4 * w["in_q"])
+    elif w["kind"] == "conv2d":
+        layer = complexnn.QuaternionConv2D(w["F"], (3, 3), padding="same", data_format="channels_first", activation="relu")
+        in_shape = (w["B"], 4 * w["in_q"], w["H"], w["W"])
     else:
         layer = complexnn.QuaternionDense(4 * w["F"], activation="relu")
         in_shape = (w["B"], 4 * w["in_q"])
@@ -234,7 +254,7 @@ def run_ours(args, w):
     layer.set_weights(ws)
 
     # ---- inputs resident in HBM; rotate buffer sets so no step finds its input in the 126 MB L2
-    n_sets = 3
+    n_sets = 3 if alg_bytes(w) < 1e9 else 1            # cfg5: one 2.1 GB input is already 17x the L2
     xs = [torch.randn(in_shape, device="cuda", dtype=torch.float32) for _ in range(n_sets)]
     y = None
     for i in range(max(args.warmup, 3)):
@@ -244,10 +264,12 @@ def run_ours(args, w):
     # parity gate on the very tensors that are timed: a fast wrong kernel is not a result
     if rank == 0:
         from oracle import qoracle as O
-        sl = slice(0, 4) if w["kind"] == "conv1d" else slice(0, 1024)
+        sl = {"conv1d": slice(0, 4), "conv2d": slice(0, 1), "dense": slice(0, 1024)}[w["kind"]]
         xh = xs[(max(args.warmup, 3) - 1) % n_sets][sl].cpu().numpy()
         if w["kind"] == "conv1d":
             ref = O.qconv_forward(xh, ws[0], ws[1], w["F"], 1, "same", "channels_last", 1, "relu")
+        elif w["kind"] == "conv2d":
+            ref = O.qconv_forward(xh, ws[0], ws[1], w["F"], (1, 1), "same", "channels_first", (1, 1), "relu")
         else:
             ref = O.qdense_forward(xh, ws[0], ws[1], 4 * w["F"], "relu")
         got = y[sl].cpu().numpy()
@@ -260,7 +282,7 @@ def run_ours(args, w):
     # ---- launch path: the K steps are replayed from a CUDA graph that holds one step per input set, so the timed
     # region measures the kernels, not the Python interpreter between two ~20 us launches (--no-graph: eager launches)
     graph = None
-    if not args.no_graph:
+    if not args.no_graph and w["kind"] != "conv2d":   # a 7 ms kernel gains nothing from graph replay
         cap_stream = torch.cuda.Stream()
         cap_stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(cap_stream):
@@ -305,7 +327,7 @@ def run_ours(args, w):
     # ---- end to end through the C ABI's host-buffer entry point (what the layer calls for NumPy inputs):
     # pinned host x -> H2D -> kernel -> D2H -> pinned host y, every step, synchronous return
     import ctypes
-    e2e_steps = max(3, min(args.steps, 20))
+    e2e_steps = max(3, min(args.steps, 20)) if alg_bytes(w) < 1e9 else 3
     xh_t = torch.empty(in_shape, dtype=torch.float32).pin_memory()
     xh_t.copy_(xs[0])
     out_shape = tuple(y.shape)
@@ -315,6 +337,11 @@ def run_ours(args, w):
     if w["kind"] == "conv1d":
         desc = _native.make_conv_desc(1, w["B"], (w["T"],), w["in_q"], w["F"], (w["k"],), (1,), (1,), "same",
                                       "channels_last", "relu")
+        host_call = lambda: _native.check(lib.qnn_conv_forward_host(ctypes.byref(desc), hp(xh_t), hp(ws[0]), hp(ws[1]),
+                                                                    hp(yh_t), None))
+    elif w["kind"] == "conv2d":
+        desc = _native.make_conv_desc(2, w["B"], (w["H"], w["W"]), w["in_q"], w["F"], (3, 3), (1, 1), (1, 1), "same",
+                                      "channels_first", "relu")
         host_call = lambda: _native.check(lib.qnn_conv_forward_host(ctypes.byref(desc), hp(xh_t), hp(ws[0]), hp(ws[1]),
                                                                     hp(yh_t), None))
     else:
@@ -346,7 +373,8 @@ def run_ours(args, w):
     pk = peaks()
     q = qmacs(w)
     flops = 32.0 * q
-    tf32_peak = pk["bf16"] / 2.0
+    long_step = ms > 2.0      # a multi-millisecond tensor-bound step runs at the power cap: sustained peak applies
+    tf32_peak = (pk["bf16_sustained"] if long_step else pk["bf16"]) / 2.0
     t_s = ms * 1e-3
     achieved_tf = flops / t_s / 1e12
     hbm_gbs = alg_bytes(w) / t_s / 1e9
@@ -355,7 +383,7 @@ def run_ours(args, w):
         traffic = json.load(open(os.path.join(REPO, "profiles", "traffic.json"))).get(args.workload)
     except Exception:
         pass
-    cpu_step, cpu_q = cpu_reference_step(w, 32 if w["kind"] == "conv1d" else 8192, np.random.default_rng(0))
+    cpu_step, cpu_q = cpu_reference_step(w, cpu_sample(w), np.random.default_rng(0))
     with all_host_threads():
         cpu_step()
         t0 = time.perf_counter()
@@ -384,13 +412,15 @@ def run_ours(args, w):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "tensor", "achieved": achieved_tf, "peak": tf32_peak, "unit": "TFLOP/s",
-                     "frac": achieved_tf / tf32_peak, "traffic": traffic, "kernel": "k_hamilton_tc",
-                     "peak_source": "tf32 dense = 1/2 x bf16 burst, " + pk["src"],
+                     "frac": achieved_tf / tf32_peak, "traffic": traffic,
+                     "kernel": "k_hamilton_tc2d" if w["kind"] == "conv2d" else "k_hamilton_tc",
+                     "peak_source": "tf32 dense = 1/2 x bf16 %s, " % ("sustained (multi-ms step at the power cap)" if long_step
+                                                                     else "burst") + pk["src"],
                      "flops_per_launch": flops, "hbm_achieved_gbs": hbm_gbs, "hbm_peak_gbs": pk["hbm_gbs"],
                      "hbm_frac": hbm_gbs / pk["hbm_gbs"], "algorithmic_bytes_per_launch": alg_bytes(w)},
         "cpu_baseline": {"value": cpu_val, "unit": "qMAC/s", "cores": host_cores(), "kind": "port",
-                         "sample": "%d x (32 of 256 sequences): NumPy fp32 expand+im2col+sgemm+bias+relu" % reps
-                         if w["kind"] == "conv1d" else "%d x 8192 of 65536 rows, NumPy fp32" % reps},
+                         "sample": "%d x (%d of %d %s): NumPy fp32 expand+im2col+sgemm+bias+relu" % (
+                             reps, cpu_sample(w), w["B"], unit_name(w))},
     }
     print(json.dumps(line))
     if world > 1:

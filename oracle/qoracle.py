@@ -368,6 +368,27 @@ def qconv1d_forward_f32(x, kernel, bias, filters, padding="same", relu=True):
     return y
 
 
+def qconv2d_forward_f32(x, kernel, bias, filters, relu=True):
+    """fp32 NumPy-literal QuaternionConv2D forward, stride 1, `same`, channels_first: expand -> im2col -> sgemm -> bias ->
+    relu (complexnn/conv.py:327-343 with K.conv2d restated as shifted slices + one GEMM per sample)."""
+    w = expand_conv_kernel(kernel, filters)                     # [kh, kw, 4in_q, 4F]
+    kh, kw = w.shape[:2]
+    B, C, H, W = x.shape
+    lo_h, hi_h, _ = pad_amounts(H, kh, 1, 1, "same")
+    lo_w, hi_w, _ = pad_amounts(W, kw, 1, 1, "same")
+    xp = np.pad(x, ((0, 0), (0, 0), (lo_h, hi_h), (lo_w, hi_w)))
+    wt = np.ascontiguousarray(w.reshape(kh * kw * C, -1).T)     # [4F, taps*4in_q]
+    y = np.empty((B, wt.shape[0], H, W), np.float32)
+    for b in range(B):
+        cols = np.concatenate([xp[b, :, i:i + H, j:j + W].reshape(C, H * W) for i in range(kh) for j in range(kw)], axis=0)
+        y[b] = (wt @ cols).reshape(-1, H, W)
+    if bias is not None:
+        y += bias[None, :, None, None]
+    if relu:
+        np.maximum(y, 0, out=y)
+    return y
+
+
 def qdense_forward_f32(x, kernel, bias, units, relu=True):
     y = x @ expand_dense_kernel(kernel, units // 4)
     if bias is not None:

@@ -254,6 +254,38 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         fence_mbar_init();
     }
     if (warp == kWarpAlloc) {
+        // The first x stages and the first pass' sub-filters are requested right here, before TMEM allocation and the
+        // CTA-wide barrier, one TMA per LANE of this warp (a single thread issuing all of them costs ~170 cycles
+        // each): the cold HBM ramp-up -- all CTAs asking at once -- is the longest latency of the start-up.
+        __syncwarp();
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // x / the kernel may be the previous kernel's output
+        const int lane = tid & 31;
+        const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total_stages = my_tiles * p.n_stages;
+        if (lane < p.x_stages && lane < total_stages) {
+            const int j = lane / p.n_stages, s = lane - j * p.n_stages;
+            const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+            const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
+            mbar_arrive_expect_tx(&bars->x_full[lane], (uint32_t)p.rows_in * 128u);
+            uint8_t* dst = x_s + (size_t)lane * p.x_stage_bytes;
+            if (p.flat)
+                tma_load_3d(dst, &tmx, &bars->x_full[lane], s * 32, t0 - p.pad_lo, b);
+            else
+                tma_load_4d(dst, &tmx, &bars->x_full[lane], (s % p.n_chunks) * 32, s / p.n_chunks, t0 - p.pad_lo, b);
+            if (lane == 0) trace(p, kTrFirstTma);
+        }
+        // The stored sub-filters land RAW in their final region (one box per tap and component: in_q_pad rows of f_tile
+        // floats, rows beyond in_q zero-filled); the packer warps transpose in place.  Every CTA wants the same boxes
+        // at the same moment: each CTA starts at a different box so that the requests spread over the L2 slices.
+        if (lane == 31) mbar_arrive_expect_tx(&bars->w_raw, p.w_bytes);
+        const int KQ0 = p.in_q_pad >> 2, nbox = p.taps * 4;
+        for (int i = lane; i < nbox; i += 32) {
+            const int tc = (i + (int)blockIdx.x) % nbox;
+            tma_load_4d(w_s + (size_t)tc * KQ0 * p.f_tile * 16, &tmw, &bars->w_raw, 0, tc & 3, 0, tc >> 2);
+        }
+        __syncwarp();
+    }
+    if (warp == kWarpAlloc) {
         tmem_alloc(&bars->tmem_base, 512);
         tmem_relinquish();
     }
@@ -283,12 +315,16 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             // =========================== MMA issuers (whole warp runs the loops, one lane issues) ===========================
             const bool elected = elect_one();
             const int b = warp - kWarpIssuer0;  // this issuer's output component
-            if (warp == kWarpAlloc && elected) {
-                // The stored sub-filters of this pass land RAW in their final region (one box per tap and component:
-                // in_q_pad rows of f_tile floats, rows beyond in_q zero-filled); the packer warps transpose in place.
+            if (warp == kWarpAlloc && elected && ft > 0) {  // (the first pass' sub-filters were requested at kernel start)
                 mbar_arrive_expect_tx(&bars->w_raw, p.w_bytes);
-                for (int tc = 0; tc < p.taps * 4; ++tc)
+                // every CTA wants the same boxes at the same moment: start each CTA at a different box so that the
+                // requests spread over the L2 slices instead of queueing on one line set
+                const int nbox = p.taps * 4;
+                int tc = (int)(blockIdx.x % (unsigned)nbox);
+                for (int i = 0; i < nbox; ++i) {
                     tma_load_4d(w_s + (size_t)tc * KQ * Fp * 16, &tmw, &bars->w_raw, ft * Fp, tc & 3, 0, tc >> 2);
+                    if (++tc == nbox) tc = 0;
+                }
             }
             __syncwarp();
             const uint32_t idesc_pos = idesc_tf32(kTileM, Fp, false, false);
@@ -373,12 +409,12 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 else
                     tma_load_4d(dst, &tmx, &bars->x_full[slot], (s % p.n_chunks) * 32, s / p.n_chunks, t0 - p.pad_lo, b);
             };
-            if (r == 0) {  // prologue: fill this group's slots (x_stages is even; every pass starts at an even stage)
+            // prologue: fill this group's slots (x_stages is even; every pass starts at an even stage).  The first
+            // pass' prologue was issued at kernel start by the barrier-initialising thread.
+            if (r == 0 && ft > 0) {
                 uint32_t slot = xs + cgrp;
-                for (int i = cgrp; i < p.x_stages && i < total_stages; i += 2, slot += 2) {
+                for (int i = cgrp; i < p.x_stages && i < total_stages; i += 2, slot += 2)
                     issue_stage(i, slot >= (uint32_t)p.x_stages ? slot - p.x_stages : slot);
-                    if (ft == 0 && i == 0) trace(p, kTrFirstTma);
-                }
             }
             int stage_i = 0;  // stage number inside this pass
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
