@@ -18,6 +18,25 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+int stream_scratch_alloc(void** ptr, size_t bytes, cudaStream_t st) {
+    static std::once_flag once;
+    std::call_once(once, [] {
+        int dev = 0;
+        cudaMemPool_t pool;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = 1ull << 30;  // freed blocks stay in the pool: steady-state calls never reach the OS allocator
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        }
+    });
+    cudaError_t e = cudaMallocAsync(ptr, bytes, st);
+    if (e != cudaSuccess) {
+        *ptr = nullptr;
+        set_error("stream-ordered scratch allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    return QNN_OK;
+}
+
 namespace {
 
 bool valid_act(int a) { return a >= QNN_ACT_LINEAR && a <= QNN_ACT_EXPONENTIAL; }

@@ -22,6 +22,9 @@ struct Geom {
 
 void set_error(const char* fmt, ...);
 extern std::atomic<unsigned long long> g_launches;
+// stream-ordered device scratch (cudaMallocAsync on the default pool, which is told once to keep freed blocks);
+// release with cudaFreeAsync on the same stream.  Returns QNN_OK or QNN_E_CUDA (error text set).
+int stream_scratch_alloc(void** ptr, size_t bytes, cudaStream_t st);
 inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
 
 // general (CUDA-core, fp32) kernels: any rank / stride / dilation / padding / data_format
@@ -35,6 +38,7 @@ struct TcPlan {
     int f_tile;       // filters per pass (<= 64)
     int n_ftiles;
     int in_q_pad;     // in_q rounded up to 8
+    int pad_x;        // in_q % 4 != 0: x goes through a channel-padding pre-pass
     int rows_in;      // 128 + (taps-1)*dilation
     int x_stages;
     size_t smem_bytes;

@@ -627,6 +627,24 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     }
 }
 
+// x[rows][4][in_q] -> xp[rows][4][xq] (xq = in_q rounded up to 4, new channels zero): one thread per output float4
+__global__ void __launch_bounds__(256) k_pad_x(const float* __restrict__ x, float4* __restrict__ xp, long long rows, int in_q,
+                                               int xq) {
+    const int n4 = xq >> 2;
+    const long long total = rows * 4 * n4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int q0 = (int)(i % n4) * 4;
+        const long long ra = i / n4;  // row * 4 + component
+        const float* src = x + ra * in_q + q0;
+        float4 o;
+        o.x = __ldg(src);  // q0 < in_q always (xq - in_q < 4)
+        o.y = q0 + 1 < in_q ? __ldg(src + 1) : 0.f;
+        o.z = q0 + 2 < in_q ? __ldg(src + 2) : 0.f;
+        o.w = q0 + 3 < in_q ? __ldg(src + 3) : 0.f;
+        xp[i] = o;
+    }
+}
+
 int num_sms() {
     static int n = 0;
     if (!n) {
@@ -668,7 +686,9 @@ TcPlan tc_plan(const Geom& g, int rank) {
     if (g.channels_first) return no("channels_first layout");
     if (rank != 1) return no("rank > 1");
     if (g.s[2] != 1) return no("stride != 1");
-    if (g.in_q % 4) return no("in_q not a multiple of 4 (TMA stride alignment)");
+    if (g.in_q < 4) return no("fewer than 4 quaternion input channels (contraction too short for the tensor cores)");
+    // in_q % 4 != 0: the component blocks of x do not start on 16-byte boundaries (TMA needs that), so x goes through a
+    // channel-padding pre-pass first (tc_forward); the stored kernel needs no padding (its box zero-fills the rows)
     if (g.F % 16) return no("filters not a multiple of 16");
     const int taps = g.k[2];
     const int rows_in = kTileM + (taps - 1) * g.d[2];
@@ -696,6 +716,7 @@ TcPlan tc_plan(const Geom& g, int rank) {
     pl.f_tile = f_tile;
     pl.n_ftiles = g.F / f_tile;
     pl.in_q_pad = in_q_pad;
+    pl.pad_x = (g.in_q % 4) ? 1 : 0;
     pl.rows_in = rows_in;
     pl.x_stages = stages;
     pl.smem_bytes = fixed + (size_t)stages * stage;
@@ -714,6 +735,24 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
         return QNN_E_UNSUPPORTED;
     }
     const int L = g.in_sp[2], Lo = g.out_sp[2];
+    // ragged channel count: pad x to a multiple of 4 channels per component in a stream-ordered scratch
+    const int xq = (g.in_q + 3) & ~3;
+    float* xp = nullptr;
+    if (pl.pad_x) {
+        const long long rows = (long long)g.batch * L;
+        int rc = stream_scratch_alloc(reinterpret_cast<void**>(&xp), (size_t)rows * 4 * xq * sizeof(float), st);
+        if (rc) return rc;
+        const long long total = rows * xq;
+        k_pad_x<<<(unsigned)std::min<long long>((total + 255) / 256, 16LL * num_sms()), 256, 0, st>>>(
+            x, reinterpret_cast<float4*>(xp), rows, g.in_q, xq);
+        count_launch();
+        x = xp;
+    }
+    struct FreeOnExit {
+        float* p;
+        cudaStream_t st;
+        ~FreeOnExit() { if (p) cudaFreeAsync(p, st); }
+    } free_xp{xp, st};
     TcParams p{};
     p.tiles_per_seq = (Lo + kTileM - 1) / kTileM;
     const long long nt = (long long)g.batch * p.tiles_per_seq;
@@ -727,10 +766,10 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     p.pad_lo = g.pad_lo[2];
     p.in_q = g.in_q;
     p.in_q_pad = pl.in_q_pad;
-    p.flat = (g.in_q % 8 == 0) ? 1 : 0;
+    p.flat = (xq % 8 == 0) ? 1 : 0;
     p.n_chunks = (pl.in_q_pad + 31) / 32;
-    p.m8 = g.in_q / 8;
-    p.n_stages = p.flat ? g.in_q / 8 : 4 * p.n_chunks;
+    p.m8 = xq / 8;
+    p.n_stages = p.flat ? xq / 8 : 4 * p.n_chunks;
     p.F = g.F;
     p.f_tile = pl.f_tile;
     p.n_ftiles = pl.n_ftiles;
@@ -756,8 +795,8 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
         }
     }
     if (p.flat) {
-        const uint64_t dims[3] = {(uint64_t)g.in_q * 4, (uint64_t)L, (uint64_t)g.batch};
-        const uint64_t str[2] = {(uint64_t)g.in_q * 16, (uint64_t)L * g.in_q * 16};
+        const uint64_t dims[3] = {(uint64_t)xq * 4, (uint64_t)L, (uint64_t)g.batch};
+        const uint64_t str[2] = {(uint64_t)xq * 16, (uint64_t)L * xq * 16};
         const uint32_t box[3] = {32, (uint32_t)pl.rows_in, 1};
         int e = make_tmap_f32(&tmx, x, 3, dims, str, box, true);
         if (e) {
@@ -765,8 +804,8 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
             return QNN_E_CUDA;
         }
     } else {
-        const uint64_t dims[4] = {(uint64_t)g.in_q, 4, (uint64_t)L, (uint64_t)g.batch};
-        const uint64_t str[3] = {(uint64_t)g.in_q * 4, (uint64_t)g.in_q * 16, (uint64_t)L * g.in_q * 16};
+        const uint64_t dims[4] = {(uint64_t)xq, 4, (uint64_t)L, (uint64_t)g.batch};
+        const uint64_t str[3] = {(uint64_t)xq * 4, (uint64_t)xq * 16, (uint64_t)L * xq * 16};
         const uint32_t box[4] = {32, 1, (uint32_t)pl.rows_in, 1};
         int e = make_tmap_f32(&tmx, x, 4, dims, str, box, true);
         if (e) {

@@ -576,27 +576,14 @@ int tc2d_forward(const Geom& g, int rank, const float* x, const float* w, const 
             configured[n_configured++] = kern;
         }
     }
-    // sub-filter pre-pass into a stream-ordered scratch (same size as the stored kernel; freed after the main kernel).
-    // The device's default pool keeps freed blocks (release threshold raised once), so steady-state calls do not go
-    // back to the OS allocator.
-    {
-        static std::once_flag once;
-        std::call_once(once, [] {
-            int dev = 0;
-            cudaMemPool_t pool;
-            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                uint64_t keep = 64ull << 20;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-        });
-    }
+    // sub-filter pre-pass into a stream-ordered scratch (same size as the stored kernel; freed after the main kernel)
     const size_t wp_bytes = (size_t)p.taps * Q * 4 * F * sizeof(float);
     float* wp = nullptr;
-    cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&wp), wp_bytes, st);
-    if (e != cudaSuccess) {
-        set_error("stream-ordered scratch allocation of %zu bytes failed: %s", wp_bytes, cudaGetErrorString(e));
-        return QNN_E_CUDA;
+    {
+        int rc = stream_scratch_alloc(reinterpret_cast<void**>(&wp), wp_bytes, st);
+        if (rc) return rc;
     }
+    cudaError_t e;
     {
         const int total = pl.n_ftiles * p.n_qc * p.taps * 8 * pl.f_tile;
         k_pack_w2d<<<std::min((total + 255) / 256, 4 * num_sms()), 256, 0, st>>>(w, reinterpret_cast<float4*>(wp), p.taps, Q,

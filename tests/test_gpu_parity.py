@@ -92,8 +92,15 @@ def test_conv_forward_vs_reference_golden(cnn, golden, monkeypatch, case, algo):
     layer.set_weights(weights)
     y = layer(x)
     assert y.is_cuda and y.dtype == torch.float32
-    if algo == "auto" and "_tc_" in name:
-        k = conv_kwargs(rank, kw)
+    from complexnn import _native
+    k = conv_kwargs(rank, kw)
+    cf = k["data_format"] == "channels_first"
+    desc = _native.make_conv_desc(rank, xs[0], xs[2:] if cf else xs[1:-1], xs[1 if cf else -1] // 4, filters,
+                                  (ksz,) * rank if isinstance(ksz, int) else ksz, k["strides"], k["dilation_rate"],
+                                  k["padding"], k["data_format"], k["activation"])
+    uses_tc = _native.lib().qnn_conv_uses_tensor_cores(ctypes.byref(desc)) == 1
+    assert uses_tc or "_tc_" not in name
+    if algo == "auto" and uses_tc:
         bound = O.qconv_abs_bound(g[name + ".x"], g[name + ".kernel"], filters, k["strides"], k["padding"],
                                   k["data_format"], k["dilation_rate"])
         check_tf32(y.cpu().numpy(), g[name + ".y"], bound, name)
@@ -117,7 +124,10 @@ def test_dense_forward_vs_reference_golden(cnn, golden, monkeypatch, case, algo)
     layer.built = True
     layer.set_weights([g[name + ".kernel"]] + ([g[name + ".bias"]] if name + ".bias" in g else []))
     y = layer(dev(g[name + ".x"]))
-    if algo == "auto" and name.startswith("d_tc_"):
+    from complexnn import _native
+    uses_tc = _native.lib().qnn_dense_uses_tensor_cores(xs[0], xs[1] // 4, units // 4) == 1
+    assert uses_tc or not name.startswith("d_tc_")
+    if algo == "auto" and uses_tc:
         check_tf32(y.cpu().numpy(), g[name + ".y"], O.qdense_abs_bound(g[name + ".x"], g[name + ".kernel"], units), name)
     else:
         check(y.cpu().numpy(), g[name + ".y"], FP32_TOL, name)
@@ -152,8 +162,8 @@ def _tc_shapes():
     lib = _native.lib()
     rng = np.random.default_rng(42)
     out = []
-    while len(out) < 32:
-        in_q = int(rng.choice([4, 8, 12, 20, 32, 40, 64, 100]))
+    while len(out) < 40:
+        in_q = int(rng.choice([4, 5, 8, 12, 20, 32, 40, 41, 64, 100]))
         F = int(rng.choice([16, 32, 48, 64, 128, 192]))
         k = int(rng.integers(1, 6))
         d = int(rng.integers(1, 4))
@@ -191,7 +201,7 @@ def test_tensor_core_conv1d_random_shapes_vs_oracle(cnn, native_lib, shape):
 
 
 @pytest.mark.parametrize("rows,in_q,units", [(1, 4, 64), (127, 8, 128), (129, 40, 256), (1000, 128, 512), (333, 64, 768),
-                                             (4096, 36, 192)])
+                                             (4096, 36, 192), (325, 250, 512), (77, 41, 64), (5, 6, 128)])
 def test_tensor_core_dense_vs_oracle(cnn, native_lib, rows, in_q, units):
     from complexnn import _ops
     from complexnn._layer import Variable
@@ -207,9 +217,12 @@ def test_tensor_core_dense_vs_oracle(cnn, native_lib, rows, in_q, units):
 def test_tensor_algo_refuses_unsupported_shapes(cnn):
     from complexnn import _ops
     from complexnn._layer import Variable
-    x = dev(np.zeros((2, 10, 12), np.float32))          # in_q = 3: not a multiple of 4
+    x = dev(np.zeros((2, 10, 12), np.float32))          # stride 2 is outside the tensor-core kernel
     with pytest.raises(NotImplementedError, match="tensor-core kernel"):
-        _ops.conv_forward(x, Variable(np.zeros((3, 3, 64), np.float32)), None, 16, (3,), (1,), "same", "channels_last",
+        _ops.conv_forward(x, Variable(np.zeros((3, 3, 64), np.float32)), None, 16, (3,), (2,), "same", "channels_last",
+                          (1,), "relu", algo="tensor")
+    with pytest.raises(NotImplementedError, match="tensor-core kernel"):   # filters not a multiple of 16
+        _ops.conv_forward(x, Variable(np.zeros((3, 3, 40), np.float32)), None, 10, (3,), (1,), "same", "channels_last",
                           (1,), "relu", algo="tensor")
 
 
@@ -389,7 +402,8 @@ def test_empty_batch_and_short_sequences(cnn):
 
 def test_baseline_config3_stack_vs_oracle(cnn):
     """BASELINE.json configs[2] (as worded): 3 x QuaternionConv1D(64, 3, same, relu) + 2 x QuaternionDense(256, relu) on
-    TIMIT-shaped input [B, T, 4*41]; the first layer (in_q = 41) runs on the general kernel, the rest on tensor cores.
+    TIMIT-shaped input [B, T, 4*41]; the first layer (in_q = 41) goes through the channel-padding pre-pass, all five
+    layers run on tensor cores.
     Checked layer by layer against the oracle fed with the GPU's own previous activations (so errors do not compound
     through relu masks) and end to end in the Frobenius norm."""
     rng = np.random.default_rng(5)

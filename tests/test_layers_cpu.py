@@ -235,7 +235,10 @@ def test_abi_argument_errors_and_kernel_selection(native_lib):
     cfg2 = _native.make_conv_desc(1, 256, (256,), 40, 64, (3,), (1,), (1,), "same", "channels_last", "relu")
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cfg2)) == 1
     assert native_lib.qnn_dense_uses_tensor_cores(65536, 40, 64) == 1
-    assert native_lib.qnn_dense_uses_tensor_cores(32, 250, 128) == 0          # DECODA first layer: in_q % 4 != 0
+    assert native_lib.qnn_dense_uses_tensor_cores(32, 250, 128) == 1          # DECODA first layer: in_q % 4 != 0 -> padding pre-pass
+    assert native_lib.qnn_dense_uses_tensor_cores(32, 250, 100) == 0          # q_units % 16 != 0
+    tim = _native.make_conv_desc(1, 256, (256,), 41, 64, (3,), (1,), (1,), "same", "channels_last", "relu")
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(tim)) == 1      # cfg 3 first layer (TIMIT, in_q = 41)
     s2 = _native.make_conv_desc(1, 8, (64,), 40, 64, (3,), (2,), (1,), "same", "channels_last", "relu")
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(s2)) == 0
     cf = _native.make_conv_desc(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")
