@@ -104,12 +104,15 @@ QNN_API int qnn_dense_forward(int64_t rows, int32_t in_q, int32_t q_units, const
 /* Gradients TF autodiff derives from the same graph.  `y` is the forward output (needed for the
  * activation derivative; only LINEAR and RELU are differentiable here).  Any of dx / dkernel / dbias may be NULL to
  * skip it.  dkernel / dbias are OVERWRITTEN (not accumulated) and have the stored-kernel / bias shapes, so they can
- * point into a flat gradient bucket that qnn_allreduce_f32 then reduces. */
+ * point into a flat gradient bucket that qnn_allreduce_f32 then reduces.
+ * math / algo as in the forward: under TF32 + AUTO the data gradient of a channels_last rank-1 / dense layer runs on
+ * the tensor cores (the forward kernel on dz with the transposed, tap-flipped stored kernel); FP32 or GENERAL selects
+ * the CUDA-core kernels. */
 QNN_API int qnn_conv_backward(const qnn_conv_desc* d, const float* x, const float* kernel, const float* y, const float* dy,
                       float* dx, float* dkernel, float* dbias, void* stream);
 QNN_API int qnn_dense_backward(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
-                       const float* y, const float* dy, int32_t activation, float* dx, float* dkernel, float* dbias,
-                       void* stream);
+                       const float* y, const float* dy, int32_t activation, int32_t math, int32_t algo, float* dx,
+                       float* dkernel, float* dbias, void* stream);
 
 /* Host-buffer convenience (the end-to-end call a non-CUDA caller makes): pageable or pinned HOST pointers in, HOST
  * result out; the library stages through its own device scratch on `stream` and returns after the result landed. */

@@ -38,7 +38,7 @@ SIGNATURES = {
                                          ctypes.c_int32, ctypes.c_int32, _P, _P]),
     "qnn_conv_backward": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "qnn_dense_backward": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P,
-                                          ctypes.c_int32, _P, _P, _P, _P]),
+                                          ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P]),
     "qnn_conv_forward_host": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
     "qnn_dense_forward_host": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P,
                                               ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P]),

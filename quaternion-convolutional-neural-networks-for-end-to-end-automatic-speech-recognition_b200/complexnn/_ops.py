@@ -134,7 +134,7 @@ def _grad_out(like_shape, out, device):
 
 
 def conv_backward(x, y, dy, kernel, has_bias, filters, kernel_size, strides, padding, data_format, dilation_rate,
-                  activation, need_dx=True, dkernel_out=None, dbias_out=None):
+                  activation, need_dx=True, dkernel_out=None, dbias_out=None, math=None, algo=None):
     """Gradients of the quaternion convolution (device tensors only).  Returns (dx | None, dkernel, dbias | None);
     dkernel_out / dbias_out may be views into a flat gradient bucket."""
     import torch
@@ -145,7 +145,7 @@ def conv_backward(x, y, dy, kernel, has_bias, filters, kernel_size, strides, pad
     in_q = shape[c_axis] // 4
     space = shape[2:] if data_format == "channels_first" else shape[1:-1]
     desc = _native.make_conv_desc(rank, shape[0], space, in_q, filters, kernel_size, strides, dilation_rate, padding,
-                                  data_format, activation)
+                                  data_format, activation, math or default_math(), algo or default_algo())
     x, y, dy = x.contiguous(), y.contiguous(), dy.contiguous()
     dx = torch.empty_like(x) if need_dx else None
     dk = _grad_out(tuple(kernel.shape), dkernel_out, x.device)
@@ -157,7 +157,8 @@ def conv_backward(x, y, dy, kernel, has_bias, filters, kernel_size, strides, pad
     return dx, dk, db
 
 
-def dense_backward(x, y, dy, kernel, has_bias, units, activation, need_dx=True, dkernel_out=None, dbias_out=None):
+def dense_backward(x, y, dy, kernel, has_bias, units, activation, need_dx=True, dkernel_out=None, dbias_out=None,
+                   math=None, algo=None):
     import torch
     lib = _native.lib()
     rows, in_q, q_units = int(x.shape[0]), int(x.shape[1]) // 4, units // 4
@@ -167,6 +168,7 @@ def dense_backward(x, y, dy, kernel, has_bias, units, activation, need_dx=True, 
     db = _grad_out((units,), dbias_out, x.device) if has_bias else None
     with torch.cuda.device(x.device):
         _native.check(lib.qnn_dense_backward(rows, in_q, q_units, _dev_ptr(x), _dev_ptr(kernel.device(x.device)),
-                                             _dev_ptr(y), _dev_ptr(dy), _native.ACT[activation], _dev_ptr(dx),
-                                             _dev_ptr(dk), _dev_ptr(db), _stream()))
+                                             _dev_ptr(y), _dev_ptr(dy), _native.ACT[activation],
+                                             _native.MATH[math or default_math()], _native.ALGO[algo or default_algo()],
+                                             _dev_ptr(dx), _dev_ptr(dk), _dev_ptr(db), _stream()))
     return dx, dk, db

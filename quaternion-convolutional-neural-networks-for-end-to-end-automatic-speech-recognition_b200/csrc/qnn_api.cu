@@ -174,6 +174,65 @@ int run_forward(const Geom& g, int rank, int math, int algo, const float* x, con
     return general_forward(g, x, w, bias, y, st);
 }
 
+// Backward.  Tensor-core path (channels_last rank 1 / dense, stride 1, shapes the forward kernel takes with the roles of
+// in_q and filters swapped): one pass makes dz = dy * act'(y) and the bias gradient, the data gradient is the SAME fused
+// Hamilton kernel run on dz with the transposed, tap-flipped stored kernel and the transposed sign table;
+// the kernel gradient folds the 16 blocks into the 4 stored sub-filters on CUDA cores (general wgrad kernel).
+int run_backward(const Geom& g, int rank, int math, int algo, const float* x, const float* w, const float* y,
+                 const float* dy, float* dx, float* dw, float* db, cudaStream_t st) {
+    if (math != QNN_MATH_TF32 && math != QNN_MATH_FP32 && math != QNN_MATH_3XTF32) {
+        set_error("unknown math mode %d", math);
+        return QNN_E_INVALID;
+    }
+    if (algo != QNN_ALGO_AUTO && algo != QNN_ALGO_GENERAL && algo != QNN_ALGO_TENSOR) {
+        set_error("unknown algo %d", algo);
+        return QNN_E_INVALID;
+    }
+    Geom gt = g;  // the transposed convolution: dz [batch, Lo, 4F] -> dx [batch, L, 4 in_q]
+    gt.in_q = g.F;
+    gt.F = g.in_q;
+    gt.in_sp[2] = g.out_sp[2];
+    gt.out_sp[2] = g.in_sp[2];
+    gt.pad_lo[2] = (g.k[2] - 1) * g.d[2] - g.pad_lo[2];
+    gt.act = QNN_ACT_LINEAR;
+    gt.conj_w = g.conj_w ? 0 : 1;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) |
+                           reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
+    const bool tc_ok = math == QNN_MATH_TF32 && algo != QNN_ALGO_GENERAL && !g.channels_first && rank == 1 && aligned &&
+                       !empty_out(g) && g.in_sp[2] > 0 && dx != nullptr && tc_plan(gt, 1).ok;
+    if (!tc_ok) {
+        if (algo == QNN_ALGO_TENSOR) {
+            set_error("tensor-core backward does not take this problem (needs dx, channels_last rank 1 / dense, stride 1, "
+                      "in_q %% 16 == 0): %s", tc_plan(gt, 1).why ? tc_plan(gt, 1).why : "");
+            return QNN_E_UNSUPPORTED;
+        }
+        return general_backward(g, x, w, y, dy, dx, dw, db, st);
+    }
+    const long long rows = (long long)g.batch * g.out_sp[2];
+    const int C = 4 * g.F, taps = g.k[2];
+    const bool relu = g.act == QNN_ACT_RELU;
+    float* dz = nullptr;
+    float* wt = nullptr;
+    int rc = QNN_OK;
+    if (relu && (rc = stream_scratch_alloc(reinterpret_cast<void**>(&dz), (size_t)rows * C * sizeof(float), st))) return rc;
+    if ((rc = stream_scratch_alloc(reinterpret_cast<void**>(&wt), (size_t)taps * g.in_q * C * sizeof(float), st))) {
+        if (dz) cudaFreeAsync(dz, st);
+        return rc;
+    }
+    const float* dzc = relu ? dz : dy;
+    if (relu || db) rc = dz_bgrad(y, dy, dz, db, rows, C, relu ? 1 : 0, st);
+    if (!rc) rc = transpose_w(w, wt, taps, g.in_q, g.F, st);
+    if (!rc) rc = tc_forward(gt, 1, dzc, wt, nullptr, dx, st);
+    if (!rc && dw) {
+        Geom gl = g;
+        gl.act = QNN_ACT_LINEAR;  // dz already carries the activation derivative
+        rc = general_backward(gl, x, w, dzc, dzc, nullptr, dw, nullptr, st);
+    }
+    if (dz) cudaFreeAsync(dz, st);
+    cudaFreeAsync(wt, st);
+    return rc;
+}
+
 // ---------------------------------------------------------------- device scratch for the *_host entry points
 struct Scratch {
     std::mutex mu;
@@ -396,12 +455,13 @@ int qnn_conv_backward(const qnn_conv_desc* d, const float* x, const float* kerne
         set_error("x, kernel, y and dy must not be NULL");
         return QNN_E_INVALID;
     }
-    return general_backward(g, x, kernel, y, dy, dx, dkernel, dbias, static_cast<cudaStream_t>(stream));
+    return run_backward(g, d->rank, d->math, d->algo, x, kernel, y, dy, dx, dkernel, dbias,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int qnn_dense_backward(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
-                       const float* y, const float* dy, int32_t activation, float* dx, float* dkernel, float* dbias,
-                       void* stream) {
+                       const float* y, const float* dy, int32_t activation, int32_t math, int32_t algo, float* dx,
+                       float* dkernel, float* dbias, void* stream) {
     Geom g;
     int rc = build_dense_geom(rows, in_q, q_units, activation, &g);
     if (rc) return rc;
@@ -413,7 +473,7 @@ int qnn_dense_backward(int64_t rows, int32_t in_q, int32_t q_units, const float*
         set_error("x, kernel, y and dy must not be NULL");
         return QNN_E_INVALID;
     }
-    return general_backward(g, x, kernel, y, dy, dx, dkernel, dbias, static_cast<cudaStream_t>(stream));
+    return run_backward(g, 1, math, algo, x, kernel, y, dy, dx, dkernel, dbias, static_cast<cudaStream_t>(stream));
 }
 
 int qnn_conv_forward_host(const qnn_conv_desc* d, const float* x_host, const float* kernel_host,

@@ -32,6 +32,11 @@ int general_forward(const Geom& g, const float* x, const float* w, const float* 
 int general_backward(const Geom& g, const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw,
                      float* db, cudaStream_t st);
 
+// helpers of the tensor-core backward path: dz = dy * act'(y) with the bias gradient folded in (either output may be
+// NULL), and the transposed / tap-flipped stored kernel the dgrad convolution consumes
+int dz_bgrad(const float* y, const float* dy, float* dz, float* db, long long rows, int C, int relu, cudaStream_t st);
+int transpose_w(const float* w, float* wt, int taps, int Q, int F, cudaStream_t st);
+
 // tensor-core kernel (tcgen05 / TMEM / TMA): channels_last rows with taps along the innermost spatial axis
 struct TcPlan {
     int ok;           // shape qualifies

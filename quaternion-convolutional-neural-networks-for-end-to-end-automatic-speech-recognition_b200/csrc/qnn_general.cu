@@ -3,6 +3,7 @@
 // three gradients -- without ever forming the 4C_in x 4C_out expanded weight: each thread carries one quaternion
 // accumulator and applies the Hamilton product directly on the four stored sub-filters.
 // They are the fallback for shapes the tensor-core kernel (qnn_hamilton_tc.cu) does not take.
+#include <algorithm>
 #include "qnn_common.h"
 
 namespace qnn {
@@ -225,6 +226,71 @@ __global__ void __launch_bounds__(256) k_general_bgrad(Geom g, const float* __re
     atomicAdd(db + c, acc);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// helpers of the tensor-core backward path (channels_last rows x C, C = 4F)
+// ---------------------------------------------------------------------------------------------------------------------
+// dz = dy * act'(y) (relu: y > 0) and dbias[c] += sum over rows of dz[., c] in ONE pass over (y, dy).
+// blockDim = (bx, by): bx float4-columns (looped when C/4 > bx), by row lanes; grid.x = row chunks.
+__global__ void __launch_bounds__(256) k_dz_bgrad(const float4* __restrict__ y, const float4* __restrict__ dy,
+                                                  float4* __restrict__ dz, float* __restrict__ db, long long rows, int C4,
+                                                  int relu) {
+    extern __shared__ float4 red[];  // [by][bx]
+    const long long per = (rows + gridDim.x - 1) / gridDim.x;
+    const long long r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
+    for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long long r = r0 + threadIdx.y; r < r1; r += blockDim.y) {
+            const long long o = r * C4 + c4;
+            float4 g = __ldg(dy + o);
+            if (relu) {
+                const float4 v = __ldg(y + o);
+                g.x = v.x > 0.f ? g.x : 0.f;
+                g.y = v.y > 0.f ? g.y : 0.f;
+                g.z = v.z > 0.f ? g.z : 0.f;
+                g.w = v.w > 0.f ? g.w : 0.f;
+            }
+            if (dz) dz[o] = g;
+            acc.x += g.x;
+            acc.y += g.y;
+            acc.z += g.z;
+            acc.w += g.w;
+        }
+        if (db) {
+            red[threadIdx.y * blockDim.x + threadIdx.x] = acc;
+            __syncthreads();
+            if (threadIdx.y == 0) {
+                for (int j = 1; j < (int)blockDim.y; ++j) {
+                    const float4 o = red[j * blockDim.x + threadIdx.x];
+                    acc.x += o.x;
+                    acc.y += o.y;
+                    acc.z += o.z;
+                    acc.w += o.w;
+                }
+                atomicAdd(db + 4 * c4 + 0, acc.x);
+                atomicAdd(db + 4 * c4 + 1, acc.y);
+                atomicAdd(db + 4 * c4 + 2, acc.z);
+                atomicAdd(db + 4 * c4 + 3, acc.w);
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// wt[taps-1-tap][f][c][q] = w[tap][q][c][f]: the stored kernel of the TRANSPOSED convolution (dgrad), still un-expanded
+__global__ void __launch_bounds__(256) k_transpose_w(const float* __restrict__ w, float* __restrict__ wt, int taps, int Q,
+                                                     int F) {
+    const int total = taps * Q * 4 * F;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        int t = i;
+        const int q = t % Q;
+        t /= Q;
+        const int c = t & 3;
+        t >>= 2;
+        const int f = t % F, tap_t = t / F;
+        wt[i] = __ldg(w + (((size_t)(taps - 1 - tap_t) * Q + q) * 4 + c) * F + f);
+    }
+}
+
 inline int grid_for(int64_t total, int block) {
     int64_t b = (total + block - 1) / block;
     const int64_t cap = 148LL * 16;
@@ -242,6 +308,47 @@ int general_forward(const Geom& g, const float* x, const float* w, const float* 
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("general forward launch failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    return QNN_OK;
+}
+
+int dz_bgrad(const float* y, const float* dy, float* dz, float* db, long long rows, int C, int relu, cudaStream_t st) {
+    if (C % 4) {
+        set_error("dz_bgrad needs a channel count that is a multiple of 4");
+        return QNN_E_INVALID;
+    }
+    cudaError_t e;
+    if (db && (e = cudaMemsetAsync(db, 0, (size_t)C * sizeof(float), st)) != cudaSuccess) {
+        set_error("dbias memset failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    if (rows == 0) return QNN_OK;
+    const int C4 = C / 4;
+    int bx = 1;
+    while (bx * 2 <= C4 && bx * 2 <= 256) bx *= 2;  // power of two <= min(C/4, 256); wider rows loop over columns
+    if (C4 <= 256 && 256 % C4 == 0) bx = C4;
+    const int by = std::max(1, 256 / bx);
+    const int grid = (int)std::min<long long>((rows + by - 1) / by, 148 * 8);
+    k_dz_bgrad<<<grid, dim3(bx, by), (size_t)bx * by * sizeof(float4), st>>>(
+        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(dy), reinterpret_cast<float4*>(dz), db, rows, C4,
+        relu);
+    count_launch();
+    e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("dz/bgrad launch failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    return QNN_OK;
+}
+
+int transpose_w(const float* w, float* wt, int taps, int Q, int F, cudaStream_t st) {
+    const int total = taps * Q * 4 * F;
+    k_transpose_w<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(w, wt, taps, Q, F);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("kernel transpose launch failed: %s", cudaGetErrorString(e));
         return QNN_E_CUDA;
     }
     return QNN_OK;

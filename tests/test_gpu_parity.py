@@ -518,3 +518,58 @@ def test_baseline_config5_conv2d_slice_and_properties(cnn):
     finally:
         del os.environ["QNN_ALGO"], os.environ["QNN_MATH"]
     assert float((yg - yf[:1]).norm() / yg.norm()) < TF32_TOL
+
+
+TC_BWD_CASES = [
+    # name, x shape (channels_last), F, k, d, pad, act
+    ("cfg3_layer2_slice", (4, 200, 256), 64, 3, 1, "same", "relu"),
+    ("valid_k5_d2_linear", (2, 150, 64), 16, 5, 2, "valid", "linear"),
+    ("causal_k2_relu", (3, 131, 128), 48, 2, 3, "causal", "relu"),
+    ("ragged_F", (2, 130, 192), 20, 3, 1, "same", "relu"),       # F = 20 -> dgrad's x needs the channel-padding pre-pass
+]
+
+
+@pytest.mark.parametrize("name,xs,F,k,d,pad,act", TC_BWD_CASES, ids=[c[0] for c in TC_BWD_CASES])
+def test_tensor_core_dgrad_conv1d_vs_oracle(cnn, name, xs, F, k, d, pad, act):
+    """Data gradient on the tensor cores: the forward kernel run on dz = dy * act'(y) with the transposed, tap-flipped
+    stored kernel and the transposed sign table.  TF32 tolerance (1e-3 normwise, 2e-3 of the largest
+    element); kernel / bias gradients stay fp32 (1e-4).  The relu mask comes from the GPU's own forward output."""
+    from complexnn import _ops
+    from complexnn._layer import Variable
+    rng = np.random.default_rng(len(name))
+    in_q = xs[-1] // 4
+    x = rng.normal(size=xs).astype(np.float32)
+    kern = (rng.normal(size=(k, in_q, 4 * F)) / np.sqrt(4 * in_q * k)).astype(np.float32)
+    bias = rng.normal(0, 0.1, 4 * F).astype(np.float32)
+    xd, kv, bv = dev(x), Variable(kern), Variable(bias)
+    y = _ops.conv_forward(xd, kv, bv, F, (k,), (1,), pad, "channels_last", (d,), act, math="fp32", algo="general")
+    dy = rng.normal(size=tuple(y.shape)).astype(np.float32)
+    args = (xd, y, dev(dy), kv, True, F, (k,), (1,), pad, "channels_last", (d,), act)
+    dx, dk, db = _ops.conv_backward(*args, math="tf32", algo="tensor")
+    gx, gk, gb = _ops.conv_backward(*args, math="fp32", algo="general")
+    rdx, rdk, rdb = O.qconv_backward(x, kern, bias, F, (1,), pad, "channels_last", (d,), act, dy)
+    emax, efro = errs(dx.cpu().numpy(), rdx)
+    assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "dx: max-rel %.3e fro-rel %.3e" % (emax, efro)
+    check(gx.cpu().numpy(), rdx, 1e-4, "general dx")
+    check(dk.cpu().numpy(), rdk, 1e-4, "dkernel")
+    check(db.cpu().numpy(), rdb, 1e-4, "dbias")
+    check(gk.cpu().numpy(), rdk, 1e-4, "general dkernel")
+
+
+@pytest.mark.parametrize("rows,in_q,units,act", [(300, 64, 256, "relu"), (1000, 128, 64, "linear"), (77, 16, 512, "relu")])
+def test_tensor_core_dgrad_dense_vs_oracle(cnn, rows, in_q, units, act):
+    from complexnn import _ops
+    from complexnn._layer import Variable
+    rng = np.random.default_rng(rows)
+    x = rng.normal(size=(rows, 4 * in_q)).astype(np.float32)
+    kern = (rng.normal(size=(in_q, units)) / np.sqrt(4 * in_q)).astype(np.float32)
+    bias = rng.normal(0, 0.1, units).astype(np.float32)
+    xd, kv = dev(x), Variable(kern)
+    y = _ops.dense_forward(xd, kv, Variable(bias), units, act, math="fp32", algo="general")
+    dy = rng.normal(size=(rows, units)).astype(np.float32)
+    dx, dk, db = _ops.dense_backward(xd, y, dev(dy), kv, True, units, act, math="tf32", algo="tensor")
+    rdx, rdk, rdb = O.qdense_backward(x, kern, bias, units, act, dy)
+    emax, efro = errs(dx.cpu().numpy(), rdx)
+    assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "dx: max-rel %.3e fro-rel %.3e" % (emax, efro)
+    check(dk.cpu().numpy(), rdk, 1e-4, "dkernel")
+    check(db.cpu().numpy(), rdb, 1e-4, "dbias")
