@@ -174,10 +174,11 @@ int run_forward(const Geom& g, int rank, int math, int algo, const float* x, con
     return general_forward(g, x, w, bias, y, st);
 }
 
-// Backward.  Tensor-core path (channels_last rank 1 / dense, stride 1, shapes the forward kernel takes with the roles of
-// in_q and filters swapped): one pass makes dz = dy * act'(y) and the bias gradient, the data gradient is the SAME fused
-// Hamilton kernel run on dz with the transposed, tap-flipped stored kernel and the transposed sign table;
-// the kernel gradient folds the 16 blocks into the 4 stored sub-filters on CUDA cores (general wgrad kernel).
+// Backward.  Tensor-core path (channels_last rank 1 / dense, stride 1): one pass makes dz = dy * act'(y) and the bias
+// gradient; the data gradient is the SAME fused Hamilton kernel run on dz with the transposed, tap-flipped stored kernel
+// and the transposed sign table; the kernel gradient contracts x with dz over positions on the tensor
+// cores, the 16 blocks folding into the 4 stored sub-filters inside tensor memory (qnn_wgrad_tc.cu).  Whatever a
+// tensor-core kernel does not take falls to the CUDA-core kernels, piece by piece.
 int run_backward(const Geom& g, int rank, int math, int algo, const float* x, const float* w, const float* y,
                  const float* dy, float* dx, float* dw, float* db, cudaStream_t st) {
     if (math != QNN_MATH_TF32 && math != QNN_MATH_FP32 && math != QNN_MATH_3XTF32) {
@@ -196,18 +197,17 @@ int run_backward(const Geom& g, int rank, int math, int algo, const float* x, co
     gt.pad_lo[2] = (g.k[2] - 1) * g.d[2] - g.pad_lo[2];
     gt.act = QNN_ACT_LINEAR;
     gt.conj_w = g.conj_w ? 0 : 1;
-    const bool aligned = ((reinterpret_cast<uintptr_t>(dy) | reinterpret_cast<uintptr_t>(y) |
-                           reinterpret_cast<uintptr_t>(dx)) & 15) == 0;
-    const bool tc_ok = math == QNN_MATH_TF32 && algo != QNN_ALGO_GENERAL && !g.channels_first && rank == 1 && aligned &&
-                       !empty_out(g) && g.in_sp[2] > 0 && dx != nullptr && tc_plan(gt, 1).ok;
-    if (!tc_ok) {
-        if (algo == QNN_ALGO_TENSOR) {
-            set_error("tensor-core backward does not take this problem (needs dx, channels_last rank 1 / dense, stride 1, "
-                      "in_q %% 16 == 0): %s", tc_plan(gt, 1).why ? tc_plan(gt, 1).why : "");
-            return QNN_E_UNSUPPORTED;
-        }
-        return general_backward(g, x, w, y, dy, dx, dw, db, st);
+    auto al16 = [](const void* a) { return (reinterpret_cast<uintptr_t>(a) & 15) == 0; };
+    const bool tc_base = math == QNN_MATH_TF32 && algo != QNN_ALGO_GENERAL && !g.channels_first && rank == 1 &&
+                         !empty_out(g) && g.in_sp[2] > 0 && al16(dy) && al16(y) && al16(x);
+    const bool tc_dx = tc_base && dx && al16(dx) && tc_plan(gt, 1).ok;
+    const bool tc_dw = tc_base && dw && al16(dw) && wgrad_plan(g, 1).ok;
+    if (algo == QNN_ALGO_TENSOR && ((dx && !tc_dx) || (dw && !tc_dw))) {
+        set_error("tensor-core backward does not take this problem (channels_last rank 1 / dense, stride 1): dx: %s; "
+                  "dkernel: %s", dx ? (tc_dx ? "ok" : tc_plan(gt, 1).why) : "-", dw ? (tc_dw ? "ok" : wgrad_plan(g, 1).why) : "-");
+        return QNN_E_UNSUPPORTED;
     }
+    if (!tc_dx && !tc_dw) return general_backward(g, x, w, y, dy, dx, dw, db, st);
     const long long rows = (long long)g.batch * g.out_sp[2];
     const int C = 4 * g.F, taps = g.k[2];
     const bool relu = g.act == QNN_ACT_RELU;
@@ -215,21 +215,22 @@ int run_backward(const Geom& g, int rank, int math, int algo, const float* x, co
     float* wt = nullptr;
     int rc = QNN_OK;
     if (relu && (rc = stream_scratch_alloc(reinterpret_cast<void**>(&dz), (size_t)rows * C * sizeof(float), st))) return rc;
-    if ((rc = stream_scratch_alloc(reinterpret_cast<void**>(&wt), (size_t)taps * g.in_q * C * sizeof(float), st))) {
-        if (dz) cudaFreeAsync(dz, st);
-        return rc;
-    }
     const float* dzc = relu ? dz : dy;
+    Geom gl = g;
+    gl.act = QNN_ACT_LINEAR;  // dz already carries the activation derivative
     if (relu || db) rc = dz_bgrad(y, dy, dz, db, rows, C, relu ? 1 : 0, st);
-    if (!rc) rc = transpose_w(w, wt, taps, g.in_q, g.F, st);
-    if (!rc) rc = tc_forward(gt, 1, dzc, wt, nullptr, dx, st);
-    if (!rc && dw) {
-        Geom gl = g;
-        gl.act = QNN_ACT_LINEAR;  // dz already carries the activation derivative
-        rc = general_backward(gl, x, w, dzc, dzc, nullptr, dw, nullptr, st);
+    if (!rc && dx) {
+        if (tc_dx) {
+            rc = stream_scratch_alloc(reinterpret_cast<void**>(&wt), (size_t)taps * g.in_q * C * sizeof(float), st);
+            if (!rc) rc = transpose_w(w, wt, taps, g.in_q, g.F, st);
+            if (!rc) rc = tc_forward(gt, 1, dzc, wt, nullptr, dx, st);
+        } else {
+            rc = general_backward(gl, x, w, dzc, dzc, dx, nullptr, nullptr, st);
+        }
     }
+    if (!rc && dw) rc = tc_dw ? wgrad_tc(g, 1, x, dzc, dw, st) : general_backward(gl, x, w, dzc, dzc, nullptr, dw, nullptr, st);
     if (dz) cudaFreeAsync(dz, st);
-    cudaFreeAsync(wt, st);
+    if (wt) cudaFreeAsync(wt, st);
     return rc;
 }
 

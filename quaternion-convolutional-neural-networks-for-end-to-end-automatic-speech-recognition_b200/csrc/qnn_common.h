@@ -51,7 +51,23 @@ struct TcPlan {
 };
 TcPlan tc_plan(const Geom& g, int rank);
 void tc_set_trace(void* device_buffer, size_t bytes);
+// x[rows][4][in_q] -> xp[rows][4][xq], xq = in_q rounded up to 4, new channels zero (ragged channel counts)
+int pad_x_channels(const float* x, float* xp, long long rows, int in_q, int xq, cudaStream_t st);
 int tc_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+
+// tensor-core kernel gradient (channels_last rank 1 / dense, stride 1): contraction over positions, four persistent
+// accumulators D_c = dL/df_c in tensor memory, vector reductions into dW
+struct WgradPlan {
+    int ok;
+    int f_tile, n_ftiles, n_mblk;
+    int rows;  // x stage rows: 32 + (taps - 1) * dilation
+    int pad_x;  // in_q % 4 != 0: x goes through the channel-padding pre-pass
+    int x_stages;
+    size_t x_stage_bytes, smem_bytes;
+    const char* why;
+};
+WgradPlan wgrad_plan(const Geom& g, int rank);
+int wgrad_tc(const Geom& g, int rank, const float* x, const float* dz, float* dw, cudaStream_t st);
 
 // tensor-core kernel for channels_first tensors (rank 1 / 2, stride 1): streamed sub-filters, transposing converters
 struct Tc2dPlan {

@@ -671,6 +671,20 @@ size_t g_trace_bytes = 0;
 
 }  // namespace
 
+int pad_x_channels(const float* x, float* xp, long long rows, int in_q, int xq, cudaStream_t st) {
+    const long long total = rows * xq;
+    if (total == 0) return QNN_OK;
+    k_pad_x<<<(unsigned)std::min<long long>((total + 255) / 256, 16LL * num_sms()), 256, 0, st>>>(
+        x, reinterpret_cast<float4*>(xp), rows, in_q, xq);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("channel padding launch failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    return QNN_OK;
+}
+
 void tc_set_trace(void* device_buffer, size_t bytes) {
     g_trace = static_cast<unsigned long long*>(device_buffer);
     g_trace_bytes = bytes;
@@ -742,10 +756,11 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
         const long long rows = (long long)g.batch * L;
         int rc = stream_scratch_alloc(reinterpret_cast<void**>(&xp), (size_t)rows * 4 * xq * sizeof(float), st);
         if (rc) return rc;
-        const long long total = rows * xq;
-        k_pad_x<<<(unsigned)std::min<long long>((total + 255) / 256, 16LL * num_sms()), 256, 0, st>>>(
-            x, reinterpret_cast<float4*>(xp), rows, g.in_q, xq);
-        count_launch();
+        rc = pad_x_channels(x, xp, rows, g.in_q, xq, st);
+        if (rc) {
+            cudaFreeAsync(xp, st);
+            return rc;
+        }
         x = xp;
     }
     struct FreeOnExit {

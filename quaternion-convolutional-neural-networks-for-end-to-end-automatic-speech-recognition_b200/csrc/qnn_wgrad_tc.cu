@@ -1,0 +1,482 @@
+// Kernel gradient of the quaternion convolution / dense layer on the 5th-generation tensor cores (sm_100a only).
+//
+// What TF autodiff derives from the reference graph (complexnn/conv.py:294-334 -> SURVEY 3.4): the gradient of the
+// expanded 4in_q x 4F weight, folded back through concat / negate / slice into the four stored sub-filters
+//     dL/df_c[tap][q][f] = sum over (a, b) with a xor b = c of  sign(a, b) * sum_pos x_a[pos + tap*dil - pad][q] * dz_b[pos][f].
+// The 16 signed blocks are never formed: per k-step of 8 POSITIONS, 16 tcgen05.mma accumulate straight into FOUR
+// tensor-memory accumulators D_c (rows = (tap, q), columns = f), sign = negate-B bit -- the same 4-operand sharing as
+// the forward kernel with the contraction running over positions instead of channels.
+//
+//   A operand (x^T, rows (tap, q) x 8 positions): converter thread m owns row (tap, q) and gathers its 8 shifted positions
+//       of each input component from the x stage in shared memory (TMA box: 32 + halo rows x all 4*in_q channels),
+//       rounds to nearest tf32 and writes a 32-column A slot in tensor memory (4 components x 8 positions).  The tap
+//       shift is part of the row index, so x is loaded once for all taps.
+//   B operand (dz, 8 positions x f, K-major): the 16 packer warps read dz from global memory (coalesced 16-byte loads,
+//       two sub-tiles in flight), transpose 4 x 4 blocks in registers, round to tf32 and store the core-matrix image
+//       [component][position/4][f][position%4]; rows past the end of a sequence are zeros.
+//   D: persistent for the whole kernel -- a CTA owns one (row block of 128 (tap, q) rows, filter tile) combination and
+//       walks its share of the position sub-tiles; CTAs that own different combinations walk the same sub-tiles at the
+//       same time, so x / dz come from HBM once.  At the end every CTA adds its partial sums into dW with 16-byte
+//       vector reductions (red.global.add.v4.f32).
+// Warps: 0-15 packers then epilogue, 16-19 MMA issuers (one per D_c), 20-27 converters (two groups on alternate
+// k-steps), 28 x producer.  TMEM: [0,256) the four accumulators, [256,512) eight A slots.
+#include <algorithm>
+#include <mutex>
+#include "qnn_common.h"
+#include "qnn_ptx.cuh"
+#include "qnn_tmap.h"
+
+namespace qnn {
+namespace {
+using namespace ptx;
+
+constexpr int kSub = 32;  // positions per sub-tile (4 k-steps of 8)
+constexpr int kThreads = 1024;
+constexpr int kPackThreads = 512;
+constexpr int kSlots = 8;
+constexpr int kSlotCols = 32;
+constexpr int kAccCols = 256;
+constexpr int kBStages = 2;
+constexpr int kMaxXStages = 4;
+constexpr uint32_t kSmemLimit = 232448;
+constexpr int kRegsWg0 = 24, kRegsWg1 = 40, kRegsEpi = 96;
+static_assert(256 * kRegsWg0 + 256 * kRegsWg1 + 512 * kRegsEpi <= 1024 * 64, "register pool");
+
+constexpr uint32_t kNegConv = (1u << 4) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 12) | (1u << 14);
+constexpr uint32_t transpose_bits(uint32_t m) {
+    uint32_t t = 0;
+    for (int a = 0; a < 4; ++a)
+        for (int b = 0; b < 4; ++b)
+            if ((m >> (a * 4 + b)) & 1u) t |= 1u << (b * 4 + a);
+    return t;
+}
+constexpr uint32_t kNegDense = transpose_bits(kNegConv);
+
+enum { kWarpAlloc = 16, kWarpIssuer0 = 16, kWarpConv0 = 20, kWarpProd0 = 28 };
+
+struct WP {
+    int n_units, units_per_seq;  // position sub-tiles: unit -> (sample, t0 = (unit % units_per_seq) * 32)
+    int n_combos, n_ftiles;      // combo = mblk * n_ftiles + ft; CTA b owns combo b % n_combos
+    int taps, dil, pad_lo;
+    int in_q, F, f_tile, R;      // in_q as the kernel sees x (padded to 4); R = taps * in_q rows
+    int in_q_out;                // the layer's real in_q: rows with q >= in_q_out are padding and are not written
+    int Lo;
+    int rows, x_stages, x_stage_bytes;
+    uint32_t b_stage_bytes;
+};
+
+struct __align__(8) Bars {
+    uint64_t x_full[kMaxXStages], x_empty[kMaxXStages];
+    uint64_t a_full[kSlots], a_empty[kSlots];
+    uint64_t b_full[kBStages], b_empty[kBStages];
+    uint64_t acc_full;
+    uint32_t tmem_base;
+};
+
+template <int N>
+__device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
+                                       uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 d;\n\t"
+        "setp.ne.b32 p, %5, 0;\n\t"
+        "mov.b64 d, {%2, %3};\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], d, %4, p;\n\t"
+        "}\n" ::"r"(d_tmem),
+        "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ float4 rn4(float a, float b, float c, float d) {
+    return make_float4(__uint_as_float(__float_as_uint(a) + 0x1000u), __uint_as_float(__float_as_uint(b) + 0x1000u),
+                       __uint_as_float(__float_as_uint(c) + 0x1000u), __uint_as_float(__float_as_uint(d) + 0x1000u));
+}
+
+template <bool CONJ>
+__global__ void __launch_bounds__(kThreads, 1)
+k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const float* __restrict__ dz, float* __restrict__ dw) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* b_s = smem;                                         // kBStages transposed dz sub-tiles
+    uint8_t* x_s = b_s + (size_t)kBStages * p.b_stage_bytes;     // x ring
+    Bars* bars = reinterpret_cast<Bars*>(x_s + (size_t)p.x_stages * p.x_stage_bytes);
+
+    const int tid = threadIdx.x;
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+    const int Ft = p.f_tile;
+    const int combo = (int)(blockIdx.x % (unsigned)p.n_combos);
+    const int cgroup = (int)(blockIdx.x / (unsigned)p.n_combos);  // which share of the units
+    const int n_groups = (int)(gridDim.x / (unsigned)p.n_combos);
+    const int mblk = combo / p.n_ftiles, ft = combo - mblk * p.n_ftiles;
+    // CTAs beyond n_groups * n_combos (grid not a multiple of n_combos) own nothing
+    const int my_units = cgroup < n_groups ? (p.n_units - cgroup + n_groups - 1) / n_groups : 0;
+
+    if (tid == kWarpAlloc * 32) {
+        tma_prefetch_desc(&tmx);
+        for (int i = 0; i < kMaxXStages; ++i) {
+            mbar_init(&bars->x_full[i], 1);
+            mbar_init(&bars->x_empty[i], 256);
+        }
+        for (int i = 0; i < kSlots; ++i) {
+            mbar_init(&bars->a_full[i], 128);
+            mbar_init(&bars->a_empty[i], 4);
+        }
+        for (int i = 0; i < kBStages; ++i) {
+            mbar_init(&bars->b_full[i], kPackThreads);
+            mbar_init(&bars->b_empty[i], 4);
+        }
+        mbar_init(&bars->acc_full, 4);
+        fence_mbar_init();
+    }
+    if (warp == kWarpAlloc) {
+        tmem_alloc(&bars->tmem_base, 512);
+        tmem_relinquish();
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    tc_fence_before_sync();
+    __syncthreads();
+    tc_fence_after_sync();
+    const uint32_t t_acc = bars->tmem_base;
+    const uint32_t t_a = t_acc + kAccCols;
+
+    if (warp >= kWarpProd0) {
+        // =========================== x producer ===========================
+        reg_dealloc<kRegsWg0>();
+        if (warp == kWarpProd0 && elect_one()) {
+            uint32_t xs = 0, xph = 0;
+            for (int i = 0; i < my_units; ++i) {
+                const int unit = cgroup + i * n_groups;
+                const int n = unit / p.units_per_seq, t0 = (unit - n * p.units_per_seq) * kSub;
+                mbar_wait(&bars->x_empty[xs], xph ^ 1);
+                mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)(p.rows * 4 * p.in_q * 4));
+                tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], 0, 0, t0 - p.pad_lo, n);
+                if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
+            }
+        }
+    } else if (warp >= kWarpConv0) {
+        // =========================== converters: x stage -> A slots (rows (tap, q), columns 4 components x 8 positions) ===========================
+        reg_dealloc<kRegsWg1>();
+        const int cgrp = (tid - kWarpConv0 * 32) >> 7;
+        const int m = (tid - kWarpConv0 * 32) & 127;
+        const uint32_t lane_base = (uint32_t)(m & ~31) << 16;
+        const int row = mblk * 128 + m;  // row of dW = tap * in_q + q
+        const bool valid = row < p.R;
+        const int tap = valid ? row / p.in_q : 0, q = valid ? row - tap * p.in_q : 0;
+        const int pitch = 4 * p.in_q;    // floats per x row
+        const int base_off = tap * p.dil * pitch + q;
+        uint32_t xs = 0, xph = 0, as = 0, aph = 0;
+        for (int i = 0; i < my_units; ++i) {
+            mbar_wait(&bars->x_full[xs], xph);
+            const float* xb = reinterpret_cast<const float*>(x_s + (size_t)xs * p.x_stage_bytes) + base_off;
+#pragma unroll 1
+            for (int ks = 0; ks < kSub / 8; ++ks) {
+                if ((ks & 1) == cgrp) {
+                    mbar_wait(&bars->a_empty[as], aph ^ 1);
+                    tc_fence_after_sync();
+                    const float* xk = xb + ks * 8 * pitch;
+                    const uint32_t dst = t_a + lane_base + as * kSlotCols;
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {  // components 2h, 2h+1: 16 columns
+                        uint32_t u[16];
+#pragma unroll
+                        for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+                            for (int j = 0; j < 8; ++j)
+                                u[a2 * 8 + j] = valid ? __float_as_uint(xk[j * pitch + (2 * h + a2) * p.in_q]) + 0x1000u : 0u;
+                        tmem_st16_nc(dst + h * 16, u);
+                    }
+                    tmem_wait_st();
+                    tc_fence_before_sync();
+                    mbar_arrive(&bars->a_full[as]);
+                }
+                if (++as == kSlots) { as = 0; aph ^= 1; }
+            }
+            mbar_arrive(&bars->x_empty[xs]);
+            if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
+        }
+    } else if (warp >= kWarpAlloc) {
+        // =========================== MMA issuers: warp c feeds D_c ===========================
+        reg_dealloc<kRegsWg0>();
+        const bool elected = elect_one();
+        const int c = warp - kWarpIssuer0;
+        const uint32_t idesc_pos = idesc_tf32(128, Ft, false, false);
+        const uint32_t idesc_neg = idesc_tf32(128, Ft, false, true);
+        const uint64_t d0 = smem_desc_kmajor_noswz(smem_u32(b_s), (uint32_t)Ft * 16u, 128);
+        const uint32_t b_lo = (uint32_t)d0, desc_hi = (uint32_t)(d0 >> 32);
+        const uint32_t comp_stride = 8u * Ft;             // 16-byte units between the dz components of a stage
+        const uint32_t kstep_stride = 2u * Ft;            // ... between k-steps (2 position groups of 4)
+        const uint32_t stage_stride = p.b_stage_bytes >> 4;
+        constexpr uint32_t neg_table = CONJ ? kNegDense : kNegConv;
+        uint32_t as = 0, aph = 0, bs = 0, bph = 0, accumulate = 0;
+        for (int i = 0; i < my_units; ++i) {
+            mbar_wait(&bars->b_full[bs], bph);
+            for (int ks = 0; ks < kSub / 8; ++ks) {
+                mbar_wait(&bars->a_full[as], aph);
+                tc_fence_after_sync();
+                if (elected) {
+                    const uint32_t a_col = t_a + as * kSlotCols;
+                    const uint32_t k_lo = b_lo + bs * stage_stride + ks * kstep_stride;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const int b = a ^ c;
+                        mma_ts(t_acc + c * Ft, a_col + a * 8, k_lo + b * comp_stride, desc_hi,
+                               ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos, accumulate);
+                        accumulate = 1;
+                    }
+                    mma_commit(&bars->a_empty[as]);
+                }
+                __syncwarp();
+                if (++as == kSlots) { as = 0; aph ^= 1; }
+            }
+            if (elected) mma_commit(&bars->b_empty[bs]);
+            __syncwarp();
+            if (++bs == kBStages) { bs = 0; bph ^= 1; }
+        }
+        if (elected) mma_commit(&bars->acc_full);
+        __syncwarp();
+    } else {
+        // =========================== packers (dz -> K-major tf32 blocks), then the one epilogue ===========================
+        reg_alloc<kRegsEpi>();
+        const int e = tid;  // 0..511
+        const int f4_per = Ft >> 2;                 // 4-filter groups per component
+        const int blocks = 8 * 4 * f4_per;          // 4x4 blocks per sub-tile (<= 512)
+        const int fg = e % f4_per, bcomp = (e / f4_per) & 3, pg = e / (4 * f4_per);
+        const bool active = e < blocks;
+        const size_t C = (size_t)4 * p.F;
+        const float* col = dz + (size_t)bcomp * p.F + (size_t)ft * Ft + fg * 4;
+        float4* dst0 = reinterpret_cast<float4*>(b_s) + ((bcomp * 8 + pg) * Ft + fg * 4);
+        auto load_unit = [&](int i, float4 (&v)[4]) {
+            const int unit = cgroup + i * n_groups;
+            const int n = unit / p.units_per_seq, t = (unit - n * p.units_per_seq) * kSub + pg * 4;
+            const float* src = col + ((size_t)n * p.Lo + t) * C;
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = (active && i < my_units && t + j < p.Lo) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)j * C))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        float4 va[4], vb[4];
+        load_unit(0, va);
+        load_unit(1, vb);
+        uint32_t bs = 0, bph = 0;
+        for (int i = 0; i < my_units; ++i) {
+            mbar_wait(&bars->b_empty[bs], bph ^ 1);
+            if (active) {
+                float4* d = dst0 + (size_t)bs * (p.b_stage_bytes >> 4);
+                d[0] = rn4(va[0].x, va[1].x, va[2].x, va[3].x);
+                d[1] = rn4(va[0].y, va[1].y, va[2].y, va[3].y);
+                d[2] = rn4(va[0].z, va[1].z, va[2].z, va[3].z);
+                d[3] = rn4(va[0].w, va[1].w, va[2].w, va[3].w);
+            }
+            fence_proxy_async_smem();  // generic-proxy stores are read by the tensor core
+            mbar_arrive(&bars->b_full[bs]);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) va[j] = vb[j];
+            load_unit(i + 2, vb);
+            if (++bs == kBStages) { bs = 0; bph ^= 1; }
+        }
+        // ---- epilogue: D_c (rows (tap, q), columns f) -> dW[tap][q][c][ft*Ft + f] with vector reductions
+        if (my_units > 0) {
+            mbar_wait_sleep(&bars->acc_full, 0);
+            tc_fence_after_sync();
+            const int m = e & 127, chunk = e >> 7;  // TMEM lane, 64-column chunk
+            const uint32_t lane_base = (uint32_t)(m & ~31) << 16;
+            const int row = mblk * 128 + m;
+#pragma unroll 1
+            for (int half = 0; half < 2; ++half) {
+                const int col0 = chunk * 64 + half * 32;
+                if (col0 < 4 * Ft) {  // warp-uniform
+                    uint32_t v[32];
+                    tmem_ld32(t_acc + lane_base + col0, v);
+                    tmem_wait_ld();
+                    const int tap = row / p.in_q, q = row - tap * p.in_q;
+                    if (row < p.R && q < p.in_q_out) {
+                        const size_t orow = (size_t)tap * p.in_q_out + q;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            const int cc = col0 + j;
+                            const int c = cc / Ft, f = cc - c * Ft;
+                            red_add_v4(dw + (orow * 4 + c) * p.F + (size_t)ft * Ft + f, __uint_as_float(v[j]),
+                                       __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+                        }
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before_sync();
+    __syncthreads();
+    if (warp == kWarpAlloc) tmem_dealloc(t_acc, 512);
+}
+
+int num_sms() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+
+WgradPlan wgrad_plan(const Geom& g, int rank) {
+    WgradPlan pl{};
+    pl.ok = 0;
+    auto no = [&](const char* why) {
+        pl.why = why;
+        return pl;
+    };
+    if (g.channels_first) return no("channels_first layout");
+    if (rank != 1) return no("rank > 1");
+    if (g.s[2] != 1) return no("stride != 1");
+    if (g.in_q < 4) return no("fewer than 4 quaternion input channels");
+    const int xq = (g.in_q + 3) & ~3;  // in_q % 4 != 0: channel-padding pre-pass (TMA alignment of the component blocks)
+    if (xq > 256) return no("more than 256 quaternion input channels (TMA box limit)");
+    if (g.F % 16) return no("filters not a multiple of 16");
+    if (g.out_sp[2] < 1 || g.batch < 1) return no("empty problem");
+    const int taps = g.k[2];
+    const int rows = kSub + (taps - 1) * g.d[2];
+    if (rows > 256) return no("halo exceeds the 256-row TMA box");
+    int f_tile = g.F <= 64 ? g.F : 0;  // filters per CTA (accumulators: 4 x f_tile <= 256 TMEM columns)
+    for (int cand : {64, 48, 32, 16})
+        if (!f_tile && g.F % cand == 0) f_tile = cand;
+    const int R = taps * xq;
+    const int n_mblk = (R + 127) / 128, n_ft = g.F / f_tile;
+    if (n_mblk * n_ft > 148) return no("more (row block, filter tile) combinations than SMs");
+    const size_t b_stage = (size_t)4 * 8 * f_tile * 16;
+    const size_t x_stage = ((size_t)rows * 4 * xq * 4 + 1023) & ~size_t(1023);
+    const size_t fixed = 1024 + kBStages * b_stage + 512;
+    if (fixed + 2 * x_stage > kSmemLimit) return no("x stages do not fit in shared memory");
+    pl.ok = 1;
+    pl.f_tile = f_tile;
+    pl.n_ftiles = n_ft;
+    pl.n_mblk = n_mblk;
+    pl.rows = rows;
+    pl.pad_x = xq != g.in_q;
+    pl.x_stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / x_stage);
+    pl.x_stage_bytes = x_stage;
+    pl.smem_bytes = fixed + (size_t)pl.x_stages * x_stage;
+    pl.why = "";
+    return pl;
+}
+
+// dw (stored-kernel shape [taps][in_q][4][F]) is OVERWRITTEN.  dz = dy * act'(y), fp32, [batch][Lo][4F].
+int wgrad_tc(const Geom& g, int rank, const float* x, const float* dz, float* dw, cudaStream_t st) {
+    const WgradPlan pl = wgrad_plan(g, rank);
+    if (!pl.ok) {
+        set_error("tensor-core kernel gradient does not take this shape: %s", pl.why);
+        return QNN_E_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(dz) | reinterpret_cast<uintptr_t>(dw)) & 15) {
+        set_error("tensor-core kernel gradient needs 16-byte aligned x, dz and dkernel");
+        return QNN_E_UNSUPPORTED;
+    }
+    const int L = g.in_sp[2], Lo = g.out_sp[2], taps = g.k[2];
+    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)taps * g.in_q * 4 * g.F * sizeof(float), st);
+    if (e != cudaSuccess) {
+        set_error("dkernel memset failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    const int xq = (g.in_q + 3) & ~3;
+    float* xp = nullptr;
+    if (pl.pad_x) {
+        const long long rows = (long long)g.batch * L;
+        int rc = stream_scratch_alloc(reinterpret_cast<void**>(&xp), (size_t)rows * 4 * xq * sizeof(float), st);
+        if (!rc) rc = pad_x_channels(x, xp, rows, g.in_q, xq, st);
+        if (rc) {
+            if (xp) cudaFreeAsync(xp, st);
+            return rc;
+        }
+        x = xp;
+    }
+    struct FreeOnExit {
+        float* p;
+        cudaStream_t st;
+        ~FreeOnExit() { if (p) cudaFreeAsync(p, st); }
+    } free_xp{xp, st};
+    WP p{};
+    p.units_per_seq = (Lo + kSub - 1) / kSub;
+    const long long nu = (long long)g.batch * p.units_per_seq;
+    if (nu > 0x7fffffffLL) {
+        set_error("too many position sub-tiles");
+        return QNN_E_UNSUPPORTED;
+    }
+    p.n_units = (int)nu;
+    p.n_ftiles = pl.n_ftiles;
+    p.n_combos = pl.n_mblk * pl.n_ftiles;
+    p.taps = taps;
+    p.dil = g.d[2];
+    p.pad_lo = g.pad_lo[2];
+    p.in_q = xq;
+    p.in_q_out = g.in_q;
+    p.F = g.F;
+    p.f_tile = pl.f_tile;
+    p.R = taps * xq;
+    p.Lo = Lo;
+    p.rows = pl.rows;
+    p.x_stages = pl.x_stages;
+    p.x_stage_bytes = (int)pl.x_stage_bytes;
+    p.b_stage_bytes = (uint32_t)(4 * 8 * pl.f_tile * 16);
+    CUtensorMap tmx;
+    {
+        // x[nb][L][4][in_q]: one box = (all in_q channels, the 4 components, 32 + halo rows, one sample), no swizzle
+        const uint64_t dims[4] = {(uint64_t)xq, 4, (uint64_t)L, (uint64_t)g.batch};
+        const uint64_t str[3] = {(uint64_t)xq * 4, (uint64_t)xq * 16, (uint64_t)L * xq * 16};
+        const uint32_t box[4] = {(uint32_t)xq, 4, (uint32_t)pl.rows, 1};
+        int rc = make_tmap_f32(&tmx, x, 4, dims, str, box, false);
+        if (rc) {
+            set_error("cuTensorMapEncodeTiled(x, wgrad) failed (%d)", rc);
+            return QNN_E_CUDA;
+        }
+    }
+    auto kern = g.conj_w ? k_hamilton_wgrad_tc<true> : k_hamilton_wgrad_tc<false>;
+    static std::mutex mu;
+    static bool configured[2] = {false, false};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!configured[g.conj_w ? 1 : 0]) {
+            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
+            if (e != cudaSuccess) {
+                set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+                return QNN_E_CUDA;
+            }
+            configured[g.conj_w ? 1 : 0] = true;
+        }
+    }
+    // grid: a multiple of the number of combinations, at most one CTA per SM, no more groups than units
+    int groups = std::min(num_sms() / p.n_combos, p.n_units);
+    if (groups < 1) groups = 1;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(groups * p.n_combos);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = pl.smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    e = cudaLaunchKernelEx(&cfg, kern, tmx, p, dz, dw);
+    count_launch();
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("tensor-core kernel gradient launch failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    return QNN_OK;
+}
+
+}  // namespace qnn
