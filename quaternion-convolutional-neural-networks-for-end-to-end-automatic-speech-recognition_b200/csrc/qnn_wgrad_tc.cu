@@ -36,7 +36,7 @@ constexpr int kPackThreads = 512;
 constexpr int kSlots = 8;
 constexpr int kSlotCols = 32;
 constexpr int kAccCols = 256;
-constexpr int kBStages = 2;
+constexpr int kBStages = 3;
 constexpr int kMaxXStages = 4;
 constexpr uint32_t kSmemLimit = 232448;
 constexpr int kRegsWg0 = 24, kRegsWg1 = 40, kRegsEpi = 96;
@@ -264,25 +264,43 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
                 v[j] = (active && i < my_units && t + j < p.Lo) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)j * C))
                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         };
-        float4 va[4], vb[4];
-        load_unit(0, va);
-        load_unit(1, vb);
         uint32_t bs = 0, bph = 0;
-        for (int i = 0; i < my_units; ++i) {
+        auto store_unit = [&](const float4 (&v)[4]) {
             mbar_wait(&bars->b_empty[bs], bph ^ 1);
             if (active) {
                 float4* d = dst0 + (size_t)bs * (p.b_stage_bytes >> 4);
-                d[0] = rn4(va[0].x, va[1].x, va[2].x, va[3].x);
-                d[1] = rn4(va[0].y, va[1].y, va[2].y, va[3].y);
-                d[2] = rn4(va[0].z, va[1].z, va[2].z, va[3].z);
-                d[3] = rn4(va[0].w, va[1].w, va[2].w, va[3].w);
+                const float4 o0 = rn4(v[0].x, v[1].x, v[2].x, v[3].x), o1 = rn4(v[0].y, v[1].y, v[2].y, v[3].y),
+                             o2 = rn4(v[0].z, v[1].z, v[2].z, v[3].z), o3 = rn4(v[0].w, v[1].w, v[2].w, v[3].w);
+                // a thread owns 4 consecutive filters = four 16-byte items 64 bytes apart from its neighbour's: writing
+                // item i from every lane would hit the same banks 4 ways.  Lanes rotate their order by fg / 2 instead, so
+                // that 8 lanes (one 128-byte wavefront) cover 8 distinct 16-byte slots.
+                const int rot = (fg >> 1) & 3;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = (i + rot) & 3;
+                    d[k] = k == 0 ? o0 : k == 1 ? o1 : k == 2 ? o2 : o3;
+                }
             }
             fence_proxy_async_smem();  // generic-proxy stores are read by the tensor core
             mbar_arrive(&bars->b_full[bs]);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) va[j] = vb[j];
-            load_unit(i + 2, vb);
             if (++bs == kBStages) { bs = 0; bph ^= 1; }
+        };
+        // three sub-tiles of dz in flight per thread (global-load latency is ~2 sub-tiles of MMA time)
+        float4 v0[4], v1[4], v2[4];
+        load_unit(0, v0);
+        load_unit(1, v1);
+        load_unit(2, v2);
+        for (int i = 0; i < my_units; i += 3) {
+            store_unit(v0);
+            load_unit(i + 3, v0);
+            if (i + 1 < my_units) {
+                store_unit(v1);
+                load_unit(i + 4, v1);
+            }
+            if (i + 2 < my_units) {
+                store_unit(v2);
+                load_unit(i + 5, v2);
+            }
         }
         // ---- epilogue: D_c (rows (tap, q), columns f) -> dW[tap][q][c][ft*Ft + f] with vector reductions
         if (my_units > 0) {
