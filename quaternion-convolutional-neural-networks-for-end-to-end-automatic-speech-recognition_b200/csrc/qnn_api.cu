@@ -1,6 +1,7 @@
 // C-ABI entry points of libqnn_b200.so (declared in include/qnn.h): argument validation, geometry resolution
 // (TF/Keras padding rules), kernel selection, host-buffer staging and the NCCL gradient exchange.
 #include <dlfcn.h>
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 #include <string>
@@ -298,7 +299,14 @@ int forward_host(const Geom& g, int rank, int math, int algo, size_t nx, size_t 
     const long long units = dense ? g.in_sp[2] : g.batch;
     const size_t x_unit = nx / (size_t)units, y_unit = ny / (size_t)units;
     int chunks = 1;
-    if ((nx + ny) * 4 >= (size_t)8 << 20 && units >= 8 && g_pipe.init()) chunks = units >= 64 ? 8 : 4;
+    if ((nx + ny) * 4 >= (size_t)8 << 20 && units >= 8 && g_pipe.init()) {
+        chunks = units >= 64 ? 8 : 4;  // measured on cfg 2: 1 / 2 / 4 / 8 / 16 chunks -> 2.04 / 1.70 / 1.59 / 1.54 / 1.65 ms
+                                       // (67 MB of y over PCIe is ~1.45 ms on its own; uneven cuts gained nothing)
+        if (const char* env = getenv("QNN_HOST_CHUNKS")) {  // tuning knob: 1..16 pipeline chunks
+            const int v = atoi(env);
+            if (v >= 1 && v <= 16 && v <= units) chunks = v;
+        }
+    }
     cudaError_t e;
     if ((e = cudaMemcpyAsync(wd, wh, nw * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) goto fail;
     if (bh && (e = cudaMemcpyAsync(bd, bh, nb * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) goto fail;
