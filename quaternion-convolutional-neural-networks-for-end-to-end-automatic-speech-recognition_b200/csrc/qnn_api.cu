@@ -511,6 +511,7 @@ int qnn_dense_forward_host(int64_t rows, int32_t in_q, int32_t q_units, const fl
 int qnn_debug_trace(void* device_buffer, size_t bytes) {
     tc_set_trace(device_buffer, bytes);
     tc2d_set_trace(device_buffer, bytes);
+    wgrad_set_trace(device_buffer, bytes);
     return QNN_OK;
 }
 

@@ -67,6 +67,7 @@ struct WgradPlan {
     const char* why;
 };
 WgradPlan wgrad_plan(const Geom& g, int rank);
+void wgrad_set_trace(void* device_buffer, size_t bytes);
 int wgrad_tc(const Geom& g, int rank, const float* x, const float* dz, float* dw, cudaStream_t st);
 
 // tensor-core kernel for channels_first tensors (rank 1 / 2, stride 1): streamed sub-filters, transposing converters

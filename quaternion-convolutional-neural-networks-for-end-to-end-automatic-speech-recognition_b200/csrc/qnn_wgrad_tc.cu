@@ -39,8 +39,9 @@ constexpr int kAccCols = 256;
 constexpr int kBStages = 3;
 constexpr int kMaxXStages = 4;
 constexpr uint32_t kSmemLimit = 232448;
-constexpr int kRegsWg0 = 24, kRegsWg1 = 40, kRegsEpi = 96;
+constexpr int kRegsWg0 = 24, kRegsWg1 = 48, kRegsEpi = 88;
 static_assert(256 * kRegsWg0 + 256 * kRegsWg1 + 512 * kRegsEpi <= 1024 * 64, "register pool");
+static_assert(kSlots % (kSub / 8) == 0, "a unit's A slots must not wrap around the ring");
 
 constexpr uint32_t kNegConv = (1u << 4) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 12) | (1u << 14);
 constexpr uint32_t transpose_bits(uint32_t m) {
@@ -54,7 +55,14 @@ constexpr uint32_t kNegDense = transpose_bits(kNegConv);
 
 enum { kWarpAlloc = 16, kWarpIssuer0 = 16, kWarpConv0 = 20, kWarpProd0 = 28 };
 
+// Optional per-CTA event trace (qnn_debug_trace, tools/wgrad_trace.py): clock64() slots per CTA.
+// 0 start, 1 setup, 2 end, 3 accumulators complete, 4 epilogue done; per unit u < 24:
+// 8+8u: issuer b_full passed, +1 issuer unit committed, +2 packer b_empty passed, +3 packer stored, +4 converter x_full
+// passed, +5 converter unit done, +6 producer x_empty passed
+constexpr int kTraceSlots = 256;
+
 struct WP {
+    unsigned long long* trace;
     int n_units, units_per_seq;  // position sub-tiles: unit -> (sample, t0 = (unit % units_per_seq) * 32)
     int n_combos, n_ftiles;      // combo = mblk * n_ftiles + ft; CTA b owns combo b % n_combos
     int taps, dil, pad_lo;
@@ -72,6 +80,10 @@ struct __align__(8) Bars {
     uint64_t acc_full;
     uint32_t tmem_base;
 };
+
+__device__ __forceinline__ void trace(const WP& p, int slot) {
+    if (p.trace && slot < kTraceSlots) p.trace[(size_t)blockIdx.x * kTraceSlots + slot] = (unsigned long long)clock64();
+}
 
 template <int N>
 __device__ __forceinline__ void reg_dealloc() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
@@ -121,6 +133,7 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
     const int my_units = cgroup < n_groups ? (p.n_units - cgroup + n_groups - 1) / n_groups : 0;
 
     if (tid == kWarpAlloc * 32) {
+        trace(p, 0);
         tma_prefetch_desc(&tmx);
         for (int i = 0; i < kMaxXStages; ++i) {
             mbar_init(&bars->x_full[i], 1);
@@ -148,6 +161,7 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
     tc_fence_after_sync();
     const uint32_t t_acc = bars->tmem_base;
     const uint32_t t_a = t_acc + kAccCols;
+    if (tid == kWarpAlloc * 32) trace(p, 1);
 
     if (warp >= kWarpProd0) {
         // =========================== x producer ===========================
@@ -158,6 +172,7 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
                 const int unit = cgroup + i * n_groups;
                 const int n = unit / p.units_per_seq, t0 = (unit - n * p.units_per_seq) * kSub;
                 mbar_wait(&bars->x_empty[xs], xph ^ 1);
+                if (i < 24) trace(p, 8 + 8 * i + 6);
                 mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)(p.rows * 4 * p.in_q * 4));
                 tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], 0, 0, t0 - p.pad_lo, n);
                 if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
@@ -174,17 +189,25 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
         const int tap = valid ? row / p.in_q : 0, q = valid ? row - tap * p.in_q : 0;
         const int pitch = 4 * p.in_q;    // floats per x row
         const int base_off = tap * p.dil * pitch + q;
+        // padding lanes (row >= R) read row (tap 0, q 0) like lane 0 and mask the result: unconditional loads keep the 32
+        // shared-memory reads of a k-step in flight together (predicated ones compile into 32 serialised branches)
+        const uint32_t vmask = valid ? 0xffffffffu : 0u;
         uint32_t xs = 0, xph = 0, as = 0, aph = 0;
         for (int i = 0; i < my_units; ++i) {
             mbar_wait(&bars->x_full[xs], xph);
+            if (cgrp == 0 && m == 0 && i < 24) trace(p, 8 + 8 * i + 4);
             const float* xb = reinterpret_cast<const float*>(x_s + (size_t)xs * p.x_stage_bytes) + base_off;
-#pragma unroll 1
-            for (int ks = 0; ks < kSub / 8; ++ks) {
-                if ((ks & 1) == cgrp) {
-                    mbar_wait(&bars->a_empty[as], aph ^ 1);
-                    tc_fence_after_sync();
-                    const float* xk = xb + ks * 8 * pitch;
-                    const uint32_t dst = t_a + lane_base + as * kSlotCols;
+            {
+                // group g converts k-steps 2g and 2g+1 of the unit as ONE batch (one tcgen05.wait::st for four stores: the
+                // wait, not the store issue, is what a batch costs).  A unit's four slots never wrap (8 slots, 4 per unit).
+                const uint32_t s0 = as + 2 * cgrp;
+                mbar_wait(&bars->a_empty[s0], aph ^ 1);
+                mbar_wait(&bars->a_empty[s0 + 1], aph ^ 1);
+                tc_fence_after_sync();
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk) {
+                    const float* xk = xb + (2 * cgrp + kk) * 8 * pitch;
+                    const uint32_t dst = t_a + lane_base + (s0 + kk) * kSlotCols;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {  // components 2h, 2h+1: 16 columns
                         uint32_t u[16];
@@ -192,16 +215,19 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
                         for (int a2 = 0; a2 < 2; ++a2)
 #pragma unroll
                             for (int j = 0; j < 8; ++j)
-                                u[a2 * 8 + j] = valid ? __float_as_uint(xk[j * pitch + (2 * h + a2) * p.in_q]) + 0x1000u : 0u;
+                                u[a2 * 8 + j] = (__float_as_uint(xk[j * pitch + (2 * h + a2) * p.in_q]) + 0x1000u) & vmask;
                         tmem_st16_nc(dst + h * 16, u);
                     }
-                    tmem_wait_st();
-                    tc_fence_before_sync();
-                    mbar_arrive(&bars->a_full[as]);
                 }
-                if (++as == kSlots) { as = 0; aph ^= 1; }
+                tmem_wait_st();
+                tc_fence_before_sync();
+                mbar_arrive(&bars->a_full[s0]);
+                mbar_arrive(&bars->a_full[s0 + 1]);
+                as += kSub / 8;
+                if (as == kSlots) { as = 0; aph ^= 1; }
             }
             mbar_arrive(&bars->x_empty[xs]);
+            if (cgrp == 0 && m == 0 && i < 24) trace(p, 8 + 8 * i + 5);
             if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
         }
     } else if (warp >= kWarpAlloc) {
@@ -220,6 +246,7 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, accumulate = 0;
         for (int i = 0; i < my_units; ++i) {
             mbar_wait(&bars->b_full[bs], bph);
+            if (c == 0 && elected && i < 24) trace(p, 8 + 8 * i);
             for (int ks = 0; ks < kSub / 8; ++ks) {
                 mbar_wait(&bars->a_full[as], aph);
                 tc_fence_after_sync();
@@ -239,6 +266,7 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
                 if (++as == kSlots) { as = 0; aph ^= 1; }
             }
             if (elected) mma_commit(&bars->b_empty[bs]);
+            if (c == 0 && elected && i < 24) trace(p, 8 + 8 * i + 1);
             __syncwarp();
             if (++bs == kBStages) { bs = 0; bph ^= 1; }
         }
@@ -265,8 +293,10 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
                                                                   : make_float4(0.f, 0.f, 0.f, 0.f);
         };
         uint32_t bs = 0, bph = 0;
+        int ucount = 0;
         auto store_unit = [&](const float4 (&v)[4]) {
             mbar_wait(&bars->b_empty[bs], bph ^ 1);
+            if (e == 0 && ucount < 24) trace(p, 8 + 8 * ucount + 2);
             if (active) {
                 float4* d = dst0 + (size_t)bs * (p.b_stage_bytes >> 4);
                 const float4 o0 = rn4(v[0].x, v[1].x, v[2].x, v[3].x), o1 = rn4(v[0].y, v[1].y, v[2].y, v[3].y),
@@ -283,6 +313,8 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
             }
             fence_proxy_async_smem();  // generic-proxy stores are read by the tensor core
             mbar_arrive(&bars->b_full[bs]);
+            if (e == 0 && ucount < 24) trace(p, 8 + 8 * ucount + 3);
+            ++ucount;
             if (++bs == kBStages) { bs = 0; bph ^= 1; }
         };
         // three sub-tiles of dz in flight per thread (global-load latency is ~2 sub-tiles of MMA time)
@@ -306,6 +338,7 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
         if (my_units > 0) {
             mbar_wait_sleep(&bars->acc_full, 0);
             tc_fence_after_sync();
+            if (e == 0) trace(p, 3);
             const int m = e & 127, chunk = e >> 7;  // TMEM lane, 64-column chunk
             const uint32_t lane_base = (uint32_t)(m & ~31) << 16;
             const int row = mblk * 128 + m;
@@ -332,10 +365,15 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
         }
     }
 
+    if (tid == 0) trace(p, 4);
     tc_fence_before_sync();
     __syncthreads();
     if (warp == kWarpAlloc) tmem_dealloc(t_acc, 512);
+    if (tid == kWarpAlloc * 32) trace(p, 2);
 }
+
+unsigned long long* g_trace_w = nullptr;
+size_t g_trace_w_bytes = 0;
 
 int num_sms() {
     static int n = 0;
@@ -349,6 +387,11 @@ int num_sms() {
 }
 
 }  // namespace
+
+void wgrad_set_trace(void* device_buffer, size_t bytes) {
+    g_trace_w = static_cast<unsigned long long*>(device_buffer);
+    g_trace_w_bytes = bytes;
+}
 
 WgradPlan wgrad_plan(const Geom& g, int rank) {
     WgradPlan pl{};
@@ -477,6 +520,7 @@ int wgrad_tc(const Geom& g, int rank, const float* x, const float* dz, float* dw
     // grid: a multiple of the number of combinations, at most one CTA per SM, no more groups than units
     int groups = std::min(num_sms() / p.n_combos, p.n_units);
     if (groups < 1) groups = 1;
+    p.trace = (g_trace_w && g_trace_w_bytes >= (size_t)groups * p.n_combos * kTraceSlots * 8) ? g_trace_w : nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(groups * p.n_combos);
     cfg.blockDim = dim3(kThreads);

@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--fwd", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="capture one step in a CUDA graph and replay it (no phase split)")
     args = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     torch.cuda.set_device(local)
@@ -92,12 +93,26 @@ def main():
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    graph = None
+    if args.graph:
+        cap = torch.cuda.Stream()
+        cap.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(cap):
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=cap):
+                step()
+        torch.cuda.current_stream().wait_stream(cap)
+        graph.replay()
+        torch.cuda.synchronize()
     l0 = _native.launch_count()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     t_f = t_b = t_a = 0.0
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
+        if graph is not None:
+            graph.replay()
+            continue
         ev[0].record()
         step(ev)
         ev[3].record()
@@ -121,6 +136,7 @@ def main():
             "n_gpus": world, "per_gpu_batch": B, "ms_per_step": ms, "qmacs_per_step_per_gpu": q_total,
             "value": world * q_total / (ms * 1e-3), "unit": "qMAC/s",
             "phases_ms": {"forward": t_f / args.steps, "backward": t_b / args.steps, "allreduce": t_a / args.steps},
+            "launch": "CUDA graph replay of one captured step" if graph is not None else "eager, one C-ABI call per layer and pass",
             "bucket_floats": bucket.numel(), "launches_per_step": launches / args.steps, "steps": args.steps}))
     if world > 1:
         destroy_comm()
