@@ -29,6 +29,10 @@ if int(os.environ.get("RANK", "0")) == 0:
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(_cores)
 
+# rank 0 prints ONE JSON line on stdout: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"
+
 import numpy as np
 
 REPO = os.path.dirname(os.path.abspath(__file__))
