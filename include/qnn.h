@@ -87,6 +87,12 @@ QNN_API const char* qnn_last_error(void);
 QNN_API int qnn_conv_uses_tensor_cores(const qnn_conv_desc* d);
 QNN_API int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units);
 
+/* Which gradients of this layer qnn_*_backward computes on the tensor cores (1) or on the CUDA-core kernels (0) under
+ * the descriptor's math / algo (dense: TF32 + AUTO); pointer alignment aside.  Host-only, needs no GPU. */
+QNN_API int qnn_conv_backward_uses_tensor_cores(const qnn_conv_desc* d, int32_t* dx_tc, int32_t* dkernel_tc);
+QNN_API int qnn_dense_backward_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units, int32_t* dx_tc,
+                                         int32_t* dkernel_tc);
+
 /* replaces conv_utils.conv_output_length at complexnn/conv.py:347-372 */
 QNN_API int qnn_conv_out_spatial(const qnn_conv_desc* d, int32_t out_spatial[3]);
 

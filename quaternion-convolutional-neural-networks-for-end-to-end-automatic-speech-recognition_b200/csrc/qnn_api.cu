@@ -175,6 +175,27 @@ int run_forward(const Geom& g, int rank, int math, int algo, const float* x, con
     return general_forward(g, x, w, bias, y, st);
 }
 
+// the transposed convolution of the data gradient: dz [batch, Lo, 4F] -> dx [batch, L, 4 in_q]
+Geom transposed_geom(const Geom& g) {
+    Geom gt = g;
+    gt.in_q = g.F;
+    gt.F = g.in_q;
+    gt.in_sp[2] = g.out_sp[2];
+    gt.out_sp[2] = g.in_sp[2];
+    gt.pad_lo[2] = (g.k[2] - 1) * g.d[2] - g.pad_lo[2];
+    gt.act = QNN_ACT_LINEAR;
+    gt.conj_w = g.conj_w ? 0 : 1;
+    return gt;
+}
+
+// which gradients of this problem the tensor-core kernels take (pointer alignment aside)
+void backward_selection(const Geom& g, int rank, int math, int algo, int* dx_tc, int* dw_tc) {
+    const bool base = math == QNN_MATH_TF32 && algo != QNN_ALGO_GENERAL && !g.channels_first && rank == 1 &&
+                      !empty_out(g) && g.in_sp[2] > 0 && (g.act == QNN_ACT_LINEAR || g.act == QNN_ACT_RELU);
+    *dx_tc = base && tc_plan(transposed_geom(g), 1).ok;
+    *dw_tc = base && wgrad_plan(g, 1).ok;
+}
+
 // Backward.  Tensor-core path (channels_last rank 1 / dense, stride 1): one pass makes dz = dy * act'(y) and the bias
 // gradient; the data gradient is the SAME fused Hamilton kernel run on dz with the transposed, tap-flipped stored kernel
 // and the transposed sign table; the kernel gradient contracts x with dz over positions on the tensor
@@ -190,19 +211,13 @@ int run_backward(const Geom& g, int rank, int math, int algo, const float* x, co
         set_error("unknown algo %d", algo);
         return QNN_E_INVALID;
     }
-    Geom gt = g;  // the transposed convolution: dz [batch, Lo, 4F] -> dx [batch, L, 4 in_q]
-    gt.in_q = g.F;
-    gt.F = g.in_q;
-    gt.in_sp[2] = g.out_sp[2];
-    gt.out_sp[2] = g.in_sp[2];
-    gt.pad_lo[2] = (g.k[2] - 1) * g.d[2] - g.pad_lo[2];
-    gt.act = QNN_ACT_LINEAR;
-    gt.conj_w = g.conj_w ? 0 : 1;
+    const Geom gt = transposed_geom(g);
     auto al16 = [](const void* a) { return (reinterpret_cast<uintptr_t>(a) & 15) == 0; };
-    const bool tc_base = math == QNN_MATH_TF32 && algo != QNN_ALGO_GENERAL && !g.channels_first && rank == 1 &&
-                         !empty_out(g) && g.in_sp[2] > 0 && al16(dy) && al16(y) && al16(x);
-    const bool tc_dx = tc_base && dx && al16(dx) && tc_plan(gt, 1).ok;
-    const bool tc_dw = tc_base && dw && al16(dw) && wgrad_plan(g, 1).ok;
+    int sel_dx = 0, sel_dw = 0;
+    backward_selection(g, rank, math, algo, &sel_dx, &sel_dw);
+    const bool al_base = al16(dy) && al16(y) && al16(x);
+    const bool tc_dx = sel_dx && al_base && dx && al16(dx);
+    const bool tc_dw = sel_dw && al_base && dw && al16(dw);
     if (algo == QNN_ALGO_TENSOR && ((dx && !tc_dx) || (dw && !tc_dw))) {
         set_error("tensor-core backward does not take this problem (channels_last rank 1 / dense, stride 1): dx: %s; "
                   "dkernel: %s", dx ? (tc_dx ? "ok" : tc_plan(gt, 1).why) : "-", dw ? (tc_dw ? "ok" : wgrad_plan(g, 1).why) : "-");
@@ -432,6 +447,36 @@ int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units) {
     Geom g;
     if (build_dense_geom(rows, in_q, q_units, QNN_ACT_LINEAR, &g)) return 0;
     return tc_plan(g, 1).ok;
+}
+
+int qnn_conv_backward_uses_tensor_cores(const qnn_conv_desc* d, int32_t* dx_tc, int32_t* dkernel_tc) {
+    Geom g;
+    int rc = build_geom(d, &g);
+    if (rc) return rc;
+    if (!dx_tc || !dkernel_tc) {
+        set_error("output pointers must not be NULL");
+        return QNN_E_INVALID;
+    }
+    int a = 0, b = 0;
+    backward_selection(g, d->rank, d->math, d->algo, &a, &b);
+    *dx_tc = a;
+    *dkernel_tc = b;
+    return QNN_OK;
+}
+
+int qnn_dense_backward_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units, int32_t* dx_tc, int32_t* dkernel_tc) {
+    Geom g;
+    int rc = build_dense_geom(rows, in_q, q_units, QNN_ACT_LINEAR, &g);
+    if (rc) return rc;
+    if (!dx_tc || !dkernel_tc) {
+        set_error("output pointers must not be NULL");
+        return QNN_E_INVALID;
+    }
+    int a = 0, b = 0;
+    backward_selection(g, 1, QNN_MATH_TF32, QNN_ALGO_AUTO, &a, &b);
+    *dx_tc = a;
+    *dkernel_tc = b;
+    return QNN_OK;
 }
 
 int qnn_conv_forward(const qnn_conv_desc* d, const float* x, const float* kernel, const float* bias, float* y,

@@ -261,3 +261,37 @@ def test_no_silent_cpu_fallback():
     layer = QuaternionDense(16)
     with pytest.raises(RuntimeError, match="qnn error"):
         layer(np.zeros((4, 16), np.float32))
+
+
+def test_backward_kernel_selection_is_host_logic(native_lib):
+    """qnn_*_backward_uses_tensor_cores: which gradients run on the tensor cores (no GPU needed to ask)."""
+    from complexnn import _native
+
+    def ask(desc):
+        a, b = ctypes.c_int32(-1), ctypes.c_int32(-1)
+        assert native_lib.qnn_conv_backward_uses_tensor_cores(ctypes.byref(desc), ctypes.byref(a), ctypes.byref(b)) == 0
+        return a.value, b.value
+
+    mk = _native.make_conv_desc
+    # cfg 3 / 4 stack: inner conv layers (in_q = 64, F = 64): both gradients on tensor cores
+    assert ask(mk(1, 256, (256,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu")) == (1, 1)
+    # first layer (TIMIT in_q = 41): kernel gradient yes (padding pre-pass); data gradient would need F' = 41 filters
+    assert ask(mk(1, 256, (256,), 41, 64, (3,), (1,), (1,), "same", "channels_last", "relu")) == (0, 1)
+    # cfg 2 (in_q = 40): dx needs a multiple of 16 "filters" in the transposed problem -> CUDA cores; dkernel on tensor cores
+    assert ask(mk(1, 256, (256,), 40, 64, (3,), (1,), (1,), "same", "channels_last", "relu")) == (0, 1)
+    # strided, channels_first, rank 2, fp32 math, general algo: CUDA-core kernels
+    assert ask(mk(1, 8, (64,), 64, 64, (3,), (2,), (1,), "same", "channels_last", "relu")) == (0, 0)
+    assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")) == (0, 0)
+    assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="fp32")) == (0, 0)
+    assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", algo="general")) == (0, 0)
+    # tanh has no fused derivative: the backward entry points refuse it, the query says "not on tensor cores"
+    assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "tanh")) == (0, 0)
+    a, b = ctypes.c_int32(-1), ctypes.c_int32(-1)
+    assert native_lib.qnn_dense_backward_uses_tensor_cores(65536, 64, 64, ctypes.byref(a), ctypes.byref(b)) == 0
+    assert (a.value, b.value) == (1, 1)
+    assert native_lib.qnn_dense_backward_uses_tensor_cores(325, 250, 128, ctypes.byref(a), ctypes.byref(b)) == 0
+    assert (a.value, b.value) == (0, 0)          # DECODA first layer: 250 "filters" do not tile in the transposed problem,
+    #                                              and a 32-row x stage of 4 x 252 channels (129 KB) does not fit twice
+    assert native_lib.qnn_dense_backward_uses_tensor_cores(325, 128, 128, ctypes.byref(a), ctypes.byref(b)) == 0
+    assert (a.value, b.value) == (1, 1)          # DECODA QDNN layers 2 and 3
+    assert native_lib.qnn_conv_backward_uses_tensor_cores(None, ctypes.byref(a), ctypes.byref(b)) == -1
