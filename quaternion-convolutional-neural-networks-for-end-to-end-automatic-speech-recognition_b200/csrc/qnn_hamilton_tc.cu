@@ -10,14 +10,17 @@
 //   x tiles      TMA: raw fp32 (128 rows + halo, 32 channels) -> 128B-swizzled smem ring, issued by the converter group
 //                that owns the ring slot as soon as it has consumed it (no separate producer warp).  When in_q is a
 //                multiple of 8 the channel axis is walked flat (a 32-channel box may span two components, no padding);
-//                otherwise per component with the out-of-range tail zero-filled by TMA
-//   warps 20-27  converters  : two groups of four warps that take alternate x stages; smem -> registers, round-to-nearest tf32 (the tensor core would truncate), tcgen05.st into
-//                              a ring of A-operand slots in tensor memory; the tap shift is a row offset in this read;
-//                              all taps of a stage are converted as one batch (one tcgen05.wait::st per batch)
+//                otherwise per component with the out-of-range tail zero-filled by TMA.  in_q % 4 != 0: x first goes
+//                through a channel-padding pre-pass (k_pad_x), TMA boxes must start on 16-byte boundaries
+//   warps 20-27  converters  : two groups of four warps that take alternate x stages; smem -> registers, round-to-nearest
+//                              tf32 (the tensor core would truncate), tcgen05.st into a ring of A-operand slots in tensor
+//                              memory; the tap shift is a row offset in this read; all taps of a stage are converted as
+//                              one batch (one tcgen05.wait::st per batch -- the wait is what a batch costs)
 //   warps 16-19  MMA issuers : one warp per output component (y_r, y_i, y_j, y_k): a single thread sustains only one
-//                              tcgen05.mma per ~117 cycles, four issuers reach ~38 (measured; floor 32 at N = 64);
+//                              tcgen05.mma per ~117 cycles, four issuers reach ~37 (measured; floor 32 at N = 64);
 //                              A from TMEM, B = sub-filter block resident in smem (K-major, no swizzle).  Warp 16 also
-//                              owns the TMEM allocation and issues the sub-filter TMA loads of each pass
+//                              initialises the barriers, fires the first x stages and the first pass' sub-filter boxes
+//                              (one TMA per lane, before anything else) and owns the TMEM allocation
 //   warps 0-15   epilogue    : first pack + round the sub-filters into smem (overlapping the first x loads); per tile all
 //                              16 warps pull the accumulators into registers at once (TMEM is free again after two
 //                              tcgen05.ld), then +bias -> activation -> swizzled staging -> TMA store (clips ragged tiles)
@@ -42,7 +45,6 @@ constexpr int kASlotCols = 32;
 constexpr int kAccCols = 256;
 constexpr int kMaxXStages = 4;
 constexpr int kMaxTapBatch = 4;              // taps converted per tcgen05.wait::st
-constexpr int kPackBatch = 4;                // 4x4 sub-filter blocks (4 x 16-byte loads each) in flight per packer thread
 constexpr int kStagingBytes = kTileM * 128;  // one [128 x 32] fp32 store tile
 constexpr uint32_t kSmemLimit = 232448;      // 227 KB opt-in maximum per CTA
 // register budget: 896 x 72 = 64512 at launch = 128 x kRegsWg0 + 256 x kRegsWg1 + 512 x kRegsEpi
@@ -86,7 +88,6 @@ struct TcParams {
     int rows_in, x_stages, x_stage_bytes;
     int act, has_bias;
     uint32_t w_bytes;
-    uint32_t magic_f4, magic_kq;  // floor(2^32 / d) + 1: exact n / d by __umulhi for n < 2^16
 };
 
 struct __align__(8) Barriers {
@@ -155,13 +156,6 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_
         "}\n" ::"r"(d_tmem),
         "r"(a_tmem), "r"(desc_lo), "r"(desc_hi), "r"(idesc), "r"(accumulate)
         : "memory");
-}
-
-__device__ __forceinline__ uint32_t rn_bias(float v) { return __float_as_uint(v) + 0x1000u; }
-__device__ __forceinline__ void swap4(uint4& a, uint4& b) {
-    const uint4 t = a;
-    a = b;
-    b = t;
 }
 
 template <int ACT>
@@ -794,8 +788,6 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     p.act = g.act;
     p.has_bias = bias != nullptr;
     p.w_bytes = (uint32_t)((size_t)p.taps * 4 * p.in_q_pad * p.f_tile * 4);
-    p.magic_f4 = (uint32_t)((1ull << 32) / (uint32_t)(p.f_tile / 4)) + 1;
-    p.magic_kq = (uint32_t)((1ull << 32) / (uint32_t)(p.in_q_pad / 4)) + 1;
 
     CUtensorMap tmx, tmy, tmw;
     {
