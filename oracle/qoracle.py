@@ -398,6 +398,47 @@ def qdense_forward_f32(x, kernel, bias, units, relu=True):
     return y
 
 
+# The same three paths with the real convolution / matmul handed to torch's CPU kernels (oneDNN / MKL) -- the closest thing
+# in this image to what TensorFlow's CPU backend would run under the reference; the expansion stays inside the timed call.
+def qconv1d_forward_torch_cpu(x, kernel, bias, filters, padding="same", relu=True):
+    import torch
+    w = expand_conv_kernel(kernel, filters)                                  # [k, 4in_q, 4F]
+    k = w.shape[0]
+    lo, hi, _ = pad_amounts(x.shape[1], k, 1, 1, padding)
+    xt = torch.from_numpy(x).permute(0, 2, 1)                                # NCL view of the channels_last memory
+    if lo or hi:
+        xt = torch.nn.functional.pad(xt, (lo, hi))
+    y = torch.nn.functional.conv1d(xt, torch.from_numpy(np.ascontiguousarray(w.transpose(2, 1, 0))),
+                                   torch.from_numpy(bias) if bias is not None else None)
+    if relu:
+        y = torch.relu_(y)
+    return y.permute(0, 2, 1).contiguous().numpy()
+
+
+def qconv2d_forward_torch_cpu(x, kernel, bias, filters, relu=True):
+    import torch
+    w = expand_conv_kernel(kernel, filters)                                  # [kh, kw, 4in_q, 4F]
+    kh, kw = w.shape[:2]
+    lo_h, hi_h, _ = pad_amounts(x.shape[2], kh, 1, 1, "same")
+    lo_w, hi_w, _ = pad_amounts(x.shape[3], kw, 1, 1, "same")
+    xt = torch.nn.functional.pad(torch.from_numpy(x), (lo_w, hi_w, lo_h, hi_h))
+    y = torch.nn.functional.conv2d(xt, torch.from_numpy(np.ascontiguousarray(w.transpose(3, 2, 0, 1))),
+                                   torch.from_numpy(bias) if bias is not None else None)
+    if relu:
+        y = torch.relu_(y)
+    return y.numpy()
+
+
+def qdense_forward_torch_cpu(x, kernel, bias, units, relu=True):
+    import torch
+    y = torch.from_numpy(x) @ torch.from_numpy(expand_dense_kernel(kernel, units // 4))
+    if bias is not None:
+        y += torch.from_numpy(bias)
+    if relu:
+        y = torch.relu_(y)
+    return y.numpy()
+
+
 def qmacs_conv(batch, out_spatial, kernel_size, in_q, filters):
     return int(batch) * int(np.prod(out_spatial)) * int(np.prod(kernel_size)) * int(in_q) * int(filters)
 
