@@ -165,7 +165,8 @@ int run_forward(const Geom& g, int rank, int math, int algo, const float* x, con
     const bool aligned =
         ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) == 0;
     if (algo == QNN_ALGO_TENSOR)
-        return g.channels_first ? tc2d_forward(g, rank, x, w, bias, y, st) : tc_forward(g, rank, x, w, bias, y, st);
+        return (g.channels_first || (!tc_plan(g, rank).ok && tc2d_plan(g, rank).ok)) ? tc2d_forward(g, rank, x, w, bias, y, st)
+                                                                                      : tc_forward(g, rank, x, w, bias, y, st);
     if (algo != QNN_ALGO_AUTO) {
         set_error("unknown algo %d", algo);
         return QNN_E_INVALID;

@@ -23,9 +23,15 @@
 //   * the epilogue transposes back through a [32 channels][128 positions] staging tile and TMA-stores it (4-D box),
 //     which also clips ragged tiles.
 // Work item = (tile, filter tile of <= 64 filters); persistent CTAs stride over the items.
+//
+// EXPERIMENTAL, off unless QNN_EXPERIMENTAL_CL2D=1 (written after round 1's GPU budget was spent: compiles, NOT yet run
+// on hardware): template parameter CL selects a channels_last rank-2 variant of the same main loop -- the x stage is a
+// 5-D box [8 q][4 components][128 + halo columns][1 row][1 sample] under the 128-byte swizzle (one 128-byte line per
+// position, read with 16-byte loads like qnn_hamilton_tc.cu), the epilogue stages [128 positions][32 channels] rows.
 // Warp roles and the TMEM plan are those of qnn_hamilton_tc.cu: warps 0-15 epilogue, 16-19 MMA issuers (one per output
 // component), 20-27 converters (two groups on alternate stages), 28 / 29 producers (x stages / sub-filter blocks); TMEM [0,256) accumulators, [256,512) eight A slots.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include "qnn_common.h"
 #include "qnn_ptx.cuh"
@@ -140,6 +146,20 @@ __device__ __forceinline__ void stage_chunk_t(const uint32_t (&v)[32], const flo
     for (int j = 0; j < 32; ++j) st[j * kTileM + r] = activate<ACT>(__uint_as_float(v[j]) + bias32[j], act_rt);
 }
 
+// channels_last variant: the same 32 columns as one 128-byte row of this thread's position, 128B-swizzled staging tile
+template <int ACT>
+__device__ __forceinline__ void stage_chunk_rows(const uint32_t (&v)[32], const float* bias32, uint8_t* st, int r, int act_rt) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        float4 o;
+        o.x = activate<ACT>(__uint_as_float(v[4 * j + 0]) + bias32[4 * j + 0], act_rt);
+        o.y = activate<ACT>(__uint_as_float(v[4 * j + 1]) + bias32[4 * j + 1], act_rt);
+        o.z = activate<ACT>(__uint_as_float(v[4 * j + 2]) + bias32[4 * j + 2], act_rt);
+        o.w = activate<ACT>(__uint_as_float(v[4 * j + 3]) + bias32[4 * j + 3], act_rt);
+        *reinterpret_cast<float4*>(st + swz128((uint32_t)r, (uint32_t)j)) = o;
+    }
+}
+
 struct ItemPos {
     int ft, b, ho, w0;
 };
@@ -154,7 +174,7 @@ __device__ __forceinline__ ItemPos item_pos(const P2& p, int item) {
     return ip;
 }
 
-template <int ACT>
+template <bool CL, int ACT>
 __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn, int which, int pair, int turn, int r,
                                           int n_out, int Fp, const ItemPos& ip, const P2& p, const float* bias_s,
                                           float* st, const CUtensorMap* tmy) {
@@ -164,19 +184,25 @@ __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn,
     const int ch0 = (col / Fp) * p.F + ip.ft * Fp + (col % Fp);  // first of 32 consecutive output channels
     const bool mine = turn == act_turn;
     if (mine) {
-        stage_chunk_t<ACT>(v, bias_s + ch0, st, r, p.act);
+        if (CL)
+            stage_chunk_rows<ACT>(v, bias_s + ch0, reinterpret_cast<uint8_t*>(st), r, p.act);
+        else
+            stage_chunk_t<ACT>(v, bias_s + ch0, st, r, p.act);
         fence_proxy_async_smem();
     }
     named_bar_sync(5 + pair, 256);
     if (mine && r == 0) {
-        tma_store_4d(tmy, st, ip.w0, ip.ho, ch0, ip.b);
+        if (CL)
+            tma_store_4d(tmy, st, ch0, ip.w0, ip.ho, ip.b);  // y[nb][Ho][Wo][4F]: box (32 channels, 128 positions, 1, 1)
+        else
+            tma_store_4d(tmy, st, ip.w0, ip.ho, ch0, ip.b);
         tma_store_commit();
         tma_store_wait_read<0>();  // the staging tile may now be overwritten by the partner group
     }
     named_bar_sync(5 + pair, 256);
 }
 
-template <bool CONJ, int ACT>
+template <bool CONJ, bool CL, int ACT>
 __global__ void __launch_bounds__(kThreads, 1)
 k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const P2 p,
                 const float* __restrict__ wp, const float* __restrict__ bias) {
@@ -284,7 +310,11 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
                     for (int kh = 0; kh < p.KH; ++kh) {
                         mbar_wait(&bars->x_empty[xs], xph ^ 1);
                         mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)(32 * p.wbox * 4));
-                        tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], cx, cy + kh * p.dh, qc * 8, cb);
+                        if (CL)  // x[nb][H][W][4][Q]: box (8 q, 4 components, wbox columns, 1 row, 1 sample)
+                            tma_load_5d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], qc * 8, 0,
+                                        ip.w0 - p.pad_w, cy + kh * p.dh, ip.b);
+                        else
+                            tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], cx, cy + kh * p.dh, qc * 8, cb);
                         if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
                     }
             }
@@ -337,15 +367,35 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
                     if (tr && s < 48 && tap0 == 0) trace(p, kTrConv + 4 * (s >> 1) + 1);
                     as_b = as;
                     for (int tb = 0; tb < nb; ++tb) {
-                        const float* xt = xb + (tap0 + tb) * p.dw;
                         const uint32_t dst = t_a + lane_base + as_b * kSlotCols;
+                        if (CL) {
+                            // one 128-byte line per position: [4 components][8 q], 16-byte chunks XORed with row % 8
+                            const uint32_t row = (uint32_t)(r + (tap0 + tb) * p.dw);
+                            const uint8_t* xrow = x_s + (size_t)xs * p.x_stage_bytes + row * 128u;
+                            const uint32_t sw = row & 7u;
 #pragma unroll
-                        for (int h = 0; h < 2; ++h) {
-                            uint32_t u[16];
+                            for (int h = 0; h < 2; ++h) {
+                                uint32_t u[16];
 #pragma unroll
-                            for (int c = 0; c < 16; ++c)
-                                u[c] = __float_as_uint(xt[(h * 16 + c) * ch_stride]) + 0x1000u;  // round to nearest tf32
-                            tmem_st16_nc(dst + h * 16, u);
+                                for (int c4 = 0; c4 < 4; ++c4) {
+                                    const uint4 v = *reinterpret_cast<const uint4*>(xrow + (((h * 4 + c4) ^ sw) << 4));
+                                    u[4 * c4 + 0] = v.x + 0x1000u;
+                                    u[4 * c4 + 1] = v.y + 0x1000u;
+                                    u[4 * c4 + 2] = v.z + 0x1000u;
+                                    u[4 * c4 + 3] = v.w + 0x1000u;
+                                }
+                                tmem_st16_nc(dst + h * 16, u);
+                            }
+                        } else {
+                            const float* xt = xb + (tap0 + tb) * p.dw;
+#pragma unroll
+                            for (int h = 0; h < 2; ++h) {
+                                uint32_t u[16];
+#pragma unroll
+                                for (int c = 0; c < 16; ++c)
+                                    u[c] = __float_as_uint(xt[(h * 16 + c) * ch_stride]) + 0x1000u;  // round to nearest tf32
+                                tmem_st16_nc(dst + h * 16, u);
+                            }
                         }
                         if (++as_b == kSlots) as_b = 0;
                     }
@@ -385,10 +435,10 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
             tmem_wait_ld();
             tc_fence_before_sync();
             mbar_arrive(&bars->acc_empty);  // accumulators are in registers: the next item's MMAs may start
-            epi_phase<ACT>(v0, 0, 0, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
-            epi_phase<ACT>(v0, 1, 0, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
-            epi_phase<ACT>(v1, 0, 1, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
-            epi_phase<ACT>(v1, 1, 1, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
+            epi_phase<CL, ACT>(v0, 0, 0, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
+            epi_phase<CL, ACT>(v0, 1, 0, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
+            epi_phase<CL, ACT>(v1, 0, 1, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
+            epi_phase<CL, ACT>(v1, 1, 1, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
             if (e == 0 && icount < 12) trace(p, kTrItem + 4 * icount + 3);
             accph ^= 1;
         }
@@ -445,10 +495,13 @@ typedef void (*Tc2dKernel)(const CUtensorMap, const CUtensorMap, const P2, const
 unsigned long long* g_trace2d = nullptr;
 size_t g_trace2d_bytes = 0;
 
-Tc2dKernel pick_kernel(int act) {
+Tc2dKernel pick_kernel(int act, bool channels_last) {
     const int a = act == QNN_ACT_LINEAR ? kActLinear : (act == QNN_ACT_RELU ? kActRelu : kActGeneric);
-    return a == kActLinear ? k_hamilton_tc2d<false, kActLinear>
-                           : a == kActRelu ? k_hamilton_tc2d<false, kActRelu> : k_hamilton_tc2d<false, kActGeneric>;
+    if (channels_last)
+        return a == kActLinear ? k_hamilton_tc2d<false, true, kActLinear>
+                               : a == kActRelu ? k_hamilton_tc2d<false, true, kActRelu> : k_hamilton_tc2d<false, true, kActGeneric>;
+    return a == kActLinear ? k_hamilton_tc2d<false, false, kActLinear>
+                           : a == kActRelu ? k_hamilton_tc2d<false, false, kActRelu> : k_hamilton_tc2d<false, false, kActGeneric>;
 }
 
 }  // namespace
@@ -465,18 +518,28 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank) {
         pl.why = why;
         return pl;
     };
-    if (!g.channels_first) return no("channels_last layout");
+    const bool cl = !g.channels_first;
+    if (cl) {
+        // channels_last rank 2: experimental variant, opt-in (see the header comment); rank 1 belongs to qnn_hamilton_tc.cu
+        static const bool enabled = [] {
+            const char* e = getenv("QNN_EXPERIMENTAL_CL2D");
+            return e && e[0] == '1';
+        }();
+        if (!enabled) return no("channels_last layout (rank 2 variant is experimental: QNN_EXPERIMENTAL_CL2D=1)");
+        if (rank != 2) return no("channels_last rank 1 / 3");
+    }
     if (rank > 2) return no("rank 3");
     if (g.conj_w) return no("dense table");
     if (g.s[1] != 1 || g.s[2] != 1) return no("stride != 1");
     if (g.in_q % 8) return no("in_q not a multiple of 8");
     if (g.F % 32) return no("filters not a multiple of 32");
-    if (g.in_sp[2] % 4 || g.out_sp[2] % 4) return no("row length not a multiple of 4 (TMA stride alignment)");
+    if (!cl && (g.in_sp[2] % 4 || g.out_sp[2] % 4)) return no("row length not a multiple of 4 (TMA stride alignment)");
     if (g.out_sp[2] < 1 || g.out_sp[1] < 1 || g.batch < 1) return no("empty problem");
-    // un-swizzled TMA boxes must start on a 16-byte boundary of the innermost axis (measured: an odd start column is an
-    // illegal instruction, profiles/r01_tma_box_probe.log), so the box starts up to 3 columns early
-    const int xshift = (4 - (g.pad_lo[2] & 3)) & 3;
-    const int wbox = (kTileM + (g.k[2] - 1) * g.d[2] + xshift + 3) & ~3;
+    // channels_first: un-swizzled TMA boxes must start on a 16-byte boundary of the innermost axis (measured: an odd start
+    // column is an illegal instruction, profiles/r01_tma_box_probe.log), so the box starts up to 3 columns early.
+    // channels_last: the column axis is not the innermost one, any start works.
+    const int xshift = cl ? 0 : (4 - (g.pad_lo[2] & 3)) & 3;
+    const int wbox = cl ? kTileM + (g.k[2] - 1) * g.d[2] : (kTileM + (g.k[2] - 1) * g.d[2] + xshift + 3) & ~3;
     if (wbox > 256) return no("halo exceeds the 256-element TMA box");
     const int f_tile = g.F % 64 == 0 ? 64 : 32;
     const size_t blk = (size_t)32 * f_tile * 4;
@@ -536,7 +599,7 @@ int tc2d_forward(const Geom& g, int rank, const float* x, const float* w, const 
     p.b_blk_bytes = (uint32_t)(32 * pl.f_tile * 4);
 
     CUtensorMap tmx, tmy;
-    {
+    if (g.channels_first) {
         // x[nb][4][Q][H][W] seen as [nb*4][Q][H][W]: box = (wbox positions, 1 row, 8 quaternion channels, the 4
         // components of one sample), no swizzle
         const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)Q, (uint64_t)4 * g.batch};
@@ -547,21 +610,39 @@ int tc2d_forward(const Geom& g, int rank, const float* x, const float* w, const 
             set_error("cuTensorMapEncodeTiled(x, channels_first) failed (%d)", e);
             return QNN_E_CUDA;
         }
-    }
-    {
         // y[nb][4F][Ho][Wo]: box = (128 positions, 1 row, 32 channels, 1 sample)
-        const uint64_t dims[4] = {(uint64_t)Wo, (uint64_t)Ho, (uint64_t)4 * F, (uint64_t)g.batch};
-        const uint64_t str[3] = {(uint64_t)Wo * 4, (uint64_t)Ho * Wo * 4, (uint64_t)4 * F * Ho * Wo * 4};
-        const uint32_t box[4] = {(uint32_t)kTileM, 1, 32, 1};
-        int e = make_tmap_f32(&tmy, y, 4, dims, str, box, false);
+        const uint64_t ydims[4] = {(uint64_t)Wo, (uint64_t)Ho, (uint64_t)4 * F, (uint64_t)g.batch};
+        const uint64_t ystr[3] = {(uint64_t)Wo * 4, (uint64_t)Ho * Wo * 4, (uint64_t)4 * F * Ho * Wo * 4};
+        const uint32_t ybox[4] = {(uint32_t)kTileM, 1, 32, 1};
+        e = make_tmap_f32(&tmy, y, 4, ydims, ystr, ybox, false);
         if (e) {
             set_error("cuTensorMapEncodeTiled(y, channels_first) failed (%d)", e);
             return QNN_E_CUDA;
         }
+    } else {
+        // x[nb][H][W][4][Q]: box = (8 quaternion channels, 4 components, wbox positions, 1 row, 1 sample) -> one 128-byte
+        // line per position, 128B swizzle
+        const uint64_t dims[5] = {(uint64_t)Q, 4, (uint64_t)W, (uint64_t)H, (uint64_t)g.batch};
+        const uint64_t str[4] = {(uint64_t)Q * 4, (uint64_t)Q * 16, (uint64_t)W * Q * 16, (uint64_t)H * W * Q * 16};
+        const uint32_t box[5] = {8, 4, (uint32_t)pl.wbox, 1, 1};
+        int e = make_tmap_f32(&tmx, x, 5, dims, str, box, true);
+        if (e) {
+            set_error("cuTensorMapEncodeTiled(x, channels_last rank 2) failed (%d)", e);
+            return QNN_E_CUDA;
+        }
+        // y[nb][Ho][Wo][4F]: box = (32 channels, 128 positions, 1 row, 1 sample), 128B swizzle
+        const uint64_t ydims[4] = {(uint64_t)4 * F, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)g.batch};
+        const uint64_t ystr[3] = {(uint64_t)F * 16, (uint64_t)Wo * F * 16, (uint64_t)Ho * Wo * F * 16};
+        const uint32_t ybox[4] = {32, (uint32_t)kTileM, 1, 1};
+        e = make_tmap_f32(&tmy, y, 4, ydims, ystr, ybox, true);
+        if (e) {
+            set_error("cuTensorMapEncodeTiled(y, channels_last rank 2) failed (%d)", e);
+            return QNN_E_CUDA;
+        }
     }
-    Tc2dKernel kern = pick_kernel(g.act);
+    Tc2dKernel kern = pick_kernel(g.act, !g.channels_first);
     static std::mutex mu;
-    static Tc2dKernel configured[4];
+    static Tc2dKernel configured[8];
     static int n_configured = 0;
     {
         std::lock_guard<std::mutex> lock(mu);

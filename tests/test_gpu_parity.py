@@ -580,3 +580,22 @@ def test_tensor_core_dgrad_dense_vs_oracle(cnn, rows, in_q, units, act):
     emax, efro = errs(dk.cpu().numpy(), rdk)
     assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "dkernel: max-rel %.3e fro-rel %.3e" % (emax, efro)
     check(db.cpu().numpy(), rdb, 1e-4, "dbias")
+
+
+@pytest.mark.skipif(os.environ.get("QNN_EXPERIMENTAL_CL2D") != "1",
+                    reason="experimental channels_last rank-2 tensor-core variant: written after round 1's GPU budget was "
+                           "spent, never run on hardware; opt in with QNN_EXPERIMENTAL_CL2D=1 (run it in its own process)")
+@pytest.mark.parametrize("shape", [(1, (4, 128), 8, 32, (3, 3), (1, 1), "same"), (2, (5, 131), 16, 64, (3, 5), (1, 1), "same"),
+                                   (1, (9, 70), 8, 128, (3, 2), (2, 1), "valid")])
+def test_experimental_channels_last_conv2d_tensor_core(cnn, native_lib, shape):
+    from complexnn import _ops
+    from complexnn._layer import Variable
+    B, sp, in_q, F, k, d, pad = shape
+    rng = np.random.default_rng(B + in_q + F)
+    x = rng.normal(size=(B,) + sp + (4 * in_q,)).astype(np.float32)
+    kern = (rng.normal(size=k + (in_q, 4 * F)) / np.sqrt(4 * in_q * np.prod(k))).astype(np.float32)
+    bias = rng.normal(0, 0.1, size=4 * F).astype(np.float32)
+    y = _ops.conv_forward(dev(x), Variable(kern), Variable(bias), F, k, (1, 1), pad, "channels_last", d, "relu",
+                          math="tf32", algo="tensor")
+    ref = O.qconv_forward(x, kern, bias, F, (1, 1), pad, "channels_last", d, "relu")
+    check_tf32(y.cpu().numpy(), ref, O.qconv_abs_bound(x, kern, F, (1, 1), pad, "channels_last", d), str(shape))
