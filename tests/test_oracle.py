@@ -168,3 +168,26 @@ def test_empty_and_ragged_shapes():
     assert O.qconv_forward(np.zeros((2, 2, 4), np.float32), k, None, 2).shape == (2, 0, 8)     # shorter than the kernel
     assert O.qconv_forward(np.zeros((2, 2, 4), np.float32), k, None, 2, padding="same").shape == (2, 2, 8)
     assert O.conv_output_length(7, 3, "same", 2) == 4 and O.conv_output_length(7, 3, "valid", 2, 2) == 2
+
+
+def test_timed_cpu_baselines_agree_with_the_oracle():
+    """The fp32 restatements bench.py times as the CPU arm (NumPy im2col + sgemm, and torch-CPU / oneDNN conv on the
+    expanded weight) compute the same thing as the fp64 oracle."""
+    rng = np.random.default_rng(11)
+    x = rng.normal(size=(3, 50, 16)).astype(np.float32)
+    k = (rng.normal(size=(3, 4, 32)) * 0.2).astype(np.float32)
+    b = rng.normal(0, 0.1, 32).astype(np.float32)
+    for pad in ("same", "valid", "causal"):
+        ref = O.qconv_forward(x, k, b, 8, 1, pad, "channels_last", 1, "relu")
+        for fn in (O.qconv1d_forward_f32, O.qconv1d_forward_torch_cpu):
+            np.testing.assert_allclose(fn(x, k, b, 8, pad, True), ref, rtol=1e-5, atol=1e-5)
+    x2 = rng.normal(size=(2, 16, 9, 10)).astype(np.float32)
+    k2 = (rng.normal(size=(3, 2, 4, 32)) * 0.2).astype(np.float32)
+    ref2 = O.qconv_forward(x2, k2, b, 8, (1, 1), "same", "channels_first", (1, 1), "relu")
+    for fn in (O.qconv2d_forward_f32, O.qconv2d_forward_torch_cpu):
+        np.testing.assert_allclose(fn(x2, k2, b, 8, True), ref2, rtol=1e-5, atol=1e-5)
+    xd = rng.normal(size=(7, 16)).astype(np.float32)
+    kd = (rng.normal(size=(4, 32)) * 0.2).astype(np.float32)
+    refd = O.qdense_forward(xd, kd, b, 32, "relu")
+    for fn in (O.qdense_forward_f32, O.qdense_forward_torch_cpu):
+        np.testing.assert_allclose(fn(xd, kd, b, 32, True), refd, rtol=1e-5, atol=1e-5)
