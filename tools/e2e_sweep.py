@@ -1,8 +1,9 @@
+"""Host-buffer path (qnn_conv_forward_host, cfg 2) timed for several pipeline chunk counts: python tools/e2e_sweep.py 1 2 4 8 16"""
 import ctypes, os, sys, time
 import numpy as np, torch
-REPO="/root/repo"
-PKG=os.path.join(REPO,"quaternion-convolutional-neural-networks-for-end-to-end-automatic-speech-recognition_b200")
-sys.path[:0]=[REPO,PKG]
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(REPO, "quaternion-convolutional-neural-networks-for-end-to-end-automatic-speech-recognition_b200")
+sys.path[:0] = [REPO, PKG]
 from complexnn import _native
 lib=_native.lib()
 x=torch.randn(256,256,160).pin_memory(); y=torch.empty(256,256,256).pin_memory()
