@@ -262,7 +262,38 @@ class AveragePooling2D(_Unsupported): pass
 class AveragePooling3D(_Unsupported): pass
 class BatchNormalization(_Unsupported): pass
 class ConvLSTM2D(_Unsupported): pass
-class PReLU(_Unsupported): pass
+
+class PReLU(Layer):
+    """keras.layers.PReLU: f(x) = max(x, 0) + alpha * min(x, 0) with a learned alpha per feature, shared over
+    `shared_axes` (1-based, batch excluded).  models/interspeech_model.py:95-99 puts `PReLU(shared_axes=[1, 0])` after
+    the quaternion convolutions; like Keras, axis 0 lands on `param_shape[-1]` (Python's negative index), which is what
+    makes the variable-length time axis shareable there."""
+
+    def __init__(self, alpha_initializer="zeros", alpha_regularizer=None, alpha_constraint=None, shared_axes=None, **kwargs):
+        super(PReLU, self).__init__(**kwargs)
+        self.alpha_initializer = get_initializer(alpha_initializer)
+        if shared_axes is None:
+            self.shared_axes = None
+        elif not isinstance(shared_axes, (list, tuple)):
+            self.shared_axes = [shared_axes]
+        else:
+            self.shared_axes = list(shared_axes)
+
+    def build(self, input_shape):
+        param_shape = list(input_shape[1:])
+        for i in self.shared_axes or []:
+            param_shape[i - 1] = 1
+        if any(d is None for d in param_shape):
+            raise ValueError("PReLU needs every unshared axis to be defined, got input shape %s" % (tuple(input_shape),))
+        self.alpha = self.add_weight(shape=tuple(param_shape), initializer=self.alpha_initializer, name="alpha")
+        self.built = True
+
+    def call(self, inputs):
+        return torch.relu(inputs) - self.alpha.device(inputs.device) * torch.relu(-inputs)
+
+    def compute_output_shape(self, input_shape):
+        return tuple(input_shape)
+
 class Add(_Unsupported): pass
 class Concatenate(_Unsupported): pass
 

@@ -191,3 +191,22 @@ def test_fit_reduces_loss_like_working_example(facade_path, native_lib):
     loss1, acc1 = model.evaluate(x, y)
     assert loss1 < 0.5 * loss0 and acc1 > 0.9 and len(hist.history["loss"]) == 6
     assert set(hist.history) == {"loss", "acc", "val_loss", "val_acc"}
+
+
+def test_prelu_matches_keras_definition_on_cpu(facade_path):
+    """interspeech_model.py:95-99: PReLU(shared_axes=[1, 0]) after a channels_first quaternion conv with a variable-length
+    time axis -- alpha has shape (1, 41, 1); f(x) = max(x, 0) + alpha * min(x, 0)."""
+    import torch
+    from keras.layers import Input, PReLU
+    layer = PReLU(shared_axes=[1, 0])
+    out = layer(Input((128, 41, None)))
+    assert out.shape == (None, 128, 41, None)
+    assert [tuple(w.shape) for w in layer.weights] == [(1, 41, 1)]
+    alpha = np.linspace(-0.5, 0.5, 41).astype(np.float32).reshape(1, 41, 1)
+    layer.set_weights([alpha])
+    x = torch.randn(2, 128, 41, 7)
+    y = layer.call(x).numpy()
+    xn = x.numpy()
+    np.testing.assert_allclose(y, np.maximum(xn, 0) + alpha[None] * np.minimum(xn, 0), rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        PReLU()(Input((4, None)))          # an unshared undefined axis cannot carry a weight
