@@ -121,5 +121,19 @@ def ctc_batch_cost(*args, **kwargs):
     raise NotImplementedError("CTC is outside the quaternion conv/dense path")
 
 
-def function(inputs, outputs, **kwargs):
-    raise NotImplementedError("K.function: use Model.predict with the facade")
+def function(inputs, outputs, updates=None, **kwargs):
+    """K.function(inputs, outputs): a callable taking a list of arrays and returning a list of NumPy arrays
+    (models/interspeech_model.py:184 builds its validation function this way).  Runs the recorded layer graph eagerly on
+    the CUDA device, like Model.predict."""
+    from ..models import Model
+    models = [Model(list(inputs), o) for o in outputs]
+
+    def run(feeds):
+        import torch
+        outs = []
+        with torch.no_grad():
+            for m in models:
+                outs.append(m._forward([m._to_device(f) for f in feeds], False).cpu().numpy())
+        return outs
+
+    return run

@@ -82,13 +82,26 @@ def test_reference_model_files_import_and_build_unchanged(facade_path):
                                                                "QuaternionDense", "Dense"]
         p.model = "CNN"
         assert CNN(p).count_params() == 533128
-        import models.interspeech_model as im           # Python-2 source: importable, not callable (xrange, n/2)
+        import models.interspeech_model as im           # Python-2 source (xrange, n/2): importable ...
         assert hasattr(im, "getTimitModel2D")
-        with pytest.raises(NameError):
-            class D(object):
-                num_layers, start_filter, act, aact, dropout, l2, model, quat_init = 2, 8, "relu", "none", 0.1, 1e-4, \
-                    "quaternion", "quaternion"
+
+        class D(object):
+            num_layers, start_filter, act, aact, dropout, l2, model, quat_init = 4, 8, "relu", "prelu", 0.1, 1e-4, \
+                "quaternion", "quaternion"
+        with pytest.raises(NameError):                  # ... not callable under Python 3 as it stands,
             im.getTimitModel2D(D())
+        import builtins                                 # ... but it is with a Python-2 `xrange` stand-in and nothing else:
+        builtins.xrange = lambda *a: range(*[int(v) for v in a])
+        try:
+            timit, val_function = im.getTimitModel2D(D())
+        finally:
+            del builtins.xrange
+        names = [l.__class__.__name__ for l in timit.layers]
+        assert names.count("QuaternionConv2D") == 5 and names.count("PReLU") == 8 and names.count("TimeDistributed") == 4
+        assert names[:3] == ["QuaternionConv2D", "PReLU", "MaxPooling2D"] and names[-1] == "Lambda"     # ... -> CTC lambda
+        assert [tuple(w.shape) for w in timit.layers[0].weights] == [(3, 5, 1, 32), (32,)]     # in_q = 1, 8 filters (F2)
+        assert [tuple(w.shape) for w in timit.layers[1].weights] == [(1, 41, 1)]               # PReLU(shared_axes=[1, 0])
+        assert timit.count_params() == 138338 and callable(val_function)
     finally:
         sys.path.remove(REF)
         for m in ("models", "models.example_model", "models.interspeech_model"):

@@ -26,6 +26,9 @@ def main():
     # our packages shadow the reference's `complexnn`; the reference's `models` package and data files stay visible
     sys.path[:0] = [PKG, os.path.join(PKG, "keras_facade")]
     sys.path.append(ref)
+    import builtins
+    if not hasattr(builtins, "xrange"):    # models/interspeech_model.py is Python-2 source (xrange(0, n/2)): a stand-in
+        builtins.xrange = lambda *a: range(*[int(v) for v in a])   # lets getTimitModel2D run unchanged under Python 3
     os.chdir(ref)                      # the script opens 'decoda/...' relative to its checkout
     sys.argv = [script] + rest
     runpy.run_path(os.path.join(ref, script), run_name="__main__")
