@@ -148,5 +148,19 @@ def softmax(x, axis=-1):
     return _t(e / e.sum(axis=axis, keepdims=True))
 
 
-def ctc_batch_cost(*a, **k):
-    raise NotImplementedError("CTC is outside the quaternion conv/dense path")
+def reshape(x, shape):
+    return _t(np.reshape(np.asarray(x), tuple(int(v) for v in shape)))
+
+
+def function(inputs, outputs, updates=None, **kwargs):
+    """K.function([x], [y]) (models/interspeech_model.py:184): evaluates the recorded graph of y for a fed x."""
+    from ..models import Model
+    models = [Model(inputs[0] if len(inputs) == 1 else inputs, o) for o in outputs]
+    return lambda feeds: [m.predict(feeds[0]) for m in models]
+
+
+def ctc_batch_cost(y_true, y_pred, input_length, label_length):
+    """CTC is outside the quaternion conv/dense path: a placeholder of the right shape, so that the reference's model
+    builder (which wires the loss into the graph, models/interspeech_model.py:37-39,178) can run to completion.  Nothing
+    reads its value."""
+    return _t(np.zeros((np.shape(y_pred)[0], 1), dtype=_FLOATX))

@@ -274,6 +274,79 @@ class AveragePooling1D(Layer):
         return y
 
 
+class MaxPooling2D(Layer):
+    """tf.nn.max_pool semantics (SAME pads with -inf, the odd element at the end)."""
+
+    def __init__(self, pool_size=(2, 2), strides=None, padding="valid", data_format=None, **kwargs):
+        super(MaxPooling2D, self).__init__(**kwargs)
+        self.pool_size = (pool_size, pool_size) if isinstance(pool_size, int) else tuple(pool_size)
+        strides = self.pool_size if strides is None else strides
+        self.strides = (strides, strides) if isinstance(strides, int) else tuple(strides)
+        self.padding = padding.lower()
+        self.data_format = K.normalize_data_format(data_format)
+
+    def call(self, inputs):
+        x = np.asarray(inputs)
+        if self.data_format == "channels_last":
+            x = np.moveaxis(x, -1, 1)
+        pads, outs = [], []
+        for a in range(2):
+            lo, hi, out = K._pad_amounts(x.shape[2 + a], self.pool_size[a], self.strides[a], 1, self.padding)
+            pads.append((lo, hi))
+            outs.append(out)
+        xp = np.pad(x, ((0, 0), (0, 0)) + tuple(pads), constant_values=-np.inf)
+        y = np.full(x.shape[:2] + tuple(outs), -np.inf, dtype=x.dtype)
+        for i in range(self.pool_size[0]):
+            for j in range(self.pool_size[1]):
+                y = np.maximum(y, xp[:, :, i:i + (outs[0] - 1) * self.strides[0] + 1:self.strides[0],
+                                     j:j + (outs[1] - 1) * self.strides[1] + 1:self.strides[1]])
+        return y if self.data_format == "channels_first" else np.moveaxis(y, 1, -1)
+
+
+class TimeDistributed(Layer):
+    """Applies the wrapped layer to every time step: (B, T, ...) -> reshape (B*T, ...) -> layer -> (B, T, ...)."""
+
+    def __init__(self, layer, **kwargs):
+        super(TimeDistributed, self).__init__(**kwargs)
+        self.layer = layer
+
+    def call(self, inputs):
+        x = np.asarray(inputs)
+        y = np.asarray(self.layer(K._t(x.reshape((x.shape[0] * x.shape[1],) + x.shape[2:]))))
+        return y.reshape((x.shape[0], x.shape[1]) + y.shape[1:])
+
+    def get_weights(self):
+        return self.layer.get_weights()
+
+    def set_weights(self, weights):
+        self.layer.set_weights(weights)
+
+    def count_params(self):
+        return self.layer.count_params()
+
+
+class PReLU(Layer):
+    """f(x) = max(x, 0) + alpha * min(x, 0); alpha per feature, shared over `shared_axes` (Keras' own index arithmetic:
+    param_shape[i - 1] = 1, so axis 0 lands on the LAST axis)."""
+
+    def __init__(self, alpha_initializer="zeros", alpha_regularizer=None, alpha_constraint=None, shared_axes=None, **kwargs):
+        super(PReLU, self).__init__(**kwargs)
+        self.alpha_initializer = initializers.get(alpha_initializer)
+        self.shared_axes = None if shared_axes is None else list(shared_axes) if isinstance(shared_axes, (list, tuple)) \
+            else [shared_axes]
+
+    def build(self, input_shape):
+        param_shape = list(input_shape[1:])
+        for i in self.shared_axes or []:
+            param_shape[i - 1] = 1
+        self.alpha = self.add_weight(shape=tuple(param_shape), name="alpha", initializer=self.alpha_initializer)
+        self.built = True
+
+    def call(self, inputs):
+        x = np.asarray(inputs)
+        return np.maximum(x, 0) + np.asarray(self.alpha) * np.minimum(x, 0)
+
+
 class _Stub(Layer):
     def __init__(self, *a, **k):
         raise NotImplementedError(self.__class__.__name__ + " is outside the quaternion conv/dense path")
@@ -281,11 +354,8 @@ class _Stub(Layer):
 
 class AveragePooling2D(_Stub): pass
 class AveragePooling3D(_Stub): pass
-class MaxPooling2D(_Stub): pass
 class BatchNormalization(_Stub): pass
 class ConvLSTM2D(_Stub): pass
-class TimeDistributed(_Stub): pass
-class PReLU(_Stub): pass
 class Add(_Stub): pass
 class Concatenate(_Stub): pass
 

@@ -130,6 +130,41 @@ def main():
         dec[tag + ".probs"] = f32(out)
         print(tag, "layers", [l.name for l in model.layers], "out", out.shape, "argmax", out.argmax(-1)[:8])
     np.savez(os.path.join(OUT, "decoda_models.npz"), **dec)
+
+    # config 3 (secondary reading): the reference's own TIMIT builder, models/interspeech_model.py:getTimitModel2D
+    # -- Python-2 source, run unchanged with a stand-in for `xrange` -- QuaternionConv2D (3,5) channels_first stack with
+    # PReLU(shared_axes=[1,0]), MaxPooling2D((1,3)), Permute + reshape, 3 x TimeDistributed(QuaternionDense(256)),
+    # TimeDistributed(Dense(62, softmax)); evaluated through its own validation function K.function([I], [pred]).
+    import builtins
+    builtins.xrange = lambda *a: range(*[int(v) for v in a])
+    try:
+        import models.interspeech_model as im
+    finally:
+        pass
+
+    class D(object):
+        num_layers, start_filter, act, aact, dropout, l2, model, quat_init = 4, 8, "relu", "prelu", 0.1, 1e-4, \
+            "quaternion", "quaternion"
+    np.random.seed(400)
+    rng = np.random.default_rng(400)
+    timit, val_function = im.getTimitModel2D(D())
+    del builtins.xrange
+    tm = {"x": f32(rng.normal(0, 1, (2, 4, 41, 12)))}
+    k = 0
+    for l in timit.layers:
+        ws = [f32(w) for w in l.get_weights()]
+        if l.__class__.__name__ == "PReLU":                       # zeros-initialised: give the slopes something to do
+            ws = [f32(rng.uniform(-0.3, 0.3, w.shape)) for w in ws]
+        elif len(ws) == 2:
+            ws[1] = f32(rng.normal(0, 0.1, ws[1].shape))          # non-zero biases
+        l.set_weights([w.astype(np.float64) for w in ws])
+        for w in ws:
+            tm["w%d" % k] = w
+            k += 1
+    tm["layers"] = np.array([l.__class__.__name__ for l in timit.layers])
+    tm["pred"] = f32(val_function([tm["x"].astype(np.float64)])[0])
+    print("TIMIT", len(timit.layers), "layers,", k, "weight arrays, pred", tm["pred"].shape, "row sums", tm["pred"].sum(-1).ravel()[:3])
+    np.savez(os.path.join(OUT, "timit_model.npz"), **tm)
     total = sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT))
     print("golden bytes:", total)
 

@@ -191,3 +191,41 @@ def test_timed_cpu_baselines_agree_with_the_oracle():
     refd = O.qdense_forward(xd, kd, b, 32, "relu")
     for fn in (O.qdense_forward_f32, O.qdense_forward_torch_cpu):
         np.testing.assert_allclose(fn(xd, kd, b, 32, True), refd, rtol=1e-5, atol=1e-5)
+
+
+def timit_oracle_forward(g, conv=None, dense=None):
+    """models/interspeech_model.py:getTimitModel2D (quaternion variant, n = 4 layers, sf = 8, PReLU) restated layer by layer
+    on the weights of tests/golden/timit_model.npz.  `conv` / `dense` default to the oracle; the GPU test passes the
+    product layers' forward instead."""
+    conv = conv or (lambda h, k, b, F: O.qconv_forward(h, k, b, F, (1, 1), "same", "channels_first", (1, 1), None))
+    dense = dense or (lambda h, k, b: O.qdense_forward(h, k, b, 256, None))
+    prelu = lambda h, a: np.maximum(h, 0) + a * np.minimum(h, 0)
+    w = [g["w%d" % i] for i in range(26)]
+    h = prelu(conv(g["x"], w[0], w[1], 8), w[2][None])
+    # MaxPooling2D((1, 3), 'same') with Keras' DEFAULT data_format (channels_last) on a channels_first tensor: it pools
+    # the 41-feature axis by 3 (SAME: one -inf column at the end), exactly what the reference model does
+    hp = np.pad(h, ((0, 0), (0, 0), (0, 1), (0, 0)), constant_values=-np.inf)
+    h = hp.reshape(h.shape[0], h.shape[1], 14, 3, h.shape[3]).max(axis=3)
+    i = 3
+    for F in (8, 8, 16, 16):
+        h = prelu(conv(h, w[i], w[i + 1], F), w[i + 2][None])
+        i += 3
+    B, C, Fq, T = h.shape
+    h = np.transpose(h, (0, 3, 1, 2)).reshape(B * T, C * Fq)
+    for _ in range(3):
+        h = prelu(dense(np.ascontiguousarray(h, dtype=np.float32), w[i], w[i + 1]), w[i + 2])
+        i += 3
+    z = h.astype(np.float64) @ w[i] + w[i + 1]
+    e = np.exp(z - z.max(-1, keepdims=True))
+    return (e / e.sum(-1, keepdims=True)).reshape(B, T, 62)
+
+
+def test_timit_model_oracle_matches_the_reference_builder(golden):
+    """The oracle chained as getTimitModel2D chains its layers reproduces what the reference's own builder computed
+    (through its validation function) on the Keras stand-in: pins QuaternionConv2D channels_first (3,5) 'same' with
+    in_q = 1 / 8 / 16 and TimeDistributed(QuaternionDense) with in_q = 224 / 64."""
+    g = golden.load("timit_model")
+    assert list(g["layers"][:3]) == ["QuaternionConv2D", "PReLU", "MaxPooling2D"] and g["w0"].shape == (3, 5, 1, 32)
+    pred = timit_oracle_forward(g)
+    np.testing.assert_allclose(pred, g["pred"], rtol=2e-4, atol=2e-6)
+    np.testing.assert_allclose(pred.sum(-1), 1.0, rtol=1e-6)
