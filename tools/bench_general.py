@@ -2,7 +2,6 @@
 """Timing of the general (CUDA-core) kernels on shapes the tensor-core kernel does not take (diagnostics)."""
 import os
 import sys
-import time
 
 import numpy as np
 import torch

@@ -2,7 +2,6 @@
    python tools/try_tc2d.py [--time] [--big]"""
 import os
 import sys
-import time
 
 import numpy as np
 import torch
