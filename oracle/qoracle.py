@@ -22,7 +22,6 @@ torch.nn.functional.conv{1,2,3}d in tests/test_oracle.py.
 """
 from __future__ import annotations
 
-import math
 import numpy as np
 
 # ----------------------------------------------------------------------------------------------------------------------
