@@ -1,6 +1,8 @@
 """CPU tests of the oracle (oracle/qoracle.py): it must reproduce the golden vectors produced by the reference's own
 code (oracle/make_golden.py), agree with an independent conv implementation (torch CPU, fp64) and with its own
 direct 16-block formulation, and its gradients must pass finite differences."""
+import os
+
 import numpy as np
 import pytest
 
@@ -229,3 +231,83 @@ def test_timit_model_oracle_matches_the_reference_builder(golden):
     pred = timit_oracle_forward(g)
     np.testing.assert_allclose(pred, g["pred"], rtol=2e-4, atol=2e-6)
     np.testing.assert_allclose(pred.sum(-1), 1.0, rtol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# The plain-C restatement (oracle/qoracle_c.c): a third, independent implementation of the reference path
+# ----------------------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def c_oracle():
+    import ctypes
+    import importlib.util
+    from conftest import REPO
+    spec = importlib.util.spec_from_file_location("graft_entry", os.path.join(REPO, "__graft_entry__.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    lib = ctypes.CDLL(mod.build_c_oracle())
+    fp, i = ctypes.POINTER(ctypes.c_float), ctypes.c_int
+    lib.qoc_conv1d_forward.argtypes = [fp, fp, fp, fp] + [i] * 9
+    lib.qoc_conv2d_cf_forward.argtypes = [fp, fp, fp, fp] + [i] * 13
+    lib.qoc_dense_forward.argtypes = [fp, fp, fp, fp] + [i] * 4
+    lib.qoc_conv1d_out_len.argtypes = [i] * 5
+    return lib
+
+
+def _fp(a):
+    import ctypes
+    return None if a is None else a.ctypes.data_as(ctypes.POINTER(ctypes.c_float))
+
+
+PADS = {"valid": 0, "same": 1, "causal": 2}
+
+
+def test_c_oracle_matches_reference_golden_and_numpy_oracle(c_oracle, golden):
+    g = golden.load("conv_forward")
+    checked = 0
+    for name, rank, xs, filters, ksz, kw in CONV_CASES:
+        k = conv_kwargs(rank, kw)
+        if k["activation"] not in (None, "relu"):
+            continue
+        x, kern, bias = g[name + ".x"], g[name + ".kernel"], g.get(name + ".bias")
+        relu = int(k["activation"] == "relu")
+        if rank == 1 and k["data_format"] == "channels_last":
+            B, L, C = x.shape
+            Lo = c_oracle.qoc_conv1d_out_len(L, kern.shape[0], k["strides"][0], k["dilation_rate"][0], PADS[k["padding"]])
+            y = np.empty((B, Lo, 4 * filters), np.float32)
+            rc = c_oracle.qoc_conv1d_forward(_fp(x), _fp(kern), _fp(bias), _fp(y), B, L, C // 4, filters, kern.shape[0],
+                                             k["strides"][0], k["dilation_rate"][0], PADS[k["padding"]], relu)
+            assert rc == Lo
+        elif rank == 2 and k["data_format"] == "channels_first":
+            B, C, H, W = x.shape
+            ref_shape = g[name + ".y"].shape
+            y = np.empty(ref_shape, np.float32)
+            rc = c_oracle.qoc_conv2d_cf_forward(_fp(x), _fp(kern), _fp(bias), _fp(y), B, H, W, C // 4, filters, kern.shape[0],
+                                                kern.shape[1], k["strides"][0], k["strides"][1], k["dilation_rate"][0],
+                                                k["dilation_rate"][1], PADS[k["padding"]], relu)
+            assert rc == 0
+        else:
+            continue
+        np.testing.assert_allclose(y, g[name + ".y"], rtol=1e-5, atol=1e-5, err_msg=name)
+        checked += 1
+    assert checked >= 12
+    gd = golden.load("dense_forward")
+    for name, xs, units, kw in DENSE_CASES:
+        if kw.get("activation") not in (None, "relu"):
+            continue
+        x, kern, bias = gd[name + ".x"], gd[name + ".kernel"], gd.get(name + ".bias")
+        y = np.empty((x.shape[0], units), np.float32)
+        assert c_oracle.qoc_dense_forward(_fp(x), _fp(kern), _fp(bias), _fp(y), x.shape[0], x.shape[1] // 4, units // 4,
+                                          int(kw.get("activation") == "relu")) == 0
+        np.testing.assert_allclose(y, gd[name + ".y"], rtol=1e-5, atol=1e-5, err_msg=name)
+
+
+def test_c_oracle_known_answers(c_oracle, golden):
+    """(1+2i+3j+4k) (x) (5+6i+7j+8k) = -60+12i+30j+24k for the convolution, conj(w) (x) x = 70+0i-16j-8k for the dense layer."""
+    kat = golden.load("kat")
+    x = np.array([5, 6, 7, 8], np.float32)
+    w = np.array([1, 2, 3, 4], np.float32)
+    y = np.empty(4, np.float32)
+    assert c_oracle.qoc_conv1d_forward(_fp(x), _fp(w), None, _fp(y), 1, 1, 1, 1, 1, 1, 1, 0, 0) == 1
+    np.testing.assert_array_equal(y, kat["conv_w1234_x5678"].ravel())
+    assert c_oracle.qoc_dense_forward(_fp(x), _fp(w), None, _fp(y), 1, 1, 1, 0) == 0
+    np.testing.assert_array_equal(y, kat["dense_w1234_x5678"].ravel())
