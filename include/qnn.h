@@ -6,8 +6,14 @@
  *
  * Conventions: every function returns 0 (QNN_OK) or a negative qnn_status; nothing throws; caller owns every buffer;
  * pointers are DEVICE pointers unless the name says `_host`; work is enqueued asynchronously on `stream`
- * (a cudaStream_t passed as void*; NULL = legacy default stream) and no call synchronises the device;
+ * (a cudaStream_t passed as void*; NULL = legacy default stream) and no device-pointer call synchronises the device
+ * (the `_host` calls return after their result landed, i.e. they synchronise `stream` only);
  * qnn_last_error() returns a thread-local message for the last failing call on this thread.
+ * Scratch: there is no caller workspace.  Whatever a call needs beyond its arguments (a packed kernel image when the
+ * caller did not supply one, dz = dy * act'(y), a channel-padded copy of x for in_q % 4 != 0, host-path staging) is
+ * stream-ordered memory from the device's default pool (cudaMallocAsync / cudaFreeAsync on `stream`): no implicit
+ * synchronisation, safe under CUDA-graph capture, re-entrant across threads, streams and devices (all library state
+ * is per device; the device is the one current when the call is made).
  * Tensors are fp32.  Channel axes are component-BLOCKED: [r(0:C) | i(C:2C) | j(2C:3C) | k(3C:4C)]
  * (reference: complexnn/conv.py:294-307, complexnn/dense.py:131-134, complexnn/utils.py:17-79).
  */
@@ -21,7 +27,7 @@
 extern "C" {
 #endif
 
-#define QNN_ABI_VERSION 1
+#define QNN_ABI_VERSION 2
 #if defined(__GNUC__)
 #define QNN_API __attribute__((visibility("default")))
 #else
@@ -33,7 +39,7 @@ typedef enum qnn_status {
     QNN_E_INVALID = -1,     /* bad argument (maps to ValueError in the Python mirror)            */
     QNN_E_UNSUPPORTED = -2, /* shape / option outside what the selected algorithm implements    */
     QNN_E_CUDA = -3,        /* a CUDA runtime / driver call failed                              */
-    QNN_E_WORKSPACE = -4,   /* workspace missing or too small                                   */
+    /* -4 was QNN_E_WORKSPACE in ABI 1 (never returned: the library allocates stream-ordered scratch itself) */
     QNN_E_COMM = -5,        /* NCCL unavailable or a collective failed                          */
     QNN_E_STATE = -6        /* call sequence error (e.g. all-reduce before qnn_comm_init)       */
 } qnn_status;
@@ -54,8 +60,14 @@ typedef enum qnn_activation {
     QNN_ACT_EXPONENTIAL = 9
 } qnn_activation;
 
-/* Arithmetic of the contraction.  TF32: operands rounded to nearest tf32, fp32 accumulate in tensor memory
- * (tcgen05.mma kind::tf32).  FP32: CUDA-core FMA.  3XTF32: hi/lo split, three tensor-core products (fp32-faithful). */
+/* Arithmetic of the contraction.
+ * TF32   (fast): operands rounded to nearest tf32, fp32 accumulate in tensor memory (tcgen05.mma kind::tf32);
+ *        max|d| / max|ref| ~ 3e-4, a fraction of a percent of outputs miss allclose(rtol 1e-3, atol 1e-3 rms).
+ * 3XTF32 (parity-safe): every operand split into hi = rn_tf32(v) and lo = rn_tf32(v - hi), each block is
+ *        x_lo.w_hi + x_hi.w_lo + x_hi.w_hi on the tensor cores (three MMAs) -- fp32-faithful like the reference's
+ *        arithmetic (complexnn/conv.py:334, dense.py:149); shapes no tensor-core kernel takes run the FP32 kernel.
+ *        The kernel gradient under 3XTF32 runs on the FP32 kernel.
+ * FP32:  CUDA-core FMA. */
 typedef enum qnn_math { QNN_MATH_TF32 = 0, QNN_MATH_FP32 = 1, QNN_MATH_3XTF32 = 2 } qnn_math;
 
 /* Kernel selection.  AUTO picks the tensor-core kernel when the shape qualifies, else the general kernel. */
@@ -107,21 +119,50 @@ QNN_API int qnn_conv_forward(const qnn_conv_desc* d, const float* x, const float
 QNN_API int qnn_dense_forward(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
                       const float* bias, int32_t activation, int32_t math, int32_t algo, float* y, void* stream);
 
+/* Packed kernel images.  The tensor-core kernels consume the stored kernel as a K-major, tf32-rounded core-matrix image
+ * (3XTF32: hi and lo parts).  The plain entry points build it in scratch on every call (one extra ~2 us launch); a
+ * caller that keeps weights across calls -- the layer mirror does, keyed by a weight version -- packs once per weight
+ * update into its own buffer and passes it to the *_packed entry points (one launch per call).
+ * kind FORWARD feeds qnn_*_forward_packed, kind DGRAD (the transposed, tap-flipped kernel of the data gradient, read
+ * straight from the stored kernel) feeds qnn_*_backward_packed.  qnn_*_packed_bytes returns 0 when the problem has no
+ * packed form (it runs on the general kernel); the image depends on the layer (in_q, filters, kernel, dilation, layout),
+ * math and algo -- not on batch size or (as long as the same kernel family takes the problem) on the spatial extent.
+ * `packed` must be 16-byte aligned.  `kernel` may be NULL in the *_packed calls when a tensor-core kernel runs. */
+typedef enum qnn_pack_kind { QNN_PACK_FORWARD = 0, QNN_PACK_DGRAD = 1 } qnn_pack_kind;
+QNN_API size_t qnn_conv_packed_bytes(const qnn_conv_desc* d, int32_t kind);
+QNN_API int qnn_conv_pack(const qnn_conv_desc* d, int32_t kind, const float* kernel, void* packed, void* stream);
+QNN_API int qnn_conv_forward_packed(const qnn_conv_desc* d, const float* x, const float* kernel, const void* packed,
+                            const float* bias, float* y, void* stream);
+QNN_API size_t qnn_dense_packed_bytes(int64_t rows, int32_t in_q, int32_t q_units, int32_t math, int32_t algo, int32_t kind);
+QNN_API int qnn_dense_pack(int64_t rows, int32_t in_q, int32_t q_units, int32_t math, int32_t algo, int32_t kind,
+                   const float* kernel, void* packed, void* stream);
+QNN_API int qnn_dense_forward_packed(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
+                             const void* packed, const float* bias, int32_t activation, int32_t math, int32_t algo,
+                             float* y, void* stream);
+
 /* Gradients TF autodiff derives from the same graph.  `y` is the forward output (needed for the
  * activation derivative; only LINEAR and RELU are differentiable here).  Any of dx / dkernel / dbias may be NULL to
  * skip it.  dkernel / dbias are OVERWRITTEN (not accumulated) and have the stored-kernel / bias shapes, so they can
  * point into a flat gradient bucket that qnn_allreduce_f32 then reduces.
- * math / algo as in the forward: under TF32 + AUTO the data gradient of a channels_last rank-1 / dense layer runs on
- * the tensor cores (the forward kernel on dz with the transposed, tap-flipped stored kernel); FP32 or GENERAL selects
- * the CUDA-core kernels. */
+ * math / algo as in the forward: under TF32 / 3XTF32 + AUTO the data gradient of a stride-1 layer runs on the tensor
+ * cores (the forward kernel on dz with the transposed, tap-flipped kernel image -- channels_last rank 1 / dense and
+ * channels_first rank 1 / 2); the kernel gradient of a channels_last rank-1 / dense layer does under TF32; FP32 or
+ * GENERAL selects the CUDA-core kernels.  The *_packed variants take the caller's cached DGRAD image (or NULL). */
 QNN_API int qnn_conv_backward(const qnn_conv_desc* d, const float* x, const float* kernel, const float* y, const float* dy,
                       float* dx, float* dkernel, float* dbias, void* stream);
 QNN_API int qnn_dense_backward(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
                        const float* y, const float* dy, int32_t activation, int32_t math, int32_t algo, float* dx,
                        float* dkernel, float* dbias, void* stream);
+QNN_API int qnn_conv_backward_packed(const qnn_conv_desc* d, const float* x, const float* kernel, const void* packed_dgrad,
+                             const float* y, const float* dy, float* dx, float* dkernel, float* dbias, void* stream);
+QNN_API int qnn_dense_backward_packed(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
+                              const void* packed_dgrad, const float* y, const float* dy, int32_t activation,
+                              int32_t math, int32_t algo, float* dx, float* dkernel, float* dbias, void* stream);
 
 /* Host-buffer convenience (the end-to-end call a non-CUDA caller makes): pageable or pinned HOST pointers in, HOST
- * result out; the library stages through its own device scratch on `stream` and returns after the result landed. */
+ * result out; the library stages through stream-ordered device scratch (H2D, kernel and D2H pipelined in chunks over
+ * `stream` and two copy streams of its own) and returns after the result landed.  Kernel and bias stay resident on the
+ * device between calls, keyed by (host pointer, size, content hash), together with the packed image. */
 QNN_API int qnn_conv_forward_host(const qnn_conv_desc* d, const float* x_host, const float* kernel_host,
                           const float* bias_host, float* y_host, void* stream);
 QNN_API int qnn_dense_forward_host(int64_t rows, int32_t in_q, int32_t q_units, const float* x_host, const float* kernel_host,

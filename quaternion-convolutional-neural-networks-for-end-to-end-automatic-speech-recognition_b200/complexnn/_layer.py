@@ -251,6 +251,7 @@ class Variable(object):
         self._host = np.ascontiguousarray(np.asarray(value), dtype=np.float32)
         self._dev = None
         self._dev_is_master = False
+        self.version = 0          # bumped by every assignment / optimiser step: keys caches of derived device images
 
     @property
     def shape(self):
@@ -269,20 +270,27 @@ class Variable(object):
                              % (self._host.shape, value.shape))
         self._host = np.ascontiguousarray(value)
         self._dev_is_master = False
+        self.version += 1
         if self._dev is not None:
             import torch
-            self._dev.copy_(torch.from_numpy(self._host))
+            with torch.no_grad():      # the mirror may be an autograd leaf (`parameter()`): in-place copy outside the graph
+                self._dev.copy_(torch.from_numpy(self._host))
 
     def device(self, device="cuda"):
         """Device mirror (torch tensor).  In-place updates by an optimiser must call `mark_device_updated`."""
         import torch
         if self._dev is None or str(self._dev.device) != str(torch.device(device if device != "cuda" else
                                                                           "cuda:%d" % torch.cuda.current_device())):
-            self._dev = torch.from_numpy(self._host).to(device)
+            # moving to another device: the old mirror may hold the newest values (optimiser steps) -> pull them first
+            grad = self._dev is not None and self._dev.requires_grad
+            self._dev = torch.from_numpy(self.numpy()).to(device)
+            if grad:
+                self._dev.requires_grad_(True)
         return self._dev
 
     def mark_device_updated(self):
         self._dev_is_master = True
+        self.version += 1
 
     def parameter(self, device="cuda"):
         """The device mirror as an autograd leaf (for an optimiser); call `mark_device_updated` after stepping it."""

@@ -13,6 +13,8 @@ MATH = {"tf32": 0, "fp32": 1, "3xtf32": 2}
 ALGO = {"auto": 0, "general": 1, "tensor": 2}
 
 QNN_E_INVALID, QNN_E_UNSUPPORTED = -1, -2
+ABI_VERSION = 2
+PACK_FORWARD, PACK_DGRAD = 0, 1
 
 
 class ConvDesc(ctypes.Structure):
@@ -40,6 +42,18 @@ SIGNATURES = {
     "qnn_conv_forward": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P]),
     "qnn_dense_forward": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, ctypes.c_int32,
                                          ctypes.c_int32, ctypes.c_int32, _P, _P]),
+    "qnn_conv_packed_bytes": (ctypes.c_size_t, [ctypes.POINTER(ConvDesc), ctypes.c_int32]),
+    "qnn_conv_pack": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.c_int32, _P, _P, _P]),
+    "qnn_conv_forward_packed": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P]),
+    "qnn_dense_packed_bytes": (ctypes.c_size_t, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                 ctypes.c_int32, ctypes.c_int32]),
+    "qnn_dense_pack": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                      ctypes.c_int32, _P, _P, _P]),
+    "qnn_dense_forward_packed": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P,
+                                                ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P]),
+    "qnn_conv_backward_packed": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "qnn_dense_backward_packed": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P, _P,
+                                                 ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P]),
     "qnn_conv_backward": (ctypes.c_int, [ctypes.POINTER(ConvDesc), _P, _P, _P, _P, _P, _P, _P, _P]),
     "qnn_dense_backward": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P,
                                           ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P, _P, _P, _P]),
@@ -65,7 +79,7 @@ def lib():
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)
             fn.restype, fn.argtypes = res, args
-        if handle.qnn_abi_version() != 1:
+        if handle.qnn_abi_version() != ABI_VERSION:
             raise RuntimeError("libqnn_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -40,6 +40,38 @@ def _as_host_f32(x):
     return np.ascontiguousarray(x, dtype=np.float32)
 
 
+class PackedKernels(object):
+    """Per-layer cache of packed kernel images (include/qnn.h: qnn_*_pack): device buffers keyed by
+    (kind, math, algo, device, problem signature), valid for one `Variable.version`.  The layer owns one; an image is
+    rebuilt (one ~2 us launch) after every weight update and otherwise reused, so a steady-state forward is ONE launch."""
+
+    MAX_ENTRIES = 16        # variable-length inputs may change the kernel family / image: keep a few, then start over
+
+    def __init__(self):
+        self.version = None
+        self.images = {}
+
+    def get(self, kernel, key, nbytes_fn, pack_fn, device):
+        """Image for `key`, or None when the problem has no packed form (general kernel)."""
+        import torch
+        if self.version != kernel.version:
+            self.images.clear()
+            self.version = kernel.version
+        hit = self.images.get(key)
+        if hit is not None:
+            return hit if hit is not False else None
+        nbytes = int(nbytes_fn())
+        if nbytes == 0:
+            self.images[key] = False
+            return None
+        if len(self.images) >= self.MAX_ENTRIES:
+            self.images.clear()
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=device)
+        pack_fn(buf)
+        self.images[key] = buf
+        return buf
+
+
 def conv_out_shape(in_shape, filters, kernel_size, strides, padding, data_format, dilation_rate):
     rank = len(kernel_size)
     space = in_shape[2:] if data_format == "channels_first" else in_shape[1:-1]
@@ -50,10 +82,10 @@ def conv_out_shape(in_shape, filters, kernel_size, strides, padding, data_format
 
 
 def conv_forward(x, kernel, bias, filters, kernel_size, strides, padding, data_format, dilation_rate, activation,
-                 math=None, algo=None):
+                 math=None, algo=None, packed=None):
     """QuaternionConv.call (reference complexnn/conv.py:288-345) as one fused kernel launch.
     x: torch CUDA tensor (returns a torch CUDA tensor) or NumPy / torch CPU array (returns NumPy / torch CPU).
-    kernel, bias: `Variable`s (bias may be None)."""
+    kernel, bias: `Variable`s (bias may be None).  packed: the layer's `PackedKernels` cache (device path only)."""
     lib = _native.lib()
     rank = len(kernel_size)
     shape = tuple(int(s) for s in x.shape)
@@ -78,9 +110,21 @@ def conv_forward(x, kernel, bias, filters, kernel_size, strides, padding, data_f
             xt = xt.to(torch.float32).contiguous()
         y = torch.empty(out_shape, dtype=torch.float32, device=xt.device)
         with torch.cuda.device(xt.device):
-            _native.check(lib.qnn_conv_forward(ctypes.byref(desc), _dev_ptr(xt), _dev_ptr(kernel.device(xt.device)),
-                                               _dev_ptr(bias.device(xt.device)) if bias is not None else None,
-                                               _dev_ptr(y), _stream()))
+            kd = kernel.device(xt.device)
+            img = None
+            if packed is not None and y.numel():
+                key = ("conv", _native.PACK_FORWARD, desc.math, desc.algo, str(xt.device), tuple(space))
+                img = packed.get(kernel, key, lambda: lib.qnn_conv_packed_bytes(ctypes.byref(desc), _native.PACK_FORWARD),
+                                 lambda buf: _native.check(lib.qnn_conv_pack(ctypes.byref(desc), _native.PACK_FORWARD,
+                                                                             _dev_ptr(kd), _dev_ptr(buf), _stream())),
+                                 xt.device)
+            bd = _dev_ptr(bias.device(xt.device)) if bias is not None else None
+            if img is not None:
+                _native.check(lib.qnn_conv_forward_packed(ctypes.byref(desc), _dev_ptr(xt), _dev_ptr(kd), _dev_ptr(img), bd,
+                                                          _dev_ptr(y), _stream()))
+            else:
+                _native.check(lib.qnn_conv_forward(ctypes.byref(desc), _dev_ptr(xt), _dev_ptr(kd), bd, _dev_ptr(y),
+                                                   _stream()))
         return y
     xh = _as_host_f32(x)
     y = np.empty(out_shape, dtype=np.float32)
@@ -92,7 +136,7 @@ def conv_forward(x, kernel, bias, filters, kernel_size, strides, padding, data_f
     return y
 
 
-def dense_forward(x, kernel, bias, units, activation, math=None, algo=None):
+def dense_forward(x, kernel, bias, units, activation, math=None, algo=None, packed=None):
     """QuaternionDense.call (reference complexnn/dense.py:126-164) as one fused kernel launch."""
     lib = _native.lib()
     shape = tuple(int(s) for s in x.shape)
@@ -109,9 +153,22 @@ def dense_forward(x, kernel, bias, units, activation, math=None, algo=None):
             xt = xt.to(torch.float32).contiguous()
         y = torch.empty((rows, units), dtype=torch.float32, device=xt.device)
         with torch.cuda.device(xt.device):
-            _native.check(lib.qnn_dense_forward(rows, in_q, q_units, _dev_ptr(xt), _dev_ptr(kernel.device(xt.device)),
-                                                _dev_ptr(bias.device(xt.device)) if bias is not None else None,
-                                                act, m, a, _dev_ptr(y), _stream()))
+            kd = kernel.device(xt.device)
+            img = None
+            if packed is not None and rows:
+                key = ("dense", _native.PACK_FORWARD, m, a, str(xt.device))
+                img = packed.get(kernel, key,
+                                 lambda: lib.qnn_dense_packed_bytes(rows, in_q, q_units, m, a, _native.PACK_FORWARD),
+                                 lambda buf: _native.check(lib.qnn_dense_pack(rows, in_q, q_units, m, a, _native.PACK_FORWARD,
+                                                                              _dev_ptr(kd), _dev_ptr(buf), _stream())),
+                                 xt.device)
+            bd = _dev_ptr(bias.device(xt.device)) if bias is not None else None
+            if img is not None:
+                _native.check(lib.qnn_dense_forward_packed(rows, in_q, q_units, _dev_ptr(xt), _dev_ptr(kd), _dev_ptr(img), bd,
+                                                           act, m, a, _dev_ptr(y), _stream()))
+            else:
+                _native.check(lib.qnn_dense_forward(rows, in_q, q_units, _dev_ptr(xt), _dev_ptr(kd), bd, act, m, a,
+                                                    _dev_ptr(y), _stream()))
         return y
     xh = _as_host_f32(x)
     y = np.empty((rows, units), dtype=np.float32)
@@ -134,7 +191,7 @@ def _grad_out(like_shape, out, device):
 
 
 def conv_backward(x, y, dy, kernel, has_bias, filters, kernel_size, strides, padding, data_format, dilation_rate,
-                  activation, need_dx=True, dkernel_out=None, dbias_out=None, math=None, algo=None):
+                  activation, need_dx=True, dkernel_out=None, dbias_out=None, math=None, algo=None, packed=None):
     """Gradients of the quaternion convolution (device tensors only).  Returns (dx | None, dkernel, dbias | None);
     dkernel_out / dbias_out may be views into a flat gradient bucket."""
     import torch
@@ -151,14 +208,20 @@ def conv_backward(x, y, dy, kernel, has_bias, filters, kernel_size, strides, pad
     dk = _grad_out(tuple(kernel.shape), dkernel_out, x.device)
     db = _grad_out((4 * filters,), dbias_out, x.device) if has_bias else None
     with torch.cuda.device(x.device):
-        _native.check(lib.qnn_conv_backward(ctypes.byref(desc), _dev_ptr(x), _dev_ptr(kernel.device(x.device)),
-                                            _dev_ptr(y), _dev_ptr(dy), _dev_ptr(dx), _dev_ptr(dk), _dev_ptr(db),
-                                            _stream()))
+        kd = kernel.device(x.device)
+        img = None
+        if packed is not None and need_dx and dy.numel():
+            key = ("conv", _native.PACK_DGRAD, desc.math, desc.algo, str(x.device), tuple(space))
+            img = packed.get(kernel, key, lambda: lib.qnn_conv_packed_bytes(ctypes.byref(desc), _native.PACK_DGRAD),
+                             lambda buf: _native.check(lib.qnn_conv_pack(ctypes.byref(desc), _native.PACK_DGRAD, _dev_ptr(kd),
+                                                                         _dev_ptr(buf), _stream())), x.device)
+        _native.check(lib.qnn_conv_backward_packed(ctypes.byref(desc), _dev_ptr(x), _dev_ptr(kd), _dev_ptr(img), _dev_ptr(y),
+                                                   _dev_ptr(dy), _dev_ptr(dx), _dev_ptr(dk), _dev_ptr(db), _stream()))
     return dx, dk, db
 
 
 def dense_backward(x, y, dy, kernel, has_bias, units, activation, need_dx=True, dkernel_out=None, dbias_out=None,
-                   math=None, algo=None):
+                   math=None, algo=None, packed=None):
     import torch
     lib = _native.lib()
     rows, in_q, q_units = int(x.shape[0]), int(x.shape[1]) // 4, units // 4
@@ -166,9 +229,16 @@ def dense_backward(x, y, dy, kernel, has_bias, units, activation, need_dx=True, 
     dx = torch.empty_like(x) if need_dx else None
     dk = _grad_out(tuple(kernel.shape), dkernel_out, x.device)
     db = _grad_out((units,), dbias_out, x.device) if has_bias else None
+    m, a = _native.MATH[math or default_math()], _native.ALGO[algo or default_algo()]
     with torch.cuda.device(x.device):
-        _native.check(lib.qnn_dense_backward(rows, in_q, q_units, _dev_ptr(x), _dev_ptr(kernel.device(x.device)),
-                                             _dev_ptr(y), _dev_ptr(dy), _native.ACT[activation],
-                                             _native.MATH[math or default_math()], _native.ALGO[algo or default_algo()],
-                                             _dev_ptr(dx), _dev_ptr(dk), _dev_ptr(db), _stream()))
+        kd = kernel.device(x.device)
+        img = None
+        if packed is not None and need_dx and rows:
+            key = ("dense", _native.PACK_DGRAD, m, a, str(x.device))
+            img = packed.get(kernel, key, lambda: lib.qnn_dense_packed_bytes(rows, in_q, q_units, m, a, _native.PACK_DGRAD),
+                             lambda buf: _native.check(lib.qnn_dense_pack(rows, in_q, q_units, m, a, _native.PACK_DGRAD,
+                                                                          _dev_ptr(kd), _dev_ptr(buf), _stream())), x.device)
+        _native.check(lib.qnn_dense_backward_packed(rows, in_q, q_units, _dev_ptr(x), _dev_ptr(kd), _dev_ptr(img), _dev_ptr(y),
+                                                    _dev_ptr(dy), _native.ACT[activation], m, a, _dev_ptr(dx), _dev_ptr(dk),
+                                                    _dev_ptr(db), _stream()))
     return dx, dk, db

@@ -93,8 +93,11 @@ class QuaternionConv(Layer):
         gammas = ("rr", "ri", "rj", "rk", "ii", "ij", "ik", "jj", "jk", "kk")
         if self.normalize_weight:
             gamma_shape = (input_dim * self.filters,)
+            # the reference's own table (conv.py:183-256): rr, ii, jj and -- as shipped -- jk take the *diag*
+            # initialiser / regulariser / constraint, kk takes the *off* ones; reproduced so that weight lists and
+            # checkpoints stay interchangeable (the gammas are never read in call)
             for g in gammas:
-                diag = g[0] == g[1]
+                diag = g in ("rr", "ii", "jj", "jk")
                 setattr(self, "gamma_" + g, self.add_weight(
                     shape=gamma_shape, name="gamma_" + g,
                     initializer=self.gamma_diag_initializer if diag else self.gamma_off_initializer,
@@ -115,8 +118,16 @@ class QuaternionConv(Layer):
         fused = self.activation.fused
         out = _ops.conv_forward(inputs, self.kernel, self.bias, self.filters, self.kernel_size, self.strides,
                                 self.padding, self.data_format, self.dilation_rate,
-                                self.activation.name if fused else "linear")
+                                self.activation.name if fused else "linear", packed=self._packed_kernels())
         return out if fused else self.activation(out)
+
+    def _packed_kernels(self):
+        """Packed kernel images of this layer (K-major tf32 core matrices the tensor-core kernels consume), rebuilt only
+        when the kernel `Variable` changes."""
+        cache = getattr(self, "_packed", None)
+        if cache is None:
+            cache = self._packed = _ops.PackedKernels()
+        return cache
 
     def backward(self, inputs, outputs, grad_outputs, need_input_grad=True, grad_kernel_out=None, grad_bias_out=None):
         """Gradients TF autodiff would derive from the reference graph; device tensors only.
@@ -125,7 +136,8 @@ class QuaternionConv(Layer):
             raise NotImplementedError("backward supports linear and relu activations")
         return _ops.conv_backward(inputs, outputs, grad_outputs, self.kernel, self.bias is not None, self.filters,
                                   self.kernel_size, self.strides, self.padding, self.data_format, self.dilation_rate,
-                                  self.activation.name, need_input_grad, grad_kernel_out, grad_bias_out)
+                                  self.activation.name, need_input_grad, grad_kernel_out, grad_bias_out,
+                                  packed=self._packed_kernels())
 
     def compute_output_shape(self, input_shape):
         return _ops.conv_out_shape(tuple(input_shape), self.filters, self.kernel_size, self.strides, self.padding,

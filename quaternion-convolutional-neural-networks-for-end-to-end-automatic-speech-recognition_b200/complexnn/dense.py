@@ -55,15 +55,23 @@ class QuaternionDense(Layer):
     def call(self, inputs):
         fused = self.activation.fused
         out = _ops.dense_forward(inputs, self.kernel, self.bias, self.units,
-                                 self.activation.name if fused else "linear")
+                                 self.activation.name if fused else "linear", packed=self._packed_kernels())
         return out if fused else self.activation(out)
+
+    def _packed_kernels(self):
+        """Packed kernel images of this layer (see complexnn/_ops.py: PackedKernels), rebuilt only when the kernel changes."""
+        cache = getattr(self, "_packed", None)
+        if cache is None:
+            cache = self._packed = _ops.PackedKernels()
+        return cache
 
     def backward(self, inputs, outputs, grad_outputs, need_input_grad=True, grad_kernel_out=None, grad_bias_out=None):
         """Returns (grad_inputs | None, grad_kernel, grad_bias | None); device tensors only."""
         if not self.activation.fused or self.activation.name not in ("linear", "relu"):
             raise NotImplementedError("backward supports linear and relu activations")
         return _ops.dense_backward(inputs, outputs, grad_outputs, self.kernel, self.bias is not None, self.units,
-                                   self.activation.name, need_input_grad, grad_kernel_out, grad_bias_out)
+                                   self.activation.name, need_input_grad, grad_kernel_out, grad_bias_out,
+                                   packed=self._packed_kernels())
 
     def compute_output_shape(self, input_shape):
         assert input_shape and len(input_shape) == 2

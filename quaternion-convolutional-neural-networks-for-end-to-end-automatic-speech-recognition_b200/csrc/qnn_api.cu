@@ -5,6 +5,8 @@
 #include <cstring>
 #include <mutex>
 #include <string>
+#include <utility>
+#include <vector>
 #include "qnn_common.h"
 
 namespace qnn {
@@ -19,17 +21,53 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+int current_device() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) dev = 0;
+    return dev;
+}
+
+int num_sms() {
+    static std::atomic<int> n[kMaxDevices];
+    const int dev = current_device();
+    int v = n[dev].load(std::memory_order_relaxed);
+    if (!v) {
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+        n[dev].store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// cudaFuncSetAttribute is per device: remember (device, kernel) pairs, not kernels
+int ensure_dynamic_smem(const void* kernel, int bytes) {
+    static std::mutex mu;
+    static std::vector<std::pair<int, const void*>> done;
+    const int dev = current_device();
+    std::lock_guard<std::mutex> lock(mu);
+    for (const auto& d : done)
+        if (d.first == dev && d.second == kernel) return QNN_OK;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) {
+        set_error("cudaFuncSetAttribute(MaxDynamicSharedMemorySize = %d) failed: %s", bytes, cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    done.emplace_back(dev, kernel);
+    return QNN_OK;
+}
+
 int stream_scratch_alloc(void** ptr, size_t bytes, cudaStream_t st) {
-    static std::once_flag once;
-    std::call_once(once, [] {
-        int dev = 0;
+    // every device's default pool is told once to keep freed blocks: steady-state calls never reach the OS allocator
+    static std::atomic<bool> pool_ready[kMaxDevices];
+    const int dev = current_device();
+    if (!pool_ready[dev].load(std::memory_order_acquire)) {
         cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            uint64_t keep = 1ull << 30;  // freed blocks stay in the pool: steady-state calls never reach the OS allocator
+        if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+            uint64_t keep = 1ull << 30;
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
         }
-    });
-    cudaError_t e = cudaMallocAsync(ptr, bytes, st);
+        pool_ready[dev].store(true, std::memory_order_release);
+    }
+    cudaError_t e = cudaMallocAsync(ptr, bytes ? bytes : 16, st);
     if (e != cudaSuccess) {
         *ptr = nullptr;
         set_error("stream-ordered scratch allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
@@ -143,146 +181,164 @@ int build_dense_geom(int64_t rows, int in_q, int q_units, int act, Geom* g) {
 
 bool empty_out(const Geom& g) { return g.batch == 0 || g.out_sp[0] == 0 || g.out_sp[1] == 0 || g.out_sp[2] == 0; }
 
-int run_forward(const Geom& g, int rank, int math, int algo, const float* x, const float* w, const float* bias, float* y,
-                cudaStream_t st) {
-    if (empty_out(g)) return QNN_OK;
-    if (!x || !w || !y) {
-        set_error("x, kernel and y must not be NULL");
-        return QNN_E_INVALID;
-    }
-    if (math != QNN_MATH_TF32 && math != QNN_MATH_FP32 && math != QNN_MATH_3XTF32) {
+bool valid_math(int m) { return m == QNN_MATH_TF32 || m == QNN_MATH_FP32 || m == QNN_MATH_3XTF32; }
+bool valid_algo(int a) { return a == QNN_ALGO_AUTO || a == QNN_ALGO_GENERAL || a == QNN_ALGO_TENSOR; }
+bool al16(const void* a) { return (reinterpret_cast<uintptr_t>(a) & 15) == 0; }
+
+// Which kernel a forward problem gets: 0 = general (CUDA cores), 1 = channels_last rows (qnn_hamilton_tc.cu),
+// 2 = channels_first / rank 2 (qnn_hamilton_tc2d.cu).  Pointer alignment aside.
+enum { kKernGeneral = 0, kKernTc = 1, kKernTc2d = 2 };
+int forward_kernel(const Geom& g, int rank, int math, int algo) {
+    if (algo == QNN_ALGO_GENERAL || math == QNN_MATH_FP32) return kKernGeneral;
+    const int x3 = math == QNN_MATH_3XTF32;
+    if (tc_plan(g, rank, x3).ok) return kKernTc;
+    if (tc2d_plan(g, rank, x3).ok) return kKernTc2d;
+    return kKernGeneral;
+}
+
+// `packed`: the caller's cached kernel image (qnn_conv_pack / qnn_dense_pack) or NULL (pack per call into scratch).
+int run_forward(const Geom& g, int rank, int math, int algo, const float* x, const float* w, const void* packed,
+                const float* bias, float* y, cudaStream_t st) {
+    if (!valid_math(math)) {
         set_error("unknown math mode %d", math);
         return QNN_E_INVALID;
     }
-    if (algo == QNN_ALGO_GENERAL || math == QNN_MATH_FP32) return general_forward(g, x, w, bias, y, st);
-    if (math == QNN_MATH_3XTF32) {
-        if (algo == QNN_ALGO_TENSOR) {
-            set_error("3xTF32 is not implemented on the tensor-core kernel yet");
-            return QNN_E_UNSUPPORTED;
-        }
-        return general_forward(g, x, w, bias, y, st);
-    }
-    const bool aligned =
-        ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) == 0;
-    if (algo == QNN_ALGO_TENSOR)
-        return (g.channels_first || (!tc_plan(g, rank).ok && tc2d_plan(g, rank).ok)) ? tc2d_forward(g, rank, x, w, bias, y, st)
-                                                                                      : tc_forward(g, rank, x, w, bias, y, st);
-    if (algo != QNN_ALGO_AUTO) {
+    if (!valid_algo(algo)) {
         set_error("unknown algo %d", algo);
         return QNN_E_INVALID;
     }
-    if (aligned && tc_plan(g, rank).ok) return tc_forward(g, rank, x, w, bias, y, st);
-    if (aligned && tc2d_plan(g, rank).ok) return tc2d_forward(g, rank, x, w, bias, y, st);
-    return general_forward(g, x, w, bias, y, st);
+    if (empty_out(g)) return QNN_OK;
+    if (!x || (!w && !packed) || !y) {
+        set_error("x, kernel and y must not be NULL");
+        return QNN_E_INVALID;
+    }
+    const int x3 = math == QNN_MATH_3XTF32;
+    int kern = forward_kernel(g, rank, math, algo);
+    const bool aligned = al16(x) && al16(y) && (packed ? al16(packed) : al16(w));
+    if (algo == QNN_ALGO_TENSOR) {
+        if (math == QNN_MATH_FP32) {
+            set_error("the tensor-core kernels compute in TF32 or 3xTF32, not FP32");
+            return QNN_E_UNSUPPORTED;
+        }
+        if (kern == kKernGeneral) kern = g.channels_first ? kKernTc2d : kKernTc;  // let the kernel's own plan report why not
+    } else if (!aligned) {
+        kern = kKernGeneral;
+    }
+    if (kern == kKernGeneral) {
+        if (!w) {
+            set_error("this problem runs on the general kernel, which needs the stored kernel (not only its packed image)");
+            return QNN_E_INVALID;
+        }
+        return general_forward(g, x, w, bias, y, st);
+    }
+    if (kern == kKernTc)
+        return packed ? tc_forward_packed(g, rank, x3, x, packed, bias, y, st) : tc_forward(g, rank, x3, 0, x, w, bias, y, st);
+    return packed ? tc2d_forward_packed(g, rank, x3, x, packed, bias, y, st) : tc2d_forward(g, rank, x3, 0, x, w, bias, y, st);
 }
 
-// the transposed convolution of the data gradient: dz [batch, Lo, 4F] -> dx [batch, L, 4 in_q]
+// the transposed convolution of the data gradient: dz [batch, out..., 4F] -> dx [batch, in..., 4 in_q]
 Geom transposed_geom(const Geom& g) {
     Geom gt = g;
     gt.in_q = g.F;
     gt.F = g.in_q;
-    gt.in_sp[2] = g.out_sp[2];
-    gt.out_sp[2] = g.in_sp[2];
-    gt.pad_lo[2] = (g.k[2] - 1) * g.d[2] - g.pad_lo[2];
+    for (int a = 0; a < 3; ++a) {
+        gt.in_sp[a] = g.out_sp[a];
+        gt.out_sp[a] = g.in_sp[a];
+        gt.pad_lo[a] = (g.k[a] - 1) * g.d[a] - g.pad_lo[a];
+    }
     gt.act = QNN_ACT_LINEAR;
     gt.conj_w = g.conj_w ? 0 : 1;
     return gt;
 }
 
-// which gradients of this problem the tensor-core kernels take (pointer alignment aside)
-void backward_selection(const Geom& g, int rank, int math, int algo, int* dx_tc, int* dw_tc) {
-    const bool base = math == QNN_MATH_TF32 && algo != QNN_ALGO_GENERAL && !g.channels_first && rank == 1 &&
-                      !empty_out(g) && g.in_sp[2] > 0 && (g.act == QNN_ACT_LINEAR || g.act == QNN_ACT_RELU);
-    *dx_tc = base && tc_plan(transposed_geom(g), 1).ok;
-    *dw_tc = base && wgrad_plan(g, 1).ok;
+// which gradients of this problem the tensor-core kernels take (pointer alignment aside); *dx_kern = kKern* of the
+// transposed problem
+void backward_selection(const Geom& g, int rank, int math, int algo, int* dx_kern, int* dw_tc) {
+    *dx_kern = kKernGeneral;
+    *dw_tc = 0;
+    if (math == QNN_MATH_FP32 || algo == QNN_ALGO_GENERAL || empty_out(g)) return;
+    if (g.act != QNN_ACT_LINEAR && g.act != QNN_ACT_RELU) return;
+    for (int a = 0; a < 3; ++a)
+        if (g.s[a] != 1 || g.in_sp[a] < 1) return;   // a strided forward is a dilated-input transposed problem: general kernels
+    const int x3 = math == QNN_MATH_3XTF32;
+    const Geom gt = transposed_geom(g);
+    // the transposed problem must reproduce the input extent exactly (true for stride 1)
+    if (tc_plan(gt, rank, x3).ok)
+        *dx_kern = kKernTc;
+    else if (tc2d_plan(gt, rank, x3).ok)
+        *dx_kern = kKernTc2d;
+    *dw_tc = wgrad_plan(g, rank, x3).ok;
 }
 
-// Backward.  Tensor-core path (channels_last rank 1 / dense, stride 1): one pass makes dz = dy * act'(y) and the bias
-// gradient; the data gradient is the SAME fused Hamilton kernel run on dz with the transposed, tap-flipped stored kernel
-// and the transposed sign table; the kernel gradient contracts x with dz over positions on the tensor
-// cores, the 16 blocks folding into the 4 stored sub-filters inside tensor memory (qnn_wgrad_tc.cu).  Whatever a
-// tensor-core kernel does not take falls to the CUDA-core kernels, piece by piece.
-int run_backward(const Geom& g, int rank, int math, int algo, const float* x, const float* w, const float* y,
-                 const float* dy, float* dx, float* dw, float* db, cudaStream_t st) {
-    if (math != QNN_MATH_TF32 && math != QNN_MATH_FP32 && math != QNN_MATH_3XTF32) {
+// Backward.  Tensor-core path (stride 1): one pass makes dz = dy * act'(y) and the bias gradient; the data gradient is
+// the SAME fused Hamilton kernel run on dz with the transposed, tap-flipped kernel image (packed straight from the stored
+// kernel) and the transposed sign table; the kernel gradient contracts x with dz over positions on the
+// tensor cores, the 16 blocks folding into the 4 stored sub-filters inside tensor memory (qnn_wgrad_tc.cu).  Whatever
+// a tensor-core kernel does not take falls to the CUDA-core kernels, piece by piece.
+int run_backward(const Geom& g, int rank, int math, int algo, const float* x, const float* w, const void* packed_dgrad,
+                 const float* y, const float* dy, float* dx, float* dw, float* db, cudaStream_t st) {
+    if (!valid_math(math)) {
         set_error("unknown math mode %d", math);
         return QNN_E_INVALID;
     }
-    if (algo != QNN_ALGO_AUTO && algo != QNN_ALGO_GENERAL && algo != QNN_ALGO_TENSOR) {
+    if (!valid_algo(algo)) {
         set_error("unknown algo %d", algo);
         return QNN_E_INVALID;
     }
     const Geom gt = transposed_geom(g);
-    auto al16 = [](const void* a) { return (reinterpret_cast<uintptr_t>(a) & 15) == 0; };
+    const int x3 = math == QNN_MATH_3XTF32;
     int sel_dx = 0, sel_dw = 0;
     backward_selection(g, rank, math, algo, &sel_dx, &sel_dw);
     const bool al_base = al16(dy) && al16(y) && al16(x);
-    const bool tc_dx = sel_dx && al_base && dx && al16(dx);
+    const int tc_dx = (sel_dx && al_base && dx && al16(dx) && (packed_dgrad ? al16(packed_dgrad) : al16(w))) ? sel_dx : 0;
     const bool tc_dw = sel_dw && al_base && dw && al16(dw);
     if (algo == QNN_ALGO_TENSOR && ((dx && !tc_dx) || (dw && !tc_dw))) {
-        set_error("tensor-core backward does not take this problem (channels_last rank 1 / dense, stride 1): dx: %s; "
-                  "dkernel: %s", dx ? (tc_dx ? "ok" : tc_plan(gt, 1).why) : "-", dw ? (tc_dw ? "ok" : wgrad_plan(g, 1).why) : "-");
+        set_error("tensor-core backward does not take this problem: dx: %s; dkernel: %s",
+                  dx ? (tc_dx ? "ok" : (g.channels_first ? tc2d_plan(gt, rank, x3).why : tc_plan(gt, rank, x3).why)) : "-",
+                  dw ? (tc_dw ? "ok" : wgrad_plan(g, rank, x3).why) : "-");
         return QNN_E_UNSUPPORTED;
     }
     if (!tc_dx && !tc_dw) return general_backward(g, x, w, y, dy, dx, dw, db, st);
-    const long long rows = (long long)g.batch * g.out_sp[2];
-    const int C = 4 * g.F, taps = g.k[2];
+    const long long P = (long long)g.out_sp[0] * g.out_sp[1] * g.out_sp[2];
+    const long long rows = (long long)g.batch * P;
+    const int C = 4 * g.F;
     const bool relu = g.act == QNN_ACT_RELU;
     float* dz = nullptr;
-    float* wt = nullptr;
     int rc = QNN_OK;
     if (relu && (rc = stream_scratch_alloc(reinterpret_cast<void**>(&dz), (size_t)rows * C * sizeof(float), st))) return rc;
     const float* dzc = relu ? dz : dy;
     Geom gl = g;
     gl.act = QNN_ACT_LINEAR;  // dz already carries the activation derivative
-    if (relu || db) rc = dz_bgrad(y, dy, dz, db, rows, C, relu ? 1 : 0, st);
+    if (relu || db) rc = g.channels_first ? dz_bgrad_cf(y, dy, dz, db, g.batch, C, P, relu ? 1 : 0, st)
+                                         : dz_bgrad(y, dy, dz, db, rows, C, relu ? 1 : 0, st);
     if (!rc && dx) {
-        if (tc_dx) {
-            rc = stream_scratch_alloc(reinterpret_cast<void**>(&wt), (size_t)taps * g.in_q * C * sizeof(float), st);
-            if (!rc) rc = transpose_w(w, wt, taps, g.in_q, g.F, st);
-            if (!rc) rc = tc_forward(gt, 1, dzc, wt, nullptr, dx, st);
-        } else {
+        if (tc_dx == kKernTc)
+            rc = packed_dgrad ? tc_forward_packed(gt, rank, x3, dzc, packed_dgrad, nullptr, dx, st)
+                              : tc_forward(gt, rank, x3, 1, dzc, w, nullptr, dx, st);
+        else if (tc_dx == kKernTc2d)
+            rc = packed_dgrad ? tc2d_forward_packed(gt, rank, x3, dzc, packed_dgrad, nullptr, dx, st)
+                              : tc2d_forward(gt, rank, x3, 1, dzc, w, nullptr, dx, st);
+        else
             rc = general_backward(gl, x, w, dzc, dzc, dx, nullptr, nullptr, st);
-        }
     }
-    if (!rc && dw) rc = tc_dw ? wgrad_tc(g, 1, x, dzc, dw, st) : general_backward(gl, x, w, dzc, dzc, nullptr, dw, nullptr, st);
+    if (!rc && dw) rc = tc_dw ? wgrad_tc(g, rank, x3, x, dzc, dw, st) : general_backward(gl, x, w, dzc, dzc, nullptr, dw, nullptr, st);
     if (dz) cudaFreeAsync(dz, st);
-    if (wt) cudaFreeAsync(wt, st);
     return rc;
 }
 
-// ---------------------------------------------------------------- device scratch for the *_host entry points
-struct Scratch {
-    std::mutex mu;
-    void* ptr = nullptr;
-    size_t bytes = 0;
-    int reserve(size_t need) {
-        if (need <= bytes) return QNN_OK;
-        if (ptr) cudaFree(ptr);
-        ptr = nullptr;
-        bytes = 0;
-        cudaError_t e = cudaMalloc(&ptr, need);
-        if (e != cudaSuccess) {
-            set_error("device scratch allocation of %zu bytes failed: %s", need, cudaGetErrorString(e));
-            return QNN_E_CUDA;
-        }
-        bytes = need;
-        return QNN_OK;
-    }
-};
-Scratch g_scratch;
-
+// ---------------------------------------------------------------- the *_host entry points
 size_t align256(size_t v) { return (v + 255) & ~size_t(255); }
 
 // Copy engines run next to the SMs and PCIe is full duplex: the units (samples for a convolution, rows for a dense
 // layer) are cut into chunks and pipelined over three streams -- H2D of chunk i+1, kernel of chunk i and D2H of chunk
-// i-1 overlap -- so the call costs about max(H2D, D2H) instead of their sum.
+// i-1 overlap -- so the call costs about max(H2D, D2H) instead of their sum.  Everything a call needs is per device
+// and per call: a HostPipe (two copy streams + events) is borrowed from the device's free list, staging memory is
+// stream-ordered scratch (no cudaMalloc / cudaFree, hence no implicit device synchronisation), so concurrent callers
+// on different streams or devices do not serialise on each other.
 struct HostPipe {
     cudaStream_t in = nullptr, out = nullptr;
-    cudaEvent_t ev_in[16] = {}, ev_k[16] = {}, ev_start = nullptr;
-    bool ok = false;
+    cudaEvent_t ev_in[16] = {}, ev_k[16] = {}, ev_start = nullptr, ev_out = nullptr;
     bool init() {
-        if (ok) return true;
         if (cudaStreamCreateWithFlags(&in, cudaStreamNonBlocking) != cudaSuccess) return false;
         if (cudaStreamCreateWithFlags(&out, cudaStreamNonBlocking) != cudaSuccess) return false;
         for (int i = 0; i < 16; ++i) {
@@ -290,32 +346,194 @@ struct HostPipe {
             if (cudaEventCreateWithFlags(&ev_k[i], cudaEventDisableTiming) != cudaSuccess) return false;
         }
         if (cudaEventCreateWithFlags(&ev_start, cudaEventDisableTiming) != cudaSuccess) return false;
-        ok = true;
+        if (cudaEventCreateWithFlags(&ev_out, cudaEventDisableTiming) != cudaSuccess) return false;
         return true;
     }
 };
-HostPipe g_pipe;
+struct PipePool {
+    std::mutex mu;
+    std::vector<HostPipe*> idle;
+};
+PipePool g_pipes[kMaxDevices];
+
+HostPipe* borrow_pipe(int dev) {
+    {
+        std::lock_guard<std::mutex> lock(g_pipes[dev].mu);
+        if (!g_pipes[dev].idle.empty()) {
+            HostPipe* p = g_pipes[dev].idle.back();
+            g_pipes[dev].idle.pop_back();
+            return p;
+        }
+    }
+    HostPipe* p = new HostPipe();
+    if (!p->init()) {  // (a half-built pipe is leaked: creation only fails when the context is already unusable)
+        return nullptr;
+    }
+    return p;
+}
+void return_pipe(int dev, HostPipe* p) {
+    std::lock_guard<std::mutex> lock(g_pipes[dev].mu);
+    g_pipes[dev].idle.push_back(p);
+}
+
+// Weights uploaded by the *_host entry points stay resident on the device, keyed by (host pointer, size, content hash):
+// a caller that passes the same kernel / bias again (every inference step) pays a ~10 us hash instead of an upload
+// and -- on the tensor-core path -- instead of a re-pack, since the packed image is kept next to it.
+struct ResidentWeights {
+    const void* host = nullptr;
+    size_t bytes = 0;
+    uint64_t hash = 0, tick = 0;
+    float* dev_raw = nullptr;
+    void* dev_packed = nullptr;  // image for (pack_sig): 0 = none
+    uint64_t pack_sig = 0;
+    cudaEvent_t last_use = nullptr;
+};
+struct WeightCache {
+    std::mutex mu;
+    std::vector<ResidentWeights> entries;
+    uint64_t tick = 0;
+};
+WeightCache g_weights[kMaxDevices];
+constexpr size_t kMaxResident = 32;
+
+uint64_t hash_bytes(const void* p, size_t n) {  // FNV-1a over 8-byte words: ~1 GB/s per ... plenty for <= MB-sized kernels
+    const uint64_t* w = static_cast<const uint64_t*>(p);
+    uint64_t h = 1469598103934665603ull;
+    const size_t n8 = n / 8;
+    for (size_t i = 0; i < n8; ++i) h = (h ^ w[i]) * 1099511628211ull;
+    const unsigned char* t = static_cast<const unsigned char*>(p) + n8 * 8;
+    for (size_t i = 0; i < n % 8; ++i) h = (h ^ t[i]) * 1099511628211ull;
+    return h;
+}
+
+// Returns the device copy of `host` (uploading it on `st` when new or changed).  *entry_idx identifies the entry for
+// attach_packed / mark_used.  Entries are recycled least-recently-used; a recycled buffer is freed stream-ordered after
+// the last kernel that used it (its last_use event).
+int resident_weights(int dev, const float* host, size_t n_floats, cudaStream_t st, float** out, size_t* entry_idx) {
+    WeightCache& wc = g_weights[dev];
+    const size_t bytes = n_floats * sizeof(float);
+    const uint64_t h = hash_bytes(host, bytes);
+    std::lock_guard<std::mutex> lock(wc.mu);
+    for (size_t i = 0; i < wc.entries.size(); ++i) {
+        ResidentWeights& e = wc.entries[i];
+        if (e.host == host && e.bytes == bytes && e.hash == h) {
+            e.tick = ++wc.tick;
+            cudaStreamWaitEvent(st, e.last_use, 0);  // another stream may still be uploading / packing this entry
+            *out = e.dev_raw;
+            *entry_idx = i;
+            return QNN_OK;
+        }
+    }
+    size_t slot = wc.entries.size();
+    if (slot >= kMaxResident) {  // recycle the least recently used entry
+        slot = 0;
+        for (size_t i = 1; i < wc.entries.size(); ++i)
+            if (wc.entries[i].tick < wc.entries[slot].tick) slot = i;
+        ResidentWeights& old = wc.entries[slot];
+        if (old.last_use) cudaStreamWaitEvent(st, old.last_use, 0);
+        if (old.dev_raw) cudaFreeAsync(old.dev_raw, st);
+        if (old.dev_packed) cudaFreeAsync(old.dev_packed, st);
+        cudaEvent_t ev = old.last_use;
+        old = ResidentWeights();
+        old.last_use = ev;
+    } else {
+        wc.entries.emplace_back();
+    }
+    ResidentWeights& e = wc.entries[slot];
+    if (!e.last_use && cudaEventCreateWithFlags(&e.last_use, cudaEventDisableTiming) != cudaSuccess) {
+        set_error("event creation failed");
+        return QNN_E_CUDA;
+    }
+    int rc = stream_scratch_alloc(reinterpret_cast<void**>(&e.dev_raw), bytes, st);
+    if (rc) return rc;
+    cudaError_t ce = cudaMemcpyAsync(e.dev_raw, host, bytes, cudaMemcpyHostToDevice, st);
+    if (ce != cudaSuccess) {
+        set_error("weight upload failed: %s", cudaGetErrorString(ce));
+        return QNN_E_CUDA;
+    }
+    cudaEventRecord(e.last_use, st);
+    e.host = host;
+    e.bytes = bytes;
+    e.hash = h;
+    e.tick = ++wc.tick;
+    *out = e.dev_raw;
+    *entry_idx = slot;
+    return QNN_OK;
+}
+
+// the packed image kept next to a resident kernel: (re)built on `st` when the signature (kernel family, tile, math) differs
+int resident_packed(int dev, size_t entry_idx, uint64_t sig, size_t bytes, cudaStream_t st, void** out, bool* fresh) {
+    WeightCache& wc = g_weights[dev];
+    std::lock_guard<std::mutex> lock(wc.mu);
+    ResidentWeights& e = wc.entries[entry_idx];
+    *fresh = false;
+    if (e.dev_packed && e.pack_sig == sig) {
+        *out = e.dev_packed;
+        return QNN_OK;
+    }
+    if (e.dev_packed) {
+        if (e.last_use) cudaStreamWaitEvent(st, e.last_use, 0);
+        cudaFreeAsync(e.dev_packed, st);
+        e.dev_packed = nullptr;
+    }
+    int rc = stream_scratch_alloc(&e.dev_packed, bytes, st);
+    if (rc) return rc;
+    e.pack_sig = sig;
+    *out = e.dev_packed;
+    *fresh = true;
+    return QNN_OK;
+}
+
+void mark_used(int dev, size_t entry_idx, cudaStream_t st) {
+    WeightCache& wc = g_weights[dev];
+    std::lock_guard<std::mutex> lock(wc.mu);
+    if (entry_idx < wc.entries.size() && wc.entries[entry_idx].last_use) cudaEventRecord(wc.entries[entry_idx].last_use, st);
+}
 
 int forward_host(const Geom& g, int rank, int math, int algo, size_t nx, size_t nw, size_t nb, size_t ny,
                  const float* xh, const float* wh, const float* bh, float* yh, cudaStream_t st) {
+    if (!valid_math(math) || !valid_algo(algo)) {
+        set_error("unknown math mode %d / algo %d", math, algo);
+        return QNN_E_INVALID;
+    }
     if (ny == 0) return QNN_OK;
     if (!xh || !wh || !yh) {
         set_error("host x, kernel and y must not be NULL");
         return QNN_E_INVALID;
     }
-    std::lock_guard<std::mutex> lock(g_scratch.mu);
-    const size_t ox = 0, ow = ox + align256(nx * 4), ob = ow + align256(nw * 4), oy = ob + align256(nb * 4);
-    int rc = g_scratch.reserve(oy + align256(ny * 4) + 256);
+    const int dev = current_device();
+    // resident weights (+ packed image when a tensor-core kernel takes the problem)
+    float *wd = nullptr, *bd = nullptr;
+    size_t w_idx = 0, b_idx = 0;
+    int rc = resident_weights(dev, wh, nw, st, &wd, &w_idx);
+    if (!rc && bh) rc = resident_weights(dev, bh, nb, st, &bd, &b_idx);
     if (rc) return rc;
-    char* base = static_cast<char*>(g_scratch.ptr);
-    float *xd = (float*)(base + ox), *wd = (float*)(base + ow), *bd = bh ? (float*)(base + ob) : nullptr,
-          *yd = (float*)(base + oy);
+    const int x3 = math == QNN_MATH_3XTF32;
+    const int kern = forward_kernel(g, rank, math, algo);
+    void* packed = nullptr;
+    if (kern != kKernGeneral) {
+        const size_t pbytes = kern == kKernTc ? tc_packed_bytes(g, rank, x3) : tc2d_packed_bytes(g, rank, x3);
+        bool fresh = false;
+        rc = resident_packed(dev, w_idx, ((uint64_t)kern << 8) | (uint64_t)x3 | ((uint64_t)pbytes << 16), pbytes, st, &packed, &fresh);
+        if (!rc && fresh) {
+            rc = kern == kKernTc ? tc_pack(g, rank, x3, 0, wd, packed, st) : tc2d_pack(g, rank, x3, 0, wd, packed, st);
+            mark_used(dev, w_idx, st);  // later users of the entry (any stream) wait for the image
+        }
+        if (rc) return rc;
+    }
+    float *xd = nullptr, *yd = nullptr;
+    if ((rc = stream_scratch_alloc(reinterpret_cast<void**>(&xd), align256(nx * 4), st))) return rc;
+    if ((rc = stream_scratch_alloc(reinterpret_cast<void**>(&yd), align256(ny * 4), st))) {
+        cudaFreeAsync(xd, st);
+        return rc;
+    }
     // units that can be cut independently: samples (conv) or rows (dense: batch == 1, rows live in in_sp[2])
     const bool dense = g.conj_w && g.batch == 1 && g.k[2] == 1;
     const long long units = dense ? g.in_sp[2] : g.batch;
     const size_t x_unit = nx / (size_t)units, y_unit = ny / (size_t)units;
     int chunks = 1;
-    if ((nx + ny) * 4 >= (size_t)8 << 20 && units >= 8 && g_pipe.init()) {
+    HostPipe* pipe = nullptr;
+    if ((nx + ny) * 4 >= (size_t)8 << 20 && units >= 8 && (pipe = borrow_pipe(dev))) {
         chunks = units >= 64 ? 8 : 4;  // measured on cfg 2: 1 / 2 / 4 / 8 / 16 chunks -> 2.04 / 1.70 / 1.59 / 1.54 / 1.65 ms
                                        // (67 MB of y over PCIe is ~1.45 ms on its own; uneven cuts gained nothing)
         if (const char* env = getenv("QNN_HOST_CHUNKS")) {  // tuning knob: 1..16 pipeline chunks
@@ -323,21 +541,31 @@ int forward_host(const Geom& g, int rank, int math, int algo, size_t nx, size_t 
             if (v >= 1 && v <= 16 && v <= units) chunks = v;
         }
     }
-    cudaError_t e;
-    if ((e = cudaMemcpyAsync(wd, wh, nw * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) goto fail;
-    if (bh && (e = cudaMemcpyAsync(bd, bh, nb * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) goto fail;
-    if (chunks == 1) {
-        if ((e = cudaMemcpyAsync(xd, xh, nx * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) goto fail;
-        rc = run_forward(g, rank, math, algo, xd, wd, bd, yd, st);
-        if (rc) return rc;
-        if ((e = cudaMemcpyAsync(yh, yd, ny * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) goto fail;
-        if ((e = cudaStreamSynchronize(st)) != cudaSuccess) goto fail;
-        return QNN_OK;
+    cudaError_t e = cudaSuccess;
+    auto finish = [&](int code) {
+        mark_used(dev, w_idx, st);
+        if (bh) mark_used(dev, b_idx, st);
+        cudaFreeAsync(xd, st);
+        cudaFreeAsync(yd, st);
+        if (pipe) return_pipe(dev, pipe);
+        if (code == QNN_OK && e != cudaSuccess) {
+            set_error("host staging failed: %s", cudaGetErrorString(e));
+            return (int)QNN_E_CUDA;
+        }
+        return code;
+    };
+    if (chunks == 1 || !pipe) {
+        if ((e = cudaMemcpyAsync(xd, xh, nx * 4, cudaMemcpyHostToDevice, st)) != cudaSuccess) return finish(QNN_OK);
+        rc = run_forward(g, rank, math, algo, xd, wd, packed, bd, yd, st);
+        if (rc) return finish(rc);
+        if ((e = cudaMemcpyAsync(yh, yd, ny * 4, cudaMemcpyDeviceToHost, st)) != cudaSuccess) return finish(QNN_OK);
+        e = cudaStreamSynchronize(st);
+        return finish(QNN_OK);
     }
-    // the copy streams must not run ahead of work already queued on the caller's stream (scratch reuse)
-    if ((e = cudaEventRecord(g_pipe.ev_start, st)) != cudaSuccess) goto fail;
-    if ((e = cudaStreamWaitEvent(g_pipe.in, g_pipe.ev_start, 0)) != cudaSuccess) goto fail;
-    if ((e = cudaStreamWaitEvent(g_pipe.out, g_pipe.ev_start, 0)) != cudaSuccess) goto fail;
+    // the copy streams must not run ahead of work already queued on the caller's stream (scratch allocation, uploads)
+    if ((e = cudaEventRecord(pipe->ev_start, st)) != cudaSuccess) return finish(QNN_OK);
+    if ((e = cudaStreamWaitEvent(pipe->in, pipe->ev_start, 0)) != cudaSuccess) return finish(QNN_OK);
+    if ((e = cudaStreamWaitEvent(pipe->out, pipe->ev_start, 0)) != cudaSuccess) return finish(QNN_OK);
     for (int c = 0; c < chunks; ++c) {
         const long long u0 = units * c / chunks, u1 = units * (c + 1) / chunks;
         if (u1 == u0) continue;
@@ -347,22 +575,21 @@ int forward_host(const Geom& g, int rank, int math, int algo, size_t nx, size_t 
         else
             gc.batch = (int)(u1 - u0);
         if ((e = cudaMemcpyAsync(xd + u0 * x_unit, xh + u0 * x_unit, (size_t)(u1 - u0) * x_unit * 4,
-                                 cudaMemcpyHostToDevice, g_pipe.in)) != cudaSuccess) goto fail;
-        if ((e = cudaEventRecord(g_pipe.ev_in[c], g_pipe.in)) != cudaSuccess) goto fail;
-        if ((e = cudaStreamWaitEvent(st, g_pipe.ev_in[c], 0)) != cudaSuccess) goto fail;
-        rc = run_forward(gc, rank, math, algo, xd + u0 * x_unit, wd, bd, yd + u0 * y_unit, st);
-        if (rc) return rc;
-        if ((e = cudaEventRecord(g_pipe.ev_k[c], st)) != cudaSuccess) goto fail;
-        if ((e = cudaStreamWaitEvent(g_pipe.out, g_pipe.ev_k[c], 0)) != cudaSuccess) goto fail;
+                                 cudaMemcpyHostToDevice, pipe->in)) != cudaSuccess) return finish(QNN_OK);
+        if ((e = cudaEventRecord(pipe->ev_in[c], pipe->in)) != cudaSuccess) return finish(QNN_OK);
+        if ((e = cudaStreamWaitEvent(st, pipe->ev_in[c], 0)) != cudaSuccess) return finish(QNN_OK);
+        rc = run_forward(gc, rank, math, algo, xd + u0 * x_unit, wd, packed, bd, yd + u0 * y_unit, st);
+        if (rc) return finish(rc);
+        if ((e = cudaEventRecord(pipe->ev_k[c], st)) != cudaSuccess) return finish(QNN_OK);
+        if ((e = cudaStreamWaitEvent(pipe->out, pipe->ev_k[c], 0)) != cudaSuccess) return finish(QNN_OK);
         if ((e = cudaMemcpyAsync(yh + u0 * y_unit, yd + u0 * y_unit, (size_t)(u1 - u0) * y_unit * 4,
-                                 cudaMemcpyDeviceToHost, g_pipe.out)) != cudaSuccess) goto fail;
+                                 cudaMemcpyDeviceToHost, pipe->out)) != cudaSuccess) return finish(QNN_OK);
     }
-    if ((e = cudaStreamSynchronize(g_pipe.out)) != cudaSuccess) goto fail;
-    if ((e = cudaStreamSynchronize(st)) != cudaSuccess) goto fail;
-    return QNN_OK;
-fail:
-    set_error("host staging failed: %s", cudaGetErrorString(e));
-    return QNN_E_CUDA;
+    // the caller's stream joins the copy-out stream (the stream-ordered frees below must come after the last D2H)
+    if ((e = cudaEventRecord(pipe->ev_out, pipe->out)) != cudaSuccess) return finish(QNN_OK);
+    if ((e = cudaStreamWaitEvent(st, pipe->ev_out, 0)) != cudaSuccess) return finish(QNN_OK);
+    e = cudaStreamSynchronize(st);
+    return finish(QNN_OK);
 }
 
 // ---------------------------------------------------------------- NCCL through dlopen (no link-time dependency)
@@ -440,14 +667,14 @@ int qnn_conv_out_spatial(const qnn_conv_desc* d, int32_t out_spatial[3]) {
 int qnn_conv_uses_tensor_cores(const qnn_conv_desc* d) {
     Geom g;
     if (build_geom(d, &g)) return 0;
-    if (d->algo == QNN_ALGO_GENERAL || d->math != QNN_MATH_TF32) return 0;
-    return tc_plan(g, d->rank).ok || tc2d_plan(g, d->rank).ok;
+    if (!valid_math(d->math) || !valid_algo(d->algo) || empty_out(g)) return 0;
+    return forward_kernel(g, d->rank, d->math, d->algo) != kKernGeneral;
 }
 
 int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units) {
     Geom g;
     if (build_dense_geom(rows, in_q, q_units, QNN_ACT_LINEAR, &g)) return 0;
-    return tc_plan(g, 1).ok;
+    return tc_plan(g, 1, 0).ok;
 }
 
 int qnn_conv_backward_uses_tensor_cores(const qnn_conv_desc* d, int32_t* dx_tc, int32_t* dkernel_tc) {
@@ -460,7 +687,7 @@ int qnn_conv_backward_uses_tensor_cores(const qnn_conv_desc* d, int32_t* dx_tc, 
     }
     int a = 0, b = 0;
     backward_selection(g, d->rank, d->math, d->algo, &a, &b);
-    *dx_tc = a;
+    *dx_tc = a != kKernGeneral;
     *dkernel_tc = b;
     return QNN_OK;
 }
@@ -475,7 +702,7 @@ int qnn_dense_backward_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_u
     }
     int a = 0, b = 0;
     backward_selection(g, 1, QNN_MATH_TF32, QNN_ALGO_AUTO, &a, &b);
-    *dx_tc = a;
+    *dx_tc = a != kKernGeneral;
     *dkernel_tc = b;
     return QNN_OK;
 }
@@ -485,7 +712,7 @@ int qnn_conv_forward(const qnn_conv_desc* d, const float* x, const float* kernel
     Geom g;
     int rc = build_geom(d, &g);
     if (rc) return rc;
-    return run_forward(g, d->rank, d->math, d->algo, x, kernel, bias, y, static_cast<cudaStream_t>(stream));
+    return run_forward(g, d->rank, d->math, d->algo, x, kernel, nullptr, bias, y, static_cast<cudaStream_t>(stream));
 }
 
 int qnn_dense_forward(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
@@ -493,42 +720,157 @@ int qnn_dense_forward(int64_t rows, int32_t in_q, int32_t q_units, const float* 
     Geom g;
     int rc = build_dense_geom(rows, in_q, q_units, activation, &g);
     if (rc) return rc;
-    return run_forward(g, 1, math, algo, x, kernel, bias, y, static_cast<cudaStream_t>(stream));
+    return run_forward(g, 1, math, algo, x, kernel, nullptr, bias, y, static_cast<cudaStream_t>(stream));
 }
 
-int qnn_conv_backward(const qnn_conv_desc* d, const float* x, const float* kernel, const float* y, const float* dy,
-                      float* dx, float* dkernel, float* dbias, void* stream) {
+// ---- packed kernel images (caller-owned cache)
+namespace {
+// geometry + kernel family of the problem a packed image of `kind` feeds: the layer's own forward, or the transposed
+// problem of its data gradient
+int packed_problem(const Geom& g, int rank, int math, int algo, int kind, Geom* gp, int* kern) {
+    if (kind != QNN_PACK_FORWARD && kind != QNN_PACK_DGRAD) {
+        set_error("unknown packed-kernel kind %d", kind);
+        return QNN_E_INVALID;
+    }
+    if (!valid_math(math) || !valid_algo(algo)) {
+        set_error("unknown math mode %d / algo %d", math, algo);
+        return QNN_E_INVALID;
+    }
+    *kern = kKernGeneral;
+    *gp = g;
+    if (empty_out(g)) return QNN_OK;
+    if (kind == QNN_PACK_FORWARD) {
+        *kern = forward_kernel(g, rank, math, algo);
+    } else {
+        int dxk = 0, dwk = 0;
+        backward_selection(g, rank, math, algo, &dxk, &dwk);
+        *kern = dxk;
+        *gp = transposed_geom(g);
+    }
+    return QNN_OK;
+}
+size_t packed_bytes_of(const Geom& g, int rank, int math, int algo, int kind) {
+    Geom gp;
+    int kern;
+    if (packed_problem(g, rank, math, algo, kind, &gp, &kern) || kern == kKernGeneral) return 0;
+    const int x3 = math == QNN_MATH_3XTF32;
+    return kern == kKernTc ? tc_packed_bytes(gp, rank, x3) : tc2d_packed_bytes(gp, rank, x3);
+}
+int pack_of(const Geom& g, int rank, int math, int algo, int kind, const float* kernel, void* packed, cudaStream_t st) {
+    Geom gp;
+    int kern;
+    int rc = packed_problem(g, rank, math, algo, kind, &gp, &kern);
+    if (rc) return rc;
+    if (kern == kKernGeneral) {
+        set_error("this problem has no packed kernel image (it runs on the general kernel): qnn_*_packed_bytes returned 0");
+        return QNN_E_UNSUPPORTED;
+    }
+    if (!kernel || !packed) {
+        set_error("kernel and packed must not be NULL");
+        return QNN_E_INVALID;
+    }
+    const int x3 = math == QNN_MATH_3XTF32, tr = kind == QNN_PACK_DGRAD;
+    return kern == kKernTc ? tc_pack(gp, rank, x3, tr, kernel, packed, st) : tc2d_pack(gp, rank, x3, tr, kernel, packed, st);
+}
+}  // namespace
+
+size_t qnn_conv_packed_bytes(const qnn_conv_desc* d, int32_t kind) {
+    Geom g;
+    if (build_geom(d, &g)) return 0;
+    return packed_bytes_of(g, d->rank, d->math, d->algo, kind);
+}
+
+int qnn_conv_pack(const qnn_conv_desc* d, int32_t kind, const float* kernel, void* packed, void* stream) {
     Geom g;
     int rc = build_geom(d, &g);
     if (rc) return rc;
+    return pack_of(g, d->rank, d->math, d->algo, kind, kernel, packed, static_cast<cudaStream_t>(stream));
+}
+
+int qnn_conv_forward_packed(const qnn_conv_desc* d, const float* x, const float* kernel, const void* packed,
+                            const float* bias, float* y, void* stream) {
+    Geom g;
+    int rc = build_geom(d, &g);
+    if (rc) return rc;
+    return run_forward(g, d->rank, d->math, d->algo, x, kernel, packed, bias, y, static_cast<cudaStream_t>(stream));
+}
+
+size_t qnn_dense_packed_bytes(int64_t rows, int32_t in_q, int32_t q_units, int32_t math, int32_t algo, int32_t kind) {
+    Geom g;
+    if (build_dense_geom(rows, in_q, q_units, QNN_ACT_LINEAR, &g)) return 0;
+    return packed_bytes_of(g, 1, math, algo, kind);
+}
+
+int qnn_dense_pack(int64_t rows, int32_t in_q, int32_t q_units, int32_t math, int32_t algo, int32_t kind,
+                   const float* kernel, void* packed, void* stream) {
+    Geom g;
+    int rc = build_dense_geom(rows, in_q, q_units, QNN_ACT_LINEAR, &g);
+    if (rc) return rc;
+    return pack_of(g, 1, math, algo, kind, kernel, packed, static_cast<cudaStream_t>(stream));
+}
+
+int qnn_dense_forward_packed(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
+                             const void* packed, const float* bias, int32_t activation, int32_t math, int32_t algo,
+                             float* y, void* stream) {
+    Geom g;
+    int rc = build_dense_geom(rows, in_q, q_units, activation, &g);
+    if (rc) return rc;
+    return run_forward(g, 1, math, algo, x, kernel, packed, bias, y, static_cast<cudaStream_t>(stream));
+}
+
+namespace {
+int backward_checks(const Geom& g, const float* x, const float* kernel, const float* y, const float* dy, float* dx,
+                    float* dkernel, float* dbias, bool* nothing) {
+    *nothing = false;
     if (g.act != QNN_ACT_LINEAR && g.act != QNN_ACT_RELU) {
         set_error("backward supports linear and relu activations only");
         return QNN_E_UNSUPPORTED;
     }
     if (!x || !kernel || !y || !dy) {
-        if (empty_out(g) && !dkernel && !dbias && !dx) return QNN_OK;
+        if (empty_out(g) && !dkernel && !dbias && !dx) {
+            *nothing = true;
+            return QNN_OK;
+        }
         set_error("x, kernel, y and dy must not be NULL");
         return QNN_E_INVALID;
     }
-    return run_backward(g, d->rank, d->math, d->algo, x, kernel, y, dy, dx, dkernel, dbias,
+    return QNN_OK;
+}
+}  // namespace
+
+int qnn_conv_backward(const qnn_conv_desc* d, const float* x, const float* kernel, const float* y, const float* dy,
+                      float* dx, float* dkernel, float* dbias, void* stream) {
+    return qnn_conv_backward_packed(d, x, kernel, nullptr, y, dy, dx, dkernel, dbias, stream);
+}
+
+int qnn_conv_backward_packed(const qnn_conv_desc* d, const float* x, const float* kernel, const void* packed_dgrad,
+                             const float* y, const float* dy, float* dx, float* dkernel, float* dbias, void* stream) {
+    Geom g;
+    int rc = build_geom(d, &g);
+    if (rc) return rc;
+    bool nothing;
+    if ((rc = backward_checks(g, x, kernel, y, dy, dx, dkernel, dbias, &nothing)) || nothing) return rc;
+    return run_backward(g, d->rank, d->math, d->algo, x, kernel, packed_dgrad, y, dy, dx, dkernel, dbias,
                         static_cast<cudaStream_t>(stream));
 }
 
 int qnn_dense_backward(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
                        const float* y, const float* dy, int32_t activation, int32_t math, int32_t algo, float* dx,
                        float* dkernel, float* dbias, void* stream) {
+    return qnn_dense_backward_packed(rows, in_q, q_units, x, kernel, nullptr, y, dy, activation, math, algo, dx, dkernel,
+                                     dbias, stream);
+}
+
+int qnn_dense_backward_packed(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,
+                              const void* packed_dgrad, const float* y, const float* dy, int32_t activation,
+                              int32_t math, int32_t algo, float* dx, float* dkernel, float* dbias, void* stream) {
     Geom g;
     int rc = build_dense_geom(rows, in_q, q_units, activation, &g);
     if (rc) return rc;
-    if (g.act != QNN_ACT_LINEAR && g.act != QNN_ACT_RELU) {
-        set_error("backward supports linear and relu activations only");
-        return QNN_E_UNSUPPORTED;
-    }
-    if (!x || !kernel || !y || !dy) {
-        set_error("x, kernel, y and dy must not be NULL");
-        return QNN_E_INVALID;
-    }
-    return run_backward(g, 1, math, algo, x, kernel, y, dy, dx, dkernel, dbias, static_cast<cudaStream_t>(stream));
+    bool nothing;
+    if ((rc = backward_checks(g, x, kernel, y, dy, dx, dkernel, dbias, &nothing)) || nothing) return rc;
+    return run_backward(g, 1, math, algo, x, kernel, packed_dgrad, y, dy, dx, dkernel, dbias,
+                        static_cast<cudaStream_t>(stream));
 }
 
 int qnn_conv_forward_host(const qnn_conv_desc* d, const float* x_host, const float* kernel_host,

@@ -26,18 +26,26 @@ extern std::atomic<unsigned long long> g_launches;
 // release with cudaFreeAsync on the same stream.  Returns QNN_OK or QNN_E_CUDA (error text set).
 int stream_scratch_alloc(void** ptr, size_t bytes, cudaStream_t st);
 inline void count_launch(int n = 1) { g_launches.fetch_add((unsigned long long)n, std::memory_order_relaxed); }
+// Per-DEVICE state (one process may drive several GPUs): SM count of the current device, and the opt-in to more than
+// 48 KB of dynamic shared memory, recorded once per (device, kernel).  ensure_dynamic_smem returns QNN_OK / QNN_E_CUDA.
+constexpr int kMaxDevices = 64;
+int current_device();
+int num_sms();
+int ensure_dynamic_smem(const void* kernel, int bytes);
 
 // general (CUDA-core, fp32) kernels: any rank / stride / dilation / padding / data_format
 int general_forward(const Geom& g, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
 int general_backward(const Geom& g, const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw,
                      float* db, cudaStream_t st);
 
-// helpers of the tensor-core backward path: dz = dy * act'(y) with the bias gradient folded in (either output may be
-// NULL), and the transposed / tap-flipped stored kernel the dgrad convolution consumes
+// helper of the tensor-core backward path: dz = dy * act'(y) with the bias gradient folded in (either output may be
+// NULL); channels_last: rows x C, channels_first: [n][C][S] with S positions per channel
 int dz_bgrad(const float* y, const float* dy, float* dz, float* db, long long rows, int C, int relu, cudaStream_t st);
-int transpose_w(const float* w, float* wt, int taps, int Q, int F, cudaStream_t st);
+int dz_bgrad_cf(const float* y, const float* dy, float* dz, float* db, int batch, int C, long long S, int relu,
+                cudaStream_t st);
 
-// tensor-core kernel (tcgen05 / TMEM / TMA): channels_last rows with taps along the innermost spatial axis
+// tensor-core kernel (tcgen05 / TMEM / TMA): channels_last rows with taps along the innermost spatial axis.
+// `x3` selects 3xTF32 arithmetic (hi / lo operand split, three MMAs per block) instead of plain TF32.
 struct TcPlan {
     int ok;           // shape qualifies
     int f_tile;       // filters per pass (<= 64)
@@ -47,13 +55,22 @@ struct TcPlan {
     int rows_in;      // 128 + (taps-1)*dilation
     int x_stages;
     size_t smem_bytes;
+    size_t w_bytes;       // one part (hi or lo) of one filter tile's packed image
+    size_t packed_bytes;  // whole packed kernel image (all filter tiles, hi [+ lo])
     const char* why;  // reason when !ok
 };
-TcPlan tc_plan(const Geom& g, int rank);
+TcPlan tc_plan(const Geom& g, int rank, int x3);
 void tc_set_trace(void* device_buffer, size_t bytes);
 // x[rows][4][in_q] -> xp[rows][4][xq], xq = in_q rounded up to 4, new channels zero (ragged channel counts)
 int pad_x_channels(const float* x, float* xp, long long rows, int in_q, int xq, cudaStream_t st);
-int tc_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+// packed kernel image: K-major tf32 core matrices per filter tile (see qnn_hamilton_tc.cu); `transposed` reads the stored
+// kernel of the layer whose data gradient `g` describes
+size_t tc_packed_bytes(const Geom& g, int rank, int x3);
+int tc_pack(const Geom& g, int rank, int x3, int transposed, const float* w, void* packed, cudaStream_t st);
+int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const void* packed, const float* bias, float* y,
+                      cudaStream_t st);
+int tc_forward(const Geom& g, int rank, int x3, int transposed, const float* x, const float* w, const float* bias, float* y,
+               cudaStream_t st);
 
 // tensor-core kernel gradient (channels_last rank 1 / dense, stride 1): contraction over positions, four persistent
 // accumulators D_c = dL/df_c in tensor memory, vector reductions into dW
@@ -66,9 +83,9 @@ struct WgradPlan {
     size_t x_stage_bytes, smem_bytes;
     const char* why;
 };
-WgradPlan wgrad_plan(const Geom& g, int rank);
+WgradPlan wgrad_plan(const Geom& g, int rank, int x3);
 void wgrad_set_trace(void* device_buffer, size_t bytes);
-int wgrad_tc(const Geom& g, int rank, const float* x, const float* dz, float* dw, cudaStream_t st);
+int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, float* dw, cudaStream_t st);
 
 // tensor-core kernel for channels_first tensors (rank 1 / 2, stride 1): streamed sub-filters, transposing converters
 struct Tc2dPlan {
@@ -78,11 +95,17 @@ struct Tc2dPlan {
     int xshift;      // columns the box starts left of the first tap (16-byte alignment of the TMA start)
     int x_stages;
     size_t x_stage_bytes, smem_bytes;
+    size_t packed_bytes;  // packed kernel image (hi [+ lo] blocks per (filter tile, 8-channel chunk, tap))
     const char* why;
 };
-Tc2dPlan tc2d_plan(const Geom& g, int rank);
+Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3);
 void tc2d_set_trace(void* device_buffer, size_t bytes);
-int tc2d_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+size_t tc2d_packed_bytes(const Geom& g, int rank, int x3);
+int tc2d_pack(const Geom& g, int rank, int x3, int transposed, const float* w, void* packed, cudaStream_t st);
+int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const void* packed, const float* bias, float* y,
+                        cudaStream_t st);
+int tc2d_forward(const Geom& g, int rank, int x3, int transposed, const float* x, const float* w, const float* bias, float* y,
+                 cudaStream_t st);
 
 }  // namespace qnn
 

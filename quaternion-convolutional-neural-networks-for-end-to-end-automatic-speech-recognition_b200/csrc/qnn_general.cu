@@ -237,12 +237,17 @@ __global__ void __launch_bounds__(256) k_dz_bgrad(const float4* __restrict__ y, 
     extern __shared__ float4 red[];  // [by][bx]
     const long long per = (rows + gridDim.x - 1) / gridDim.x;
     const long long r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
-    for (int c4 = threadIdx.x; c4 < C4; c4 += blockDim.x) {
+    // uniform trip count (the loop body holds __syncthreads): threads past the last column run masked iterations
+    const int c4_end = ((C4 + (int)blockDim.x - 1) / (int)blockDim.x) * (int)blockDim.x;
+    for (int c4i = threadIdx.x; c4i < c4_end; c4i += blockDim.x) {
+        const bool live = c4i < C4;
+        const int c4 = live ? c4i : C4 - 1;
         float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
         // four rows per iteration: eight independent 16-byte loads in flight per thread
         long long r = r0 + threadIdx.y;
         const long long step = blockDim.y;
-        for (; r + 3 * step < r1; r += 4 * step) {
+        const long long r_end = live ? r1 : r0;  // masked threads skip the row loops
+        for (; r + 3 * step < r_end; r += 4 * step) {
             float4 g[4], v[4];
 #pragma unroll
             for (int u = 0; u < 4; ++u) g[u] = __ldg(dy + (r + u * step) * C4 + c4);
@@ -266,7 +271,7 @@ __global__ void __launch_bounds__(256) k_dz_bgrad(const float4* __restrict__ y, 
                 acc.w += g[u].w;
             }
         }
-        for (; r < r1; r += step) {
+        for (; r < r_end; r += step) {
             const long long o = r * C4 + c4;
             float4 g = __ldg(dy + o);
             if (relu) {
@@ -285,7 +290,7 @@ __global__ void __launch_bounds__(256) k_dz_bgrad(const float4* __restrict__ y, 
         if (db) {
             red[threadIdx.y * blockDim.x + threadIdx.x] = acc;
             __syncthreads();
-            if (threadIdx.y == 0) {
+            if (threadIdx.y == 0 && live) {
                 for (int j = 1; j < (int)blockDim.y; ++j) {
                     const float4 o = red[j * blockDim.x + threadIdx.x];
                     acc.x += o.x;
@@ -303,18 +308,52 @@ __global__ void __launch_bounds__(256) k_dz_bgrad(const float4* __restrict__ y, 
     }
 }
 
-// wt[taps-1-tap][f][c][q] = w[tap][q][c][f]: the stored kernel of the TRANSPOSED convolution (dgrad), still un-expanded
-__global__ void __launch_bounds__(256) k_transpose_w(const float* __restrict__ w, float* __restrict__ wt, int taps, int Q,
-                                                     int F) {
-    const int total = taps * Q * 4 * F;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        int t = i;
-        const int q = t % Q;
-        t /= Q;
-        const int c = t & 3;
-        t >>= 2;
-        const int f = t % F, tap_t = t / F;
-        wt[i] = __ldg(w + (((size_t)(taps - 1 - tap_t) * Q + q) * 4 + c) * F + f);
+// channels_first twin: tensors are [n][C][S] (S contiguous positions per channel).  One block walks whole (n, c) rows:
+// dz = dy * act'(y) with 16-byte accesses where the row is aligned, block-reduced row sums added to dbias[c].
+__global__ void __launch_bounds__(256) k_dz_bgrad_cf(const float* __restrict__ y, const float* __restrict__ dy,
+                                                     float* __restrict__ dz, float* __restrict__ db, long long rows, int C,
+                                                     long long S, int relu) {
+    __shared__ float red[8];
+    const bool vec = (S % 4) == 0;  // every row then starts on a 16-byte boundary (the base pointers are 16-byte aligned)
+    for (long long row = blockIdx.x; row < rows; row += gridDim.x) {
+        const long long base = row * S;
+        float acc = 0.f;
+        if (vec) {
+            const float4* y4 = reinterpret_cast<const float4*>(y + base);
+            const float4* g4 = reinterpret_cast<const float4*>(dy + base);
+            float4* z4 = dz ? reinterpret_cast<float4*>(dz + base) : nullptr;
+            for (long long i = threadIdx.x; i < S / 4; i += blockDim.x) {
+                float4 g = __ldg(g4 + i);
+                if (relu) {
+                    const float4 v = __ldg(y4 + i);
+                    g.x = v.x > 0.f ? g.x : 0.f;
+                    g.y = v.y > 0.f ? g.y : 0.f;
+                    g.z = v.z > 0.f ? g.z : 0.f;
+                    g.w = v.w > 0.f ? g.w : 0.f;
+                }
+                if (z4) z4[i] = g;
+                acc += (g.x + g.y) + (g.z + g.w);
+            }
+        } else {
+            for (long long i = threadIdx.x; i < S; i += blockDim.x) {
+                float g = __ldg(dy + base + i);
+                if (relu && !(__ldg(y + base + i) > 0.f)) g = 0.f;
+                if (dz) dz[base + i] = g;
+                acc += g;
+            }
+        }
+        if (db) {  // block-uniform
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float t = 0.f;
+                for (int j = 0; j < (int)(blockDim.x >> 5); ++j) t += red[j];
+                atomicAdd(db + (int)(row % C), t);
+            }
+            __syncthreads();
+        }
     }
 }
 
@@ -369,13 +408,20 @@ int dz_bgrad(const float* y, const float* dy, float* dz, float* db, long long ro
     return QNN_OK;
 }
 
-int transpose_w(const float* w, float* wt, int taps, int Q, int F, cudaStream_t st) {
-    const int total = taps * Q * 4 * F;
-    k_transpose_w<<<std::min((total + 255) / 256, 148 * 8), 256, 0, st>>>(w, wt, taps, Q, F);
+int dz_bgrad_cf(const float* y, const float* dy, float* dz, float* db, int batch, int C, long long S, int relu,
+                cudaStream_t st) {
+    cudaError_t e;
+    if (db && (e = cudaMemsetAsync(db, 0, (size_t)C * sizeof(float), st)) != cudaSuccess) {
+        set_error("dbias memset failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    const long long rows = (long long)batch * C;
+    if (rows == 0 || S == 0) return QNN_OK;
+    k_dz_bgrad_cf<<<(unsigned)std::min<long long>(rows, 148LL * 8), 256, 0, st>>>(y, dy, dz, db, rows, C, S, relu);
     count_launch();
-    cudaError_t e = cudaGetLastError();
+    e = cudaGetLastError();
     if (e != cudaSuccess) {
-        set_error("kernel transpose launch failed: %s", cudaGetErrorString(e));
+        set_error("dz/bgrad (channels_first) launch failed: %s", cudaGetErrorString(e));
         return QNN_E_CUDA;
     }
     return QNN_OK;

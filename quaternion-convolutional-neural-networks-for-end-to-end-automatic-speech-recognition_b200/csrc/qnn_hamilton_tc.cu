@@ -6,6 +6,16 @@
 // exists: the 16 signed blocks are 16 tcgen05.mma instructions that share 4 A operands (the input components) and
 // 4 B operands (the sub-filters); the sign is the instruction descriptor's negate bit.
 //
+// Sub-filters: a pre-pass (k_pack_w1d, ~2 us, cacheable by the caller: qnn_conv_pack / qnn_*_forward_packed) writes the
+// K-major, tf32-rounded core-matrix image of the stored kernel, [filter tile][hi | lo][tap][c][q/4][f][q%4]; the main
+// kernel pulls the image of its filter tile into shared memory with plain bulk copies (one per lane of a warp) and keeps
+// it resident.  It also is where the data gradient's transposed, tap-flipped kernel comes from (strided read).
+//
+// Arithmetic (template X3): TF32 = one MMA per block on operands rounded to nearest tf32; 3xTF32 = each operand is split
+// into hi = rn_tf32(v) and lo = rn_tf32(v - hi) and the block is x_hi.w_hi + x_lo.w_hi + x_hi.w_lo (three MMAs, the
+// dropped x_lo.w_lo term is 2^-22 relative): fp32-faithful results from the tensor cores (the reference computes in fp32,
+// complexnn/conv.py:334, dense.py:149).  3xTF32 halves the A ring (4 slots of hi|lo) and doubles the resident image.
+//
 // One persistent CTA per SM, 896 threads, warp-specialised:
 //   x tiles      TMA: raw fp32 (128 rows + halo, 32 channels) -> 128B-swizzled smem ring, issued by the converter group
 //                that owns the ring slot as soon as it has consumed it (no separate producer warp).  When in_q is a
@@ -19,14 +29,15 @@
 //   warps 16-19  MMA issuers : one warp per output component (y_r, y_i, y_j, y_k): a single thread sustains only one
 //                              tcgen05.mma per ~117 cycles, four issuers reach ~37 (measured; floor 32 at N = 64);
 //                              A from TMEM, B = sub-filter block resident in smem (K-major, no swizzle).  Warp 16 also
-//                              initialises the barriers, fires the first x stages and the first pass' sub-filter boxes
-//                              (one TMA per lane, before anything else) and owns the TMEM allocation
-//   warps 0-15   epilogue    : first pack + round the sub-filters into smem (overlapping the first x loads); per tile all
-//                              16 warps pull the accumulators into registers at once (TMEM is free again after two
-//                              tcgen05.ld), then +bias -> activation -> swizzled staging -> TMA store (clips ragged tiles)
+//                              initialises the barriers, fires the first x stages and the sub-filter image copies
+//                              (one per lane, before anything else) and owns the TMEM allocation
+//   warps 0-15   epilogue    : per tile all 16 warps pull the accumulators into registers at once (TMEM is free again
+//                              after two tcgen05.ld), then +bias -> activation -> swizzled staging -> TMA store (clips
+//                              ragged tiles)
 // The latency-critical roles sit on the HIGHEST warp ids: the SM's issue arbiter favours high warp ids, and the 16
 // epilogue warps spend most of their time polling an mbarrier (with a nanosleep back-off so they do not steal issue slots).
-// TMEM columns: [0,256) four fp32 accumulators y_r|y_i|y_j|y_k (<= 64 filters per pass), [256,512) eight 32-column A slots.
+// TMEM columns: [0,256) four fp32 accumulators y_r|y_i|y_j|y_k (<= 64 filters per pass), [256,512) the A ring
+// (TF32: eight 32-column slots; 3xTF32: four 64-column slots, hi | lo).
 #include <algorithm>
 #include <mutex>
 #include "qnn_common.h"
@@ -40,11 +51,10 @@ using namespace ptx;
 constexpr int kTileM = 128;
 constexpr int kThreads = 896;
 constexpr int kEpiThreads = 512;             // warps 0..15
-constexpr int kASlots = 8;
-constexpr int kASlotCols = 32;
+constexpr int kMaxASlots = 8;
 constexpr int kAccCols = 256;
 constexpr int kMaxXStages = 4;
-constexpr int kMaxTapBatch = 4;              // taps converted per tcgen05.wait::st
+constexpr int kMaxTapBatch = 4;              // taps converted per tcgen05.wait::st (<= A slots of either mode)
 constexpr int kStagingBytes = kTileM * 128;  // one [128 x 32] fp32 store tile
 constexpr uint32_t kSmemLimit = 232448;      // 227 KB opt-in maximum per CTA
 // register budget: 896 x 72 = 64512 at launch = 128 x kRegsWg0 + 256 x kRegsWg1 + 512 x kRegsEpi
@@ -66,14 +76,13 @@ constexpr uint32_t kNegDense = transpose_bits(kNegConv);
 enum { kActLinear = 0, kActRelu = 1, kActGeneric = 2 };
 enum { kWarpAlloc = 16, kWarpIssuer0 = 16, kWarpConv0 = 20 };
 
-// Optional per-CTA event trace (diagnostics, qnn_debug_trace): 64 clock64() slots per CTA, see tools/tc_trace.py
+// Optional per-CTA event trace (diagnostics, qnn_debug_trace): clock64() slots per CTA, see tools/tc_trace.py
 constexpr int kTraceSlots = 256;  // 0..63 coarse events; 64.. detailed events of the CTA's second tile
-enum { kTrStart = 0, kTrSetup = 1, kTrPacked = 2, kTrFirstTma = 3, kTrTmaDone = 4, kTrFirstX = 5, kTrWReady = 6,
+enum { kTrStart = 0, kTrSetup = 1, kTrFirstTma = 3, kTrFirstX = 5, kTrWReady = 6,
        kTrFirstA = 7, kTrTile0 = 8 /* + 5 * tile: acc_empty passed, acc_full committed, epilogue got acc, TMEM released,
                                      stores issued */, kTrEnd = 58, kTrGlobalStart = 59, kTrGlobalEnd = 60, kTrSm = 61,
        kTrConv = 64 /* + 8*stage: x_full passed, a_empty passed (tap 0..3), wait::st done, arrived */,
-       kTrIssue = 128 /* + 2*slot: a_full passed, committed */, kTrProd = 192 /* + 2*stage: x_empty passed, issued */,
-       kTrPack = 240 /* loads issued, data arrived, stored, fenced+arrived */ };
+       kTrIssue = 128 /* + 2*slot: a_full passed, committed */ };
 
 struct TcParams {
     unsigned long long* trace;
@@ -87,13 +96,16 @@ struct TcParams {
     int F, f_tile, n_ftiles;
     int rows_in, x_stages, x_stage_bytes;
     int act, has_bias;
-    uint32_t w_bytes;
+    uint32_t w_bytes;      // one part (hi or lo) of one filter tile's image
+    uint32_t w_img_bytes;  // what one pass keeps resident: w_bytes (TF32) or 2 * w_bytes (3xTF32: hi | lo)
+    uint32_t w_chunk;      // bulk-copy granule of the image load (multiple of 16 bytes)
+    int handshake;         // taps >= A slots: converter groups hand over stage by stage (see the converter role)
 };
 
 struct __align__(8) Barriers {
     uint64_t x_full[kMaxXStages];
-    uint64_t a_full[kASlots], a_empty[kASlots];
-    uint64_t acc_full, acc_empty, w_raw, w_ready;
+    uint64_t a_full[kMaxASlots], a_empty[kMaxASlots];
+    uint64_t acc_full, acc_empty, w_ready;
     uint32_t tmem_base;
 };
 
@@ -114,6 +126,17 @@ __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// plain (1-D) bulk copy global -> shared, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(smem_dst)),
+                 "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 // Walks the x stages of a tile without integer division: for every stage the number of k-steps (8 channels each)
@@ -165,6 +188,15 @@ __device__ __forceinline__ float activate(float v, int act_rt) {
     return act_apply(v, act_rt);
 }
 
+// Operand conversion.  TF32: "add half an ulp, let the tensor core truncate" = round to nearest, one integer add per
+// element (an infinite input becomes NaN; finite inputs round exactly like cvt.rna).  3xTF32: hi = rn_tf32(v) with the
+// low 13 bits cleared, lo = rn_tf32(v - hi) (the subtraction is exact in fp32).
+__device__ __forceinline__ uint32_t rn_tf32(uint32_t v) { return v + 0x1000u; }
+__device__ __forceinline__ void split_tf32(uint32_t v, uint32_t& hi, uint32_t& lo) {
+    hi = (v + 0x1000u) & 0xffffe000u;
+    lo = __float_as_uint(__uint_as_float(v) - __uint_as_float(hi)) + 0x1000u;
+}
+
 // bias + activation on 32 accumulator columns of this thread's row, written to the swizzled staging tile
 template <int ACT>
 __device__ __forceinline__ void stage_chunk(const uint32_t (&v)[32], const float* bias32, uint8_t* st, int r, int act_rt) {
@@ -205,16 +237,25 @@ __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn,
     named_bar_sync(5 + pair, 256);
 }
 
-template <bool CONJ, int ACT>
+// the resident image of filter tile `ft`: bulk copies of w_chunk bytes, chunk `i` of `n` (the last one may be shorter)
+__device__ __forceinline__ void load_w_chunk(const TcParams& p, const uint8_t* wp, uint8_t* w_s, uint64_t* bar, int ft, int i) {
+    const uint32_t off = (uint32_t)i * p.w_chunk;
+    const uint32_t n = min(p.w_chunk, p.w_img_bytes - off);
+    bulk_load(w_s + off, wp + (size_t)ft * p.w_img_bytes + off, n, bar);
+}
+
+template <bool CONJ, int ACT, bool X3>
 __global__ void __launch_bounds__(kThreads, 1)
-k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy,
-              const __grid_constant__ CUtensorMap tmw, const TcParams p, const float* __restrict__ bias) {
+k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const TcParams p,
+              const uint8_t* __restrict__ wp, const float* __restrict__ bias) {
+    constexpr int kASlots = X3 ? 4 : 8;        // A ring: 256 TMEM columns either way
+    constexpr int kASlotCols = X3 ? 64 : 32;   // 3xTF32: [hi (32) | lo (32)]
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment (TMA 128B swizzle) by offsetting the __shared__ array itself, so that every pointer derived
     // from it stays in the shared address space (LDS/STS instead of generic LD/ST)
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* w_s = smem;                                               // resident sub-filters of the current f-tile
-    uint8_t* x_s = w_s + ((p.w_bytes + 1023u) & ~1023u);               // x ring
+    uint8_t* w_s = smem;                                               // resident sub-filter image of the current f-tile
+    uint8_t* x_s = w_s + ((p.w_img_bytes + 1023u) & ~1023u);           // x ring
     uint8_t* y_s = x_s + (size_t)p.x_stages * p.x_stage_bytes;         // 2 staging tiles (one per epilogue group pair)
     float* bias_s = reinterpret_cast<float*>(y_s + 2 * kStagingBytes); // 4 * f_tile floats
     Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(bias_s) + 1024);
@@ -222,6 +263,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     const int tid = threadIdx.x;
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform by construction
     const int Fp = p.f_tile, KQ = p.in_q_pad >> 2;
+    const int n_wchunks = (int)((p.w_img_bytes + p.w_chunk - 1) / p.w_chunk);
 
     if (tid == kWarpAlloc * 32) {
         trace(p, kTrStart);
@@ -233,7 +275,6 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         }
         tma_prefetch_desc(&tmx);
         tma_prefetch_desc(&tmy);
-        tma_prefetch_desc(&tmw);
         for (int i = 0; i < kMaxXStages; ++i) {
             mbar_init(&bars->x_full[i], 1);
         }
@@ -243,16 +284,15 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         }
         mbar_init(&bars->acc_full, 4);
         mbar_init(&bars->acc_empty, kEpiThreads);
-        mbar_init(&bars->w_raw, 1);
-        mbar_init(&bars->w_ready, kEpiThreads);
+        mbar_init(&bars->w_ready, 1);
         fence_mbar_init();
     }
     if (warp == kWarpAlloc) {
-        // The first x stages and the first pass' sub-filters are requested right here, before TMEM allocation and the
-        // CTA-wide barrier, one TMA per LANE of this warp (a single thread issuing all of them costs ~170 cycles
+        // The first x stages and the first pass' sub-filter image are requested right here, before TMEM allocation and the
+        // CTA-wide barrier, one copy per LANE of this warp (a single thread issuing all of them costs ~170 cycles
         // each): the cold HBM ramp-up -- all CTAs asking at once -- is the longest latency of the start-up.
         __syncwarp();
-        asm volatile("griddepcontrol.wait;" ::: "memory");  // x / the kernel may be the previous kernel's output
+        asm volatile("griddepcontrol.wait;" ::: "memory");  // x / the packed kernel may be the previous kernel's output
         const int lane = tid & 31;
         const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
         const int total_stages = my_tiles * p.n_stages;
@@ -268,15 +308,11 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 tma_load_4d(dst, &tmx, &bars->x_full[lane], (s % p.n_chunks) * 32, s / p.n_chunks, t0 - p.pad_lo, b);
             if (lane == 0) trace(p, kTrFirstTma);
         }
-        // The stored sub-filters land RAW in their final region (one box per tap and component: in_q_pad rows of f_tile
-        // floats, rows beyond in_q zero-filled); the packer warps transpose in place.  Every CTA wants the same boxes
-        // at the same moment: each CTA starts at a different box so that the requests spread over the L2 slices.
-        if (lane == 31) mbar_arrive_expect_tx(&bars->w_raw, p.w_bytes);
-        const int KQ0 = p.in_q_pad >> 2, nbox = p.taps * 4;
-        for (int i = lane; i < nbox; i += 32) {
-            const int tc = (i + (int)blockIdx.x) % nbox;
-            tma_load_4d(w_s + (size_t)tc * KQ0 * p.f_tile * 16, &tmw, &bars->w_raw, 0, tc & 3, 0, tc >> 2);
-        }
+        // Every CTA wants the same image at the same moment: each CTA starts at a different chunk so that the requests
+        // spread over the L2 slices instead of queueing on one line set.
+        if (lane == 31) mbar_arrive_expect_tx(&bars->w_ready, p.w_img_bytes);
+        __syncwarp();
+        for (int i = lane; i < n_wchunks; i += 32) load_w_chunk(p, wp, w_s, &bars->w_ready, 0, (i + (int)blockIdx.x) % n_wchunks);
         __syncwarp();
     }
     if (warp == kWarpAlloc) {
@@ -309,15 +345,12 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             // =========================== MMA issuers (whole warp runs the loops, one lane issues) ===========================
             const bool elected = elect_one();
             const int b = warp - kWarpIssuer0;  // this issuer's output component
-            if (warp == kWarpAlloc && elected && ft > 0) {  // (the first pass' sub-filters were requested at kernel start)
-                mbar_arrive_expect_tx(&bars->w_raw, p.w_bytes);
-                // every CTA wants the same boxes at the same moment: start each CTA at a different box so that the
-                // requests spread over the L2 slices instead of queueing on one line set
-                const int nbox = p.taps * 4;
-                int tc = (int)(blockIdx.x % (unsigned)nbox);
-                for (int i = 0; i < nbox; ++i) {
-                    tma_load_4d(w_s + (size_t)tc * KQ * Fp * 16, &tmw, &bars->w_raw, ft * Fp, tc & 3, 0, tc >> 2);
-                    if (++tc == nbox) tc = 0;
+            if (warp == kWarpAlloc && elected && ft > 0) {  // (the first pass' image was requested at kernel start)
+                mbar_arrive_expect_tx(&bars->w_ready, p.w_img_bytes);
+                int i = (int)(blockIdx.x % (unsigned)n_wchunks);
+                for (int n = 0; n < n_wchunks; ++n) {
+                    load_w_chunk(p, wp, w_s, &bars->w_ready, ft, i);
+                    if (++i == n_wchunks) i = 0;
                 }
             }
             __syncwarp();
@@ -327,8 +360,9 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             const uint32_t w_lo = (uint32_t)d0, desc_hi = (uint32_t)(d0 >> 32);
             const uint32_t sub_stride = (uint32_t)KQ * Fp;  // descriptor-lo units (16 B) between sub-filters
             const uint32_t tap_stride = 4u * sub_stride;
+            const uint32_t lo_off = p.w_bytes >> 4;         // 3xTF32: the lo part of the image follows the hi part
             constexpr uint32_t neg_table = CONJ ? kNegDense : kNegConv;
-            mbar_wait(&bars->w_ready, ft & 1);  // this pass' sub-filters are packed and visible to the async proxy
+            mbar_wait(&bars->w_ready, ft & 1);  // this pass' image has landed (async-proxy writes, read by the tensor core)
             if (warp == kWarpIssuer0 && elected && ft == 0) trace(p, kTrWReady);
             int tcount = 0;
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
@@ -355,10 +389,17 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                             for (int ks = 0; ks < 4; ++ks) {
                                 if (ks >= nks) break;
                                 const int a = ka[ks];
-                                const uint32_t k_lo = tap_lo + (uint32_t)(kq[ks] >> 2) * Fp;
                                 const int c = a ^ b;  // sub-filter index: IDX[a][b] = a xor b
-                                mma_ts(t_acc + b * Fp, a_col + ks * 8, k_lo + c * sub_stride, desc_hi,
-                                       ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos, accumulate);
+                                const uint32_t k_lo = tap_lo + (uint32_t)(kq[ks] >> 2) * Fp + c * sub_stride;
+                                const uint32_t idesc = ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos;
+                                if (X3) {
+                                    // small terms first, then the leading one: x_lo.w_hi + x_hi.w_lo + x_hi.w_hi
+                                    mma_ts(t_acc + b * Fp, a_col + 32 + ks * 8, k_lo, desc_hi, idesc, accumulate);
+                                    mma_ts(t_acc + b * Fp, a_col + ks * 8, k_lo + lo_off, desc_hi, idesc, 1);
+                                    mma_ts(t_acc + b * Fp, a_col + ks * 8, k_lo, desc_hi, idesc, 1);
+                                } else {
+                                    mma_ts(t_acc + b * Fp, a_col + ks * 8, k_lo, desc_hi, idesc, accumulate);
+                                }
                                 accumulate = 1;
                             }
                             mma_commit(&bars->a_empty[as]);  // one of the four arrivals that free the slot
@@ -384,8 +425,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             // Two groups of 128 threads take alternate x stages, so one group's tcgen05.wait::st overlaps the other's
             // loads.  A group owns the ring slots of its parity: once its 128 threads are done with a slot, its thread 0
             // issues the TMA load of the stage that comes x_stages later into the same slot (no producer warp, no
-            // "slot empty" barrier).  Rounding to nearest tf32 is "add half an ulp, let the tensor core truncate": one
-            // integer add per element (an infinite input becomes NaN; finite inputs round exactly like cvt.rna).
+            // "slot empty" barrier).
             const int cgrp = (tid - kWarpConv0 * 32) >> 7;
             const int r = (tid - kWarpConv0 * 32) & 127;
             const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
@@ -426,6 +466,11 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                         while (as >= kASlots) { as -= kASlots; aph ^= 1; }
                         continue;
                     }
+                    // mbarrier parity only tells consecutive phases apart.  A group's wait on the first slot of a stage is
+                    // unambiguous as long as the other group's previous stage cannot lag a whole ring behind, which
+                    // program order guarantees for taps < A slots.  With more taps the groups hand over explicitly: a group
+                    // starts a stage only after the other one has passed every slot wait of the stage before.
+                    if (p.handshake && stage_i > 0) named_bar_sync(12 + (cgrp ^ 1), 256);
                     mbar_wait(&bars->x_full[xs], xph);
                     if (detail && s < 8) trace(p, kTrConv + 8 * s);
                     if (r == 0 && stage_i == 0 && ft == 0) trace(p, kTrFirstX);
@@ -440,23 +485,40 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                             if (++as_b == kASlots) { as_b = 0; aph_b ^= 1; }
                         }
                         tc_fence_after_sync();
+                        if (p.handshake && tap0 + nb >= p.taps && stage_i + 1 < total_stages) named_bar_arrive(12 + cgrp, 256);
                         as_b = as;
                         for (int tb = 0; tb < nb; ++tb) {
                             const uint32_t row = (uint32_t)(r + (tap0 + tb) * p.dil);
                             const uint8_t* xrow = xb + row * 128u;
                             const uint32_t sw = row & 7u;
                             const uint32_t dst = t_a + lane_base + as_b * kASlotCols;
-                            if (kc == 32) {
+                            if (X3) {
+                                for (int k0 = 0; k0 < kc; k0 += 8) {  // 8 columns at a time: hi and lo halves of the slot
+                                    const uint4 v0 = *reinterpret_cast<const uint4*>(xrow + ((((k0 >> 2)) ^ sw) << 4));
+                                    const uint4 v1 = *reinterpret_cast<const uint4*>(xrow + ((((k0 >> 2) + 1) ^ sw) << 4));
+                                    uint32_t hi[8], lo[8];
+                                    split_tf32(v0.x, hi[0], lo[0]);
+                                    split_tf32(v0.y, hi[1], lo[1]);
+                                    split_tf32(v0.z, hi[2], lo[2]);
+                                    split_tf32(v0.w, hi[3], lo[3]);
+                                    split_tf32(v1.x, hi[4], lo[4]);
+                                    split_tf32(v1.y, hi[5], lo[5]);
+                                    split_tf32(v1.z, hi[6], lo[6]);
+                                    split_tf32(v1.w, hi[7], lo[7]);
+                                    tmem_st8_nc(dst + k0, hi);
+                                    tmem_st8_nc(dst + 32 + k0, lo);
+                                }
+                            } else if (kc == 32) {
 #pragma unroll
                                 for (int h = 0; h < 2; ++h) {  // 16 columns at a time: 4 loads, 16 adds, one store
                                     uint32_t u[16];
 #pragma unroll
                                     for (int c4 = 0; c4 < 4; ++c4) {
                                         const uint4 v = *reinterpret_cast<const uint4*>(xrow + (((h * 4 + c4) ^ sw) << 4));
-                                        u[4 * c4 + 0] = v.x + 0x1000u;
-                                        u[4 * c4 + 1] = v.y + 0x1000u;
-                                        u[4 * c4 + 2] = v.z + 0x1000u;
-                                        u[4 * c4 + 3] = v.w + 0x1000u;
+                                        u[4 * c4 + 0] = rn_tf32(v.x);
+                                        u[4 * c4 + 1] = rn_tf32(v.y);
+                                        u[4 * c4 + 2] = rn_tf32(v.z);
+                                        u[4 * c4 + 3] = rn_tf32(v.w);
                                     }
                                     tmem_st16_nc(dst + h * 16, u);
                                 }
@@ -464,8 +526,8 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                                 for (int k0 = 0; k0 < kc; k0 += 8) {
                                     const uint4 v0 = *reinterpret_cast<const uint4*>(xrow + ((((k0 >> 2)) ^ sw) << 4));
                                     const uint4 v1 = *reinterpret_cast<const uint4*>(xrow + ((((k0 >> 2) + 1) ^ sw) << 4));
-                                    const uint32_t u[8] = {v0.x + 0x1000u, v0.y + 0x1000u, v0.z + 0x1000u, v0.w + 0x1000u,
-                                                           v1.x + 0x1000u, v1.y + 0x1000u, v1.z + 0x1000u, v1.w + 0x1000u};
+                                    const uint32_t u[8] = {rn_tf32(v0.x), rn_tf32(v0.y), rn_tf32(v0.z), rn_tf32(v0.w),
+                                                           rn_tf32(v1.x), rn_tf32(v1.y), rn_tf32(v1.z), rn_tf32(v1.w)};
                                     tmem_st8_nc(dst + k0, u);
                                 }
                             }
@@ -493,58 +555,11 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
       reg_alloc<kRegsEpi>();
       for (int ft = 0; ft < p.n_ftiles; ++ft) {
         {
-            // =========================== packers, then epilogue ===========================
+            // =========================== epilogue ===========================
             const int e = tid;  // 0..511
-            {
-                // raw [(tap*4+c)][q][f] -> K-major core matrices [(tap*4+c)][q/4][f][q%4], rounded to nearest tf32 ("add
-                // half an ulp", the tensor core drops the low 13 bits).  Every group of four q rows occupies exactly the
-                // f_tile*16 bytes its packed form needs, so a warp transposes one such region in place: all lanes read
-                // (4 rows x their one or two filters), then all lanes write their 16-byte items.
-                const int lane = e & 31, pw = e >> 5;
-                const int regions = p.taps * 4 * KQ;
-                const bool has2 = lane + 32 < Fp, has1 = lane < Fp;
-                // bias of this pass: requested before the wait so its latency hides behind the sub-filter load
-                float bias_v = 0.f;
-                if (e < 4 * Fp && p.has_bias) bias_v = __ldg(bias + (e / Fp) * p.F + ft * Fp + (e % Fp));
-                mbar_wait(&bars->w_raw, ft & 1);
-                if (e == 0 && ft == 0) trace(p, kTrPack);
-                int it_n = 0;
-                for (int reg = pw; reg < regions; reg += 32, ++it_n) {
-                    if (ft == 0 && lane == 0 && (pw == 0 || pw == 15) && it_n < 4) trace(p, kTrPack + 4 + (pw ? 4 : 0) + it_n);
-                    uint32_t v[2][2][4];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int rg = reg + 16 * u;
-                        const uint32_t* raw = reinterpret_cast<const uint32_t*>(w_s + (size_t)min(rg, regions - 1) * Fp * 16);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            v[u][0][j] = has1 ? raw[j * Fp + lane] : 0u;
-                            v[u][1][j] = has2 ? raw[j * Fp + lane + 32] : 0u;
-                        }
-                    }
-                    __syncwarp();
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int rg = reg + 16 * u;
-                        if (rg < regions) {
-                            uint4* dst = reinterpret_cast<uint4*>(w_s + (size_t)rg * Fp * 16);
-                            if (has1)
-                                dst[lane] = make_uint4(v[u][0][0] + 0x1000u, v[u][0][1] + 0x1000u, v[u][0][2] + 0x1000u,
-                                                       v[u][0][3] + 0x1000u);
-                            if (has2)
-                                dst[lane + 32] = make_uint4(v[u][1][0] + 0x1000u, v[u][1][1] + 0x1000u,
-                                                            v[u][1][2] + 0x1000u, v[u][1][3] + 0x1000u);
-                        }
-                    }
-                }
-                if (e < 4 * Fp) bias_s[e] = bias_v;  // 4 * f_tile <= 256 < kEpiThreads
-                if (e == 0 && ft == 0) trace(p, kTrPack + 2);
-                fence_proxy_async_smem();  // generic-proxy writes above are read by the tensor core (async proxy)
-                mbar_arrive(&bars->w_ready);
-                if (e == 0 && ft == 0) trace(p, kTrPack + 3);
-                named_bar_sync(9, kEpiThreads);  // bias_s visible to every epilogue thread
-                if (e == 0 && ft == 0) trace(p, kTrPacked);
-            }
+            // bias of this pass, laid out like the accumulator columns: [component][f_tile]
+            if (e < 4 * Fp) bias_s[e] = p.has_bias ? __ldg(bias + (e / Fp) * p.F + ft * Fp + (e % Fp)) : 0.f;  // 4 * f_tile <= 256
+            named_bar_sync(9, kEpiThreads);  // bias_s visible to every epilogue thread
             // 4 groups of 128 threads (one warp per TMEM lane quadrant); group g owns 32-column chunks g and g+4.
             // Groups g and g+2 share staging tile (g & 1) and take turns on it in lock step (256-thread named barrier).
             const int grp = e >> 7, r = e & 127;
@@ -572,7 +587,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     // sub-filters, so the x ring and the sub-filter region are free: each group gets two private staging
                     // tiles (no turn taking, no wait between its two chunks).
                     uint8_t* st_own[2] = {x_s + (size_t)grp * kStagingBytes, w_s + (size_t)grp * kStagingBytes};
-                    const bool w_region_ok = p.w_bytes >= 4u * kStagingBytes;
+                    const bool w_region_ok = p.w_img_bytes >= 4u * kStagingBytes;
 #pragma unroll
                     for (int which = 0; which < 2; ++which) {
                         const int c = grp + 4 * which;
@@ -621,6 +636,46 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     }
 }
 
+// Stored kernel element (tap, q, c, f) at w[tap_src * s_tap + q * s_q + c * s_c + f * s_f], tap_src = flip ? taps-1-tap : tap
+//   -> wp[ft][part][tap][c][q/4][f][q%4], q < in_q_pad (rows >= in_q are zero), one float4 per thread;
+// part 0 = rn_tf32(v) (3xTF32: low bits cleared), part 1 (3xTF32 only) = rn_tf32(v - hi).
+// The strides make this the forward image (s_q = 4F, s_c = F, s_f = 1) or the data gradient's transposed, tap-flipped
+// one (the roles of q and f swapped: s_q = 1, s_f = 4F of the forward layer's kernel).
+__global__ void __launch_bounds__(256) k_pack_w1d(const float* __restrict__ w, float4* __restrict__ wp, int taps, int in_q,
+                                                  int KQ, int F, int Fp, int parts, long long s_tap, long long s_q,
+                                                  long long s_c, long long s_f, int flip) {
+    const int n_ft = F / Fp;
+    const long long total = (long long)n_ft * parts * taps * 4 * KQ * Fp;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        long long t = i;
+        const int f = (int)(t % Fp);
+        t /= Fp;
+        const int k4 = (int)(t % KQ);
+        t /= KQ;
+        const int c = (int)(t & 3);
+        t >>= 2;
+        const int tap = (int)(t % taps);
+        t /= taps;
+        const int part = (int)(t % parts), ft = (int)(t / parts);
+        const float* src = w + (long long)(flip ? taps - 1 - tap : tap) * s_tap + (long long)c * s_c +
+                           (long long)(ft * Fp + f) * s_f;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = k4 * 4 + j;
+            const uint32_t v = q < in_q ? __float_as_uint(__ldg(src + (long long)q * s_q)) : 0u;
+            if (parts == 1) {
+                o[j] = v + 0x1000u;
+            } else {
+                uint32_t hi, lo;
+                split_tf32(v, hi, lo);
+                o[j] = part ? lo : hi;
+            }
+        }
+        wp[i] = make_float4(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
+    }
+}
+
 // x[rows][4][in_q] -> xp[rows][4][xq] (xq = in_q rounded up to 4, new channels zero): one thread per output float4
 __global__ void __launch_bounds__(256) k_pad_x(const float* __restrict__ x, float4* __restrict__ xp, long long rows, int in_q,
                                                int xq) {
@@ -639,29 +694,26 @@ __global__ void __launch_bounds__(256) k_pad_x(const float* __restrict__ x, floa
     }
 }
 
-int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
+typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams, const uint8_t*, const float*);
 
-typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const TcParams, const float*);
-
-TcKernel pick_kernel(bool conj, int act) {
+template <bool X3>
+TcKernel pick_kernel_x(bool conj, int act) {
     const int a = act == QNN_ACT_LINEAR ? kActLinear : (act == QNN_ACT_RELU ? kActRelu : kActGeneric);
-    if (conj) return a == kActLinear ? k_hamilton_tc<true, kActLinear> : a == kActRelu ? k_hamilton_tc<true, kActRelu>
-                                                                                        : k_hamilton_tc<true, kActGeneric>;
-    return a == kActLinear ? k_hamilton_tc<false, kActLinear> : a == kActRelu ? k_hamilton_tc<false, kActRelu>
-                                                                               : k_hamilton_tc<false, kActGeneric>;
+    if (conj) return a == kActLinear ? k_hamilton_tc<true, kActLinear, X3> : a == kActRelu ? k_hamilton_tc<true, kActRelu, X3>
+                                                                                            : k_hamilton_tc<true, kActGeneric, X3>;
+    return a == kActLinear ? k_hamilton_tc<false, kActLinear, X3> : a == kActRelu ? k_hamilton_tc<false, kActRelu, X3>
+                                                                                   : k_hamilton_tc<false, kActGeneric, X3>;
 }
+TcKernel pick_kernel(bool conj, int act, bool x3) { return x3 ? pick_kernel_x<true>(conj, act) : pick_kernel_x<false>(conj, act); }
 
 unsigned long long* g_trace = nullptr;
 size_t g_trace_bytes = 0;
+
+cudaError_t launch_check(const char* what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) set_error("%s launch failed: %s", what, cudaGetErrorString(e));
+    return e;
+}
 
 }  // namespace
 
@@ -671,12 +723,7 @@ int pad_x_channels(const float* x, float* xp, long long rows, int in_q, int xq, 
     k_pad_x<<<(unsigned)std::min<long long>((total + 255) / 256, 16LL * num_sms()), 256, 0, st>>>(
         x, reinterpret_cast<float4*>(xp), rows, in_q, xq);
     count_launch();
-    cudaError_t e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        set_error("channel padding launch failed: %s", cudaGetErrorString(e));
-        return QNN_E_CUDA;
-    }
-    return QNN_OK;
+    return launch_check("channel padding") == cudaSuccess ? QNN_OK : QNN_E_CUDA;
 }
 
 void tc_set_trace(void* device_buffer, size_t bytes) {
@@ -684,7 +731,7 @@ void tc_set_trace(void* device_buffer, size_t bytes) {
     g_trace_bytes = bytes;
 }
 
-TcPlan tc_plan(const Geom& g, int rank) {
+TcPlan tc_plan(const Geom& g, int rank, int x3) {
     TcPlan pl{};
     pl.ok = 0;
     auto no = [&](const char* why) {
@@ -696,24 +743,25 @@ TcPlan tc_plan(const Geom& g, int rank) {
     if (g.s[2] != 1) return no("stride != 1");
     if (g.in_q < 4) return no("fewer than 4 quaternion input channels (contraction too short for the tensor cores)");
     // in_q % 4 != 0: the component blocks of x do not start on 16-byte boundaries (TMA needs that), so x goes through a
-    // channel-padding pre-pass first (tc_forward); the stored kernel needs no padding (its box zero-fills the rows)
+    // channel-padding pre-pass first (tc_forward); the packed kernel image is zero-padded by the pack pre-pass
     if (g.F % 16) return no("filters not a multiple of 16");
     const int taps = g.k[2];
     const int rows_in = kTileM + (taps - 1) * g.d[2];
     if (rows_in > 256) return no("halo exceeds the 256-row TMA box");
     if (g.out_sp[2] < 1 || g.batch < 1) return no("empty problem");
     const int in_q_pad = (g.in_q + 7) & ~7;
-    if (in_q_pad > 256) return no("more than 256 quaternion input channels (TMA box limit of the sub-filter load)");
     const size_t stage = ((size_t)rows_in * 128 + 1023) & ~size_t(1023);
     // Filters per pass: the whole layer when it fits (<= 64, accumulators 4 x f_tile TMEM columns); otherwise a
     // divisor that is a multiple of 32, so that every 32-column store chunk stays inside one output component.
+    // 3xTF32 keeps twice the image (hi | lo) resident, so it usually settles on a smaller tile.
     int f_tile = 0, stages = 0;
-    size_t fixed = 0;
+    size_t fixed = 0, w_bytes = 0;
     const int cand[3] = {g.F <= 64 ? g.F : 0, 64, 32};
     for (int ci = 0; ci < 3 && !f_tile; ++ci) {
         const int ft = cand[ci];
         if (ft <= 0 || ft > g.F || g.F % ft || (ft != g.F && ft % 32)) continue;
-        const size_t w_pad = (((size_t)taps * 4 * in_q_pad * ft * 4) + 1023) & ~size_t(1023);
+        w_bytes = (size_t)taps * 4 * in_q_pad * ft * 4;
+        const size_t w_pad = ((w_bytes * (x3 ? 2 : 1)) + 1023) & ~size_t(1023);
         fixed = 1024 /*align slack*/ + w_pad + 2 * kStagingBytes + 1024 /*bias*/ + 512 /*barriers*/;
         if (fixed + 2 * stage > kSmemLimit) continue;
         f_tile = ft;
@@ -728,18 +776,52 @@ TcPlan tc_plan(const Geom& g, int rank) {
     pl.rows_in = rows_in;
     pl.x_stages = stages;
     pl.smem_bytes = fixed + (size_t)stages * stage;
+    pl.w_bytes = w_bytes;
+    pl.packed_bytes = w_bytes * (x3 ? 2 : 1) * (size_t)(g.F / f_tile);
     pl.why = "";
     return pl;
 }
 
-int tc_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
-    const TcPlan pl = tc_plan(g, rank);
+size_t tc_packed_bytes(const Geom& g, int rank, int x3) {
+    const TcPlan pl = tc_plan(g, rank, x3);
+    return pl.ok ? pl.packed_bytes : 0;
+}
+
+// `transposed`: w is the stored kernel of the layer whose DATA GRADIENT `g` describes (g.in_q = that layer's filters,
+// g.F = its in_q); the image is the transposed, tap-flipped kernel of SURVEY 3.4, read straight from the stored layout.
+int tc_pack(const Geom& g, int rank, int x3, int transposed, const float* w, void* packed, cudaStream_t st) {
+    const TcPlan pl = tc_plan(g, rank, x3);
     if (!pl.ok) {
         set_error("tensor-core kernel does not take this shape: %s", pl.why);
         return QNN_E_UNSUPPORTED;
     }
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) {
-        set_error("tensor-core kernel needs 16-byte aligned x, kernel and y");
+    if ((reinterpret_cast<uintptr_t>(packed) & 15) || !w) {
+        set_error("packed kernel image must be 16-byte aligned and the kernel non-NULL");
+        return QNN_E_INVALID;
+    }
+    const int taps = g.k[2], KQ = pl.in_q_pad >> 2, parts = x3 ? 2 : 1;
+    const long long total = (long long)pl.n_ftiles * parts * taps * 4 * KQ * pl.f_tile;
+    long long s_tap, s_q, s_c, s_f;
+    if (!transposed) {
+        s_tap = (long long)g.in_q * 4 * g.F, s_q = 4LL * g.F, s_c = g.F, s_f = 1;
+    } else {  // stored kernel of the forward layer: [tap][q_fwd = our f][c][f_fwd = our q]
+        s_tap = (long long)g.F * 4 * g.in_q, s_q = 1, s_c = g.in_q, s_f = 4LL * g.in_q;
+    }
+    k_pack_w1d<<<(unsigned)std::min<long long>((total + 255) / 256, 8LL * num_sms()), 256, 0, st>>>(
+        w, static_cast<float4*>(packed), taps, g.in_q, KQ, g.F, pl.f_tile, parts, s_tap, s_q, s_c, s_f, transposed ? 1 : 0);
+    count_launch();
+    return launch_check("kernel packing") == cudaSuccess ? QNN_OK : QNN_E_CUDA;
+}
+
+int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const void* packed, const float* bias, float* y,
+                      cudaStream_t st) {
+    const TcPlan pl = tc_plan(g, rank, x3);
+    if (!pl.ok) {
+        set_error("tensor-core kernel does not take this shape: %s", pl.why);
+        return QNN_E_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(packed)) & 15) {
+        set_error("tensor-core kernel needs 16-byte aligned x, packed kernel and y");
         return QNN_E_UNSUPPORTED;
     }
     const int L = g.in_sp[2], Lo = g.out_sp[2];
@@ -787,20 +869,13 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     p.x_stage_bytes = (int)(((size_t)pl.rows_in * 128 + 1023) & ~size_t(1023));
     p.act = g.act;
     p.has_bias = bias != nullptr;
-    p.w_bytes = (uint32_t)((size_t)p.taps * 4 * p.in_q_pad * p.f_tile * 4);
+    p.w_bytes = (uint32_t)pl.w_bytes;
+    p.w_img_bytes = (uint32_t)(pl.w_bytes * (x3 ? 2 : 1));
+    // the image load is cut into at most 32 bulk copies (one per lane of the issuing warp), 2 KB granules
+    p.w_chunk = (uint32_t)(((p.w_img_bytes + 31) / 32 + 2047) & ~2047u);
+    p.handshake = p.taps >= (x3 ? 4 : 8) ? 1 : 0;
 
-    CUtensorMap tmx, tmy, tmw;
-    {
-        // stored kernel [tap][q][c][f]: one box = (f_tile filters, one component, in_q_pad rows, one tap), no swizzle
-        const uint64_t dims[4] = {(uint64_t)g.F, 4, (uint64_t)g.in_q, (uint64_t)g.k[2]};
-        const uint64_t str[3] = {(uint64_t)g.F * 4, (uint64_t)g.F * 16, (uint64_t)g.in_q * g.F * 16};
-        const uint32_t box[4] = {(uint32_t)pl.f_tile, 1, (uint32_t)pl.in_q_pad, 1};
-        int e = make_tmap_f32(&tmw, w, 4, dims, str, box, false);
-        if (e) {
-            set_error("cuTensorMapEncodeTiled(kernel) failed (%d)", e);
-            return QNN_E_CUDA;
-        }
-    }
+    CUtensorMap tmx, tmy;
     if (p.flat) {
         const uint64_t dims[3] = {(uint64_t)xq * 4, (uint64_t)L, (uint64_t)g.batch};
         const uint64_t str[2] = {(uint64_t)xq * 16, (uint64_t)L * xq * 16};
@@ -830,23 +905,8 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
             return QNN_E_CUDA;
         }
     }
-    TcKernel kern = pick_kernel(g.conj_w != 0, g.act);
-    static std::mutex mu;
-    static TcKernel configured[8];
-    static int n_configured = 0;
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        bool done = false;
-        for (int i = 0; i < n_configured; ++i) done |= configured[i] == kern;
-        if (!done) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
-            if (e != cudaSuccess) {
-                set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-                return QNN_E_CUDA;
-            }
-            configured[n_configured++] = kern;
-        }
-    }
+    TcKernel kern = pick_kernel(g.conj_w != 0, g.act, x3 != 0);
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
     const int grid = std::min(p.n_tiles, num_sms());
     p.trace = (g_trace && g_trace_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace : nullptr;
     cudaLaunchConfig_t cfg{};
@@ -859,7 +919,7 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmx, tmy, tmw, p, bias);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmx, tmy, p, static_cast<const uint8_t*>(packed), bias);
     count_launch();
     if (e == cudaSuccess) e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -867,6 +927,24 @@ int tc_forward(const Geom& g, int rank, const float* x, const float* w, const fl
         return QNN_E_CUDA;
     }
     return QNN_OK;
+}
+
+// Stored (un-packed) kernel: pack into stream-ordered scratch, run, release -- what a caller that does not keep a packed
+// image across calls gets (two launches; qnn_*_forward_packed is the one-launch path).
+int tc_forward(const Geom& g, int rank, int x3, int transposed, const float* x, const float* w, const float* bias, float* y,
+               cudaStream_t st) {
+    const TcPlan pl = tc_plan(g, rank, x3);
+    if (!pl.ok) {
+        set_error("tensor-core kernel does not take this shape: %s", pl.why);
+        return QNN_E_UNSUPPORTED;
+    }
+    void* wp = nullptr;
+    int rc = stream_scratch_alloc(&wp, pl.packed_bytes, st);
+    if (rc) return rc;
+    rc = tc_pack(g, rank, x3, transposed, w, wp, st);
+    if (!rc) rc = tc_forward_packed(g, rank, x3, x, wp, bias, y, st);
+    cudaFreeAsync(wp, st);
+    return rc;
 }
 
 }  // namespace qnn

@@ -24,8 +24,7 @@
 //     which also clips ragged tiles.
 // Work item = (tile, filter tile of <= 64 filters); persistent CTAs stride over the items.
 //
-// EXPERIMENTAL, off unless QNN_EXPERIMENTAL_CL2D=1 (written after round 1's GPU budget was spent: compiles, NOT yet run
-// on hardware): template parameter CL selects a channels_last rank-2 variant of the same main loop -- the x stage is a
+// Template parameter CL selects the channels_last rank-2 variant of the same main loop -- the x stage is a
 // 5-D box [8 q][4 components][128 + halo columns][1 row][1 sample] under the 128-byte swizzle (one 128-byte line per
 // position, read with 16-byte loads like qnn_hamilton_tc.cu), the epilogue stages [128 positions][32 channels] rows.
 // Warp roles and the TMEM plan are those of qnn_hamilton_tc.cu: warps 0-15 epilogue, 16-19 MMA issuers (one per output
@@ -44,8 +43,7 @@ using namespace ptx;
 constexpr int kTileM = 128;
 constexpr int kThreads = 1024;
 constexpr int kEpiThreads = 512;
-constexpr int kSlots = 8;
-constexpr int kSlotCols = 32;
+constexpr int kMaxSlots = 8;   // TF32: eight 32-column A slots (and B blocks); 3xTF32: four 64-column ones (hi | lo)
 constexpr int kAccCols = 256;
 constexpr int kMaxXStages = 6;
 constexpr int kMaxTapBatch = 4;
@@ -87,12 +85,13 @@ struct P2 {
     int xshift;      // the box starts xshift (0..3) columns left of the first tap: its start must be 16-byte aligned
     int x_stages, x_stage_bytes;
     int act, has_bias;
-    uint32_t b_blk_bytes;  // 4 sub-filters x 2 k-groups x f_tile x 16 B
+    int handshake;         // KW >= A slots: converter groups hand over stage by stage (see the converter role)
+    uint32_t b_blk_bytes;  // one B slot: 4 sub-filters x 2 k-groups x f_tile x 16 B (3xTF32: twice that, hi block | lo block)
 };
 
 struct __align__(8) Bars {
     uint64_t x_full[kMaxXStages], x_empty[kMaxXStages];
-    uint64_t a_full[kSlots], b_full[kSlots], a_empty[kSlots];
+    uint64_t a_full[kMaxSlots], b_full[kMaxSlots], a_empty[kMaxSlots];
     uint64_t acc_full, acc_empty;
     uint32_t tmem_base;
 };
@@ -107,6 +106,9 @@ template <int N>
 __device__ __forceinline__ void reg_alloc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int nthreads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t desc_lo, uint32_t desc_hi, uint32_t idesc,
@@ -136,6 +138,11 @@ __device__ __forceinline__ float activate(float v, int act_rt) {
     if (ACT == kActLinear) return v;
     if (ACT == kActRelu) return fmaxf(v, 0.f);
     return act_apply(v, act_rt);
+}
+
+__device__ __forceinline__ void split_tf32(uint32_t v, uint32_t& hi, uint32_t& lo) {
+    hi = (v + 0x1000u) & 0xffffe000u;                                                   // rn_tf32(v), low bits cleared
+    lo = __float_as_uint(__uint_as_float(v) - __uint_as_float(hi)) + 0x1000u;           // rn_tf32(v - hi)
 }
 
 // bias + activation on 32 accumulator columns (= 32 output channels) of this thread's position, written transposed
@@ -202,10 +209,12 @@ __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn,
     named_bar_sync(5 + pair, 256);
 }
 
-template <bool CONJ, bool CL, int ACT>
+template <bool CONJ, bool CL, int ACT, bool X3>
 __global__ void __launch_bounds__(kThreads, 1)
 k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const P2 p,
                 const float* __restrict__ wp, const float* __restrict__ bias) {
+    constexpr int kSlots = X3 ? 4 : 8;
+    constexpr int kSlotCols = X3 ? 64 : 32;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_s = smem;                                             // kSlots sub-filter blocks
@@ -263,6 +272,7 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
         const uint32_t w_lo = (uint32_t)d0, desc_hi = (uint32_t)(d0 >> 32);
         const uint32_t sub_stride = 2u * Fp;             // descriptor-lo units (16 B) between sub-filters of a block
         const uint32_t slot_stride = p.b_blk_bytes >> 4;  // ... between B slots
+        const uint32_t lo_off = p.b_blk_bytes >> 5;       // 3xTF32: the lo block follows the hi block inside a slot
         constexpr uint32_t neg_table = CONJ ? kNegDense : kNegConv;
         const int slots_per_item = p.n_stages * p.KW;
         int icount = 0;
@@ -284,8 +294,14 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         const int c = a ^ b;  // sub-filter index: IDX[a][b] = a xor b
-                        mma_ts(t_acc + b * Fp, a_col + a * 8, blk_lo + c * sub_stride, desc_hi,
-                               ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos, accumulate);
+                        const uint32_t idesc = ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos;
+                        if (X3) {  // x_lo.w_hi + x_hi.w_lo + x_hi.w_hi
+                            mma_ts(t_acc + b * Fp, a_col + 32 + a * 8, blk_lo + c * sub_stride, desc_hi, idesc, accumulate);
+                            mma_ts(t_acc + b * Fp, a_col + a * 8, blk_lo + lo_off + c * sub_stride, desc_hi, idesc, 1);
+                            mma_ts(t_acc + b * Fp, a_col + a * 8, blk_lo + c * sub_stride, desc_hi, idesc, 1);
+                        } else {
+                            mma_ts(t_acc + b * Fp, a_col + a * 8, blk_lo + c * sub_stride, desc_hi, idesc, accumulate);
+                        }
                         accumulate = 1;
                     }
                     mma_commit(&bars->a_empty[as]);  // one of the four arrivals that free the A and the B slot
@@ -344,6 +360,8 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
         const int ch_stride = p.wbox;  // floats between channels of a stage
         int stage_i = 0;
         uint32_t xs = 0, xph = 0;
+        const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int total_stages = my_items * p.n_stages;
         for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
             const bool tr = cgrp == 0 && r == 0 && item == (int)(blockIdx.x + gridDim.x);
             for (int s = 0; s < p.n_stages; ++s, ++stage_i) {
@@ -353,6 +371,11 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
                     while (as >= kSlots) { as -= kSlots; aph ^= 1; }
                     continue;
                 }
+                // mbarrier parity only tells consecutive phases apart: with KW >= A slots a group's first slot wait of a stage
+                // could alias a phase a whole ring older if the other group lagged, so the groups hand over explicitly -- a
+                // group starts a stage only after the other one has passed every slot wait of the stage before
+                // (stage_i counts over the whole kernel here: stages alternate strictly between the groups).
+                if (p.handshake && stage_i > 0) named_bar_sync(12 + (cgrp ^ 1), 256);
                 mbar_wait(&bars->x_full[xs], xph);
                 if (tr && s < 48) trace(p, kTrConv + 4 * (s >> 1));
                 const float* xb = reinterpret_cast<const float*>(x_s + (size_t)xs * p.x_stage_bytes) + r + p.xshift;
@@ -364,6 +387,7 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
                         if (++as_b == kSlots) { as_b = 0; aph_b ^= 1; }
                     }
                     tc_fence_after_sync();
+                    if (p.handshake && tap0 + nb >= p.KW && stage_i + 1 < total_stages) named_bar_arrive(12 + cgrp, 256);
                     if (tr && s < 48 && tap0 == 0) trace(p, kTrConv + 4 * (s >> 1) + 1);
                     as_b = as;
                     for (int tb = 0; tb < nb; ++tb) {
@@ -373,28 +397,58 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
                             const uint32_t row = (uint32_t)(r + (tap0 + tb) * p.dw);
                             const uint8_t* xrow = x_s + (size_t)xs * p.x_stage_bytes + row * 128u;
                             const uint32_t sw = row & 7u;
+                            if (X3) {
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                uint32_t u[16];
-#pragma unroll
-                                for (int c4 = 0; c4 < 4; ++c4) {
-                                    const uint4 v = *reinterpret_cast<const uint4*>(xrow + (((h * 4 + c4) ^ sw) << 4));
-                                    u[4 * c4 + 0] = v.x + 0x1000u;
-                                    u[4 * c4 + 1] = v.y + 0x1000u;
-                                    u[4 * c4 + 2] = v.z + 0x1000u;
-                                    u[4 * c4 + 3] = v.w + 0x1000u;
+                                for (int g8 = 0; g8 < 4; ++g8) {
+                                    const uint4 v0 = *reinterpret_cast<const uint4*>(xrow + (((2 * g8) ^ sw) << 4));
+                                    const uint4 v1 = *reinterpret_cast<const uint4*>(xrow + (((2 * g8 + 1) ^ sw) << 4));
+                                    uint32_t hi[8], lo[8];
+                                    split_tf32(v0.x, hi[0], lo[0]);
+                                    split_tf32(v0.y, hi[1], lo[1]);
+                                    split_tf32(v0.z, hi[2], lo[2]);
+                                    split_tf32(v0.w, hi[3], lo[3]);
+                                    split_tf32(v1.x, hi[4], lo[4]);
+                                    split_tf32(v1.y, hi[5], lo[5]);
+                                    split_tf32(v1.z, hi[6], lo[6]);
+                                    split_tf32(v1.w, hi[7], lo[7]);
+                                    tmem_st8_nc(dst + g8 * 8, hi);
+                                    tmem_st8_nc(dst + 32 + g8 * 8, lo);
                                 }
-                                tmem_st16_nc(dst + h * 16, u);
+                            } else {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    uint32_t u[16];
+#pragma unroll
+                                    for (int c4 = 0; c4 < 4; ++c4) {
+                                        const uint4 v = *reinterpret_cast<const uint4*>(xrow + (((h * 4 + c4) ^ sw) << 4));
+                                        u[4 * c4 + 0] = v.x + 0x1000u;
+                                        u[4 * c4 + 1] = v.y + 0x1000u;
+                                        u[4 * c4 + 2] = v.z + 0x1000u;
+                                        u[4 * c4 + 3] = v.w + 0x1000u;
+                                    }
+                                    tmem_st16_nc(dst + h * 16, u);
+                                }
                             }
                         } else {
                             const float* xt = xb + (tap0 + tb) * p.dw;
+                            if (X3) {
 #pragma unroll
-                            for (int h = 0; h < 2; ++h) {
-                                uint32_t u[16];
+                                for (int g8 = 0; g8 < 4; ++g8) {  // one input component (8 channels) at a time: hi and lo
+                                    uint32_t hi[8], lo[8];
 #pragma unroll
-                                for (int c = 0; c < 16; ++c)
-                                    u[c] = __float_as_uint(xt[(h * 16 + c) * ch_stride]) + 0x1000u;  // round to nearest tf32
-                                tmem_st16_nc(dst + h * 16, u);
+                                    for (int c = 0; c < 8; ++c) split_tf32(__float_as_uint(xt[(g8 * 8 + c) * ch_stride]), hi[c], lo[c]);
+                                    tmem_st8_nc(dst + g8 * 8, hi);
+                                    tmem_st8_nc(dst + 32 + g8 * 8, lo);
+                                }
+                            } else {
+#pragma unroll
+                                for (int h = 0; h < 2; ++h) {
+                                    uint32_t u[16];
+#pragma unroll
+                                    for (int c = 0; c < 16; ++c)
+                                        u[c] = __float_as_uint(xt[(h * 16 + c) * ch_stride]) + 0x1000u;  // round to nearest tf32
+                                    tmem_st16_nc(dst + h * 16, u);
+                                }
                             }
                         }
                         if (++as_b == kSlots) as_b = 0;
@@ -451,12 +505,15 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
     if (tid == kWarpAlloc * 32) trace(p, kTrEnd);
 }
 
-// Stored kernel [tap][q][c][F]  ->  wp[ft][qc][tap][c][kg][f][q%4]  (q = qc*8 + kg*4 + q%4), rounded to nearest tf32:
-// the K-major, un-swizzled core-matrix image of each (filter tile, 8-channel chunk, tap) block, contiguous.
+// Stored kernel element (tap, q, c, f) at w[tap_src * s_tap + q * s_q + c * s_c + f * s_f] (tap_src: both kernel axes flipped
+// when `flip`)  ->  wp[ft][qc][tap][part][c][kg][f][q%4]  (q = qc*8 + kg*4 + q%4): the K-major, un-swizzled core-matrix image of
+// each (filter tile, 8-channel chunk, tap) block, contiguous; part 0 = rn_tf32(v), part 1 (3xTF32 only) = rn_tf32(v - hi).
+// The strides select the forward image or the data gradient's transposed, tap-flipped one (q and f swap roles).
 __global__ void __launch_bounds__(256) k_pack_w2d(const float* __restrict__ w, float4* __restrict__ wp, int taps, int Q,
-                                                  int F, int Fp) {
+                                                  int F, int Fp, int parts, long long s_tap, long long s_q, long long s_c,
+                                                  long long s_f, int flip) {
     const int n_qc = Q >> 3, n_ft = F / Fp;
-    const int total = n_ft * n_qc * taps * 4 * 2 * Fp;
+    const int total = n_ft * n_qc * taps * parts * 4 * 2 * Fp;
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
         int t = i;
         const int f = t % Fp;
@@ -465,29 +522,27 @@ __global__ void __launch_bounds__(256) k_pack_w2d(const float* __restrict__ w, f
         t >>= 1;
         const int c = t & 3;
         t >>= 2;
+        const int part = t % parts;
+        t /= parts;
         const int tap = t % taps;
         t /= taps;
         const int qc = t % n_qc, ft = t / n_qc;
-        const float* src = w + ((size_t)(tap * Q + qc * 8 + kg * 4) * 4 + c) * F + ft * Fp + f;
-        const size_t qs = (size_t)4 * F;
-        float4 o;
-        o.x = __uint_as_float(__float_as_uint(__ldg(src)) + 0x1000u);
-        o.y = __uint_as_float(__float_as_uint(__ldg(src + qs)) + 0x1000u);
-        o.z = __uint_as_float(__float_as_uint(__ldg(src + 2 * qs)) + 0x1000u);
-        o.w = __uint_as_float(__float_as_uint(__ldg(src + 3 * qs)) + 0x1000u);
-        wp[i] = o;
+        const float* src = w + (long long)(flip ? taps - 1 - tap : tap) * s_tap + (long long)(qc * 8 + kg * 4) * s_q +
+                           (long long)c * s_c + (long long)(ft * Fp + f) * s_f;
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t v = __float_as_uint(__ldg(src + (long long)j * s_q));
+            if (parts == 1) {
+                o[j] = v + 0x1000u;
+            } else {
+                uint32_t hi, lo;
+                split_tf32(v, hi, lo);
+                o[j] = part ? lo : hi;
+            }
+        }
+        wp[i] = make_float4(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
     }
-}
-
-int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
 }
 
 typedef void (*Tc2dKernel)(const CUtensorMap, const CUtensorMap, const P2, const float*, const float*);
@@ -495,13 +550,16 @@ typedef void (*Tc2dKernel)(const CUtensorMap, const CUtensorMap, const P2, const
 unsigned long long* g_trace2d = nullptr;
 size_t g_trace2d_bytes = 0;
 
-Tc2dKernel pick_kernel(int act, bool channels_last) {
+template <bool CL, bool X3>
+Tc2dKernel pick_kernel_x(int a, bool conj) {
+    if (conj) return k_hamilton_tc2d<true, CL, kActLinear, X3>;  // transposed sign table: the data gradient (no activation)
+    return a == kActLinear ? k_hamilton_tc2d<false, CL, kActLinear, X3>
+                           : a == kActRelu ? k_hamilton_tc2d<false, CL, kActRelu, X3> : k_hamilton_tc2d<false, CL, kActGeneric, X3>;
+}
+Tc2dKernel pick_kernel(int act, bool channels_last, bool x3, bool conj) {
     const int a = act == QNN_ACT_LINEAR ? kActLinear : (act == QNN_ACT_RELU ? kActRelu : kActGeneric);
-    if (channels_last)
-        return a == kActLinear ? k_hamilton_tc2d<false, true, kActLinear>
-                               : a == kActRelu ? k_hamilton_tc2d<false, true, kActRelu> : k_hamilton_tc2d<false, true, kActGeneric>;
-    return a == kActLinear ? k_hamilton_tc2d<false, false, kActLinear>
-                           : a == kActRelu ? k_hamilton_tc2d<false, false, kActRelu> : k_hamilton_tc2d<false, false, kActGeneric>;
+    if (channels_last) return x3 ? pick_kernel_x<true, true>(a, conj) : pick_kernel_x<true, false>(a, conj);
+    return x3 ? pick_kernel_x<false, true>(a, conj) : pick_kernel_x<false, false>(a, conj);
 }
 
 }  // namespace
@@ -511,7 +569,7 @@ void tc2d_set_trace(void* device_buffer, size_t bytes) {
     g_trace2d_bytes = bytes;
 }
 
-Tc2dPlan tc2d_plan(const Geom& g, int rank) {
+Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3) {
     Tc2dPlan pl{};
     pl.ok = 0;
     auto no = [&](const char* why) {
@@ -519,17 +577,16 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank) {
         return pl;
     };
     const bool cl = !g.channels_first;
+    if (cl && rank != 2) return no("channels_last rank 1 / 3");  // rank 1 belongs to qnn_hamilton_tc.cu
     if (cl) {
-        // channels_last rank 2: experimental variant, opt-in (see the header comment); rank 1 belongs to qnn_hamilton_tc.cu
         static const bool enabled = [] {
             const char* e = getenv("QNN_EXPERIMENTAL_CL2D");
             return e && e[0] == '1';
         }();
-        if (!enabled) return no("channels_last layout (rank 2 variant is experimental: QNN_EXPERIMENTAL_CL2D=1)");
-        if (rank != 2) return no("channels_last rank 1 / 3");
+        if (!enabled) return no("channels_last rank 2 (variant under validation: QNN_EXPERIMENTAL_CL2D=1)");
     }
     if (rank > 2) return no("rank 3");
-    if (g.conj_w) return no("dense table");
+    if (g.conj_w && g.act != QNN_ACT_LINEAR) return no("transposed sign table with an activation");
     if (g.s[1] != 1 || g.s[2] != 1) return no("stride != 1");
     if (g.in_q % 8) return no("in_q not a multiple of 8");
     if (g.F % 32) return no("filters not a multiple of 32");
@@ -541,10 +598,11 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank) {
     const int xshift = cl ? 0 : (4 - (g.pad_lo[2] & 3)) & 3;
     const int wbox = cl ? kTileM + (g.k[2] - 1) * g.d[2] : (kTileM + (g.k[2] - 1) * g.d[2] + xshift + 3) & ~3;
     if (wbox > 256) return no("halo exceeds the 256-element TMA box");
+    const int slots = x3 ? 4 : 8;
     const int f_tile = g.F % 64 == 0 ? 64 : 32;
-    const size_t blk = (size_t)32 * f_tile * 4;
+    const size_t blk = (size_t)32 * f_tile * 4 * (x3 ? 2 : 1);
     const size_t stage = ((size_t)32 * wbox * 4 + 1023) & ~size_t(1023);
-    const size_t fixed = 1024 + kSlots * blk + 2 * kStagingBytes + (((size_t)g.F * 16 + 1023) & ~size_t(1023)) + 512;
+    const size_t fixed = 1024 + slots * blk + 2 * kStagingBytes + (((size_t)g.F * 16 + 1023) & ~size_t(1023)) + 512;
     if (fixed + 2 * stage > kSmemLimit) return no("x stages do not fit in shared memory");
     pl.ok = 1;
     pl.f_tile = f_tile;
@@ -554,18 +612,57 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank) {
     pl.x_stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / stage);
     pl.x_stage_bytes = stage;
     pl.smem_bytes = fixed + (size_t)pl.x_stages * stage;
+    pl.packed_bytes = (size_t)g.k[1] * g.k[2] * g.in_q * 4 * g.F * sizeof(float) * (x3 ? 2 : 1);
     pl.why = "";
     return pl;
 }
 
-int tc2d_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st) {
-    const Tc2dPlan pl = tc2d_plan(g, rank);
+size_t tc2d_packed_bytes(const Geom& g, int rank, int x3) {
+    const Tc2dPlan pl = tc2d_plan(g, rank, x3);
+    return pl.ok ? pl.packed_bytes : 0;
+}
+
+// `transposed`: w is the stored kernel of the layer whose DATA GRADIENT `g` describes (g.in_q = that layer's filters,
+// g.F = its in_q): the image is the transposed kernel with both kernel axes flipped.
+int tc2d_pack(const Geom& g, int rank, int x3, int transposed, const float* w, void* packed, cudaStream_t st) {
+    const Tc2dPlan pl = tc2d_plan(g, rank, x3);
     if (!pl.ok) {
         set_error("channels_first tensor-core kernel does not take this shape: %s", pl.why);
         return QNN_E_UNSUPPORTED;
     }
-    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(w)) & 15) {
-        set_error("tensor-core kernel needs 16-byte aligned x, kernel and y");
+    if ((reinterpret_cast<uintptr_t>(packed) & 15) || !w) {
+        set_error("packed kernel image must be 16-byte aligned and the kernel non-NULL");
+        return QNN_E_INVALID;
+    }
+    const int taps = g.k[1] * g.k[2], Q = g.in_q, F = g.F, parts = x3 ? 2 : 1;
+    long long s_tap, s_q, s_c, s_f;
+    if (!transposed) {
+        s_tap = (long long)Q * 4 * F, s_q = 4LL * F, s_c = F, s_f = 1;
+    } else {
+        s_tap = (long long)F * 4 * Q, s_q = 1, s_c = Q, s_f = 4LL * Q;
+    }
+    const int total = pl.n_ftiles * (Q / 8) * taps * parts * 8 * pl.f_tile;
+    k_pack_w2d<<<std::min((total + 255) / 256, 4 * num_sms()), 256, 0, st>>>(w, static_cast<float4*>(packed), taps, Q, F,
+                                                                          pl.f_tile, parts, s_tap, s_q, s_c, s_f,
+                                                                          transposed ? 1 : 0);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("kernel packing launch failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    return QNN_OK;
+}
+
+int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const void* packed, const float* bias, float* y,
+                        cudaStream_t st) {
+    const Tc2dPlan pl = tc2d_plan(g, rank, x3);
+    if (!pl.ok) {
+        set_error("channels_first tensor-core kernel does not take this shape: %s", pl.why);
+        return QNN_E_UNSUPPORTED;
+    }
+    if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(packed)) & 15) {
+        set_error("tensor-core kernel needs 16-byte aligned x, packed kernel and y");
         return QNN_E_UNSUPPORTED;
     }
     const int H = g.in_sp[1], W = g.in_sp[2], Ho = g.out_sp[1], Wo = g.out_sp[2], Q = g.in_q, F = g.F;
@@ -596,7 +693,8 @@ int tc2d_forward(const Geom& g, int rank, const float* x, const float* w, const 
     p.x_stage_bytes = (int)pl.x_stage_bytes;
     p.act = g.act;
     p.has_bias = bias != nullptr;
-    p.b_blk_bytes = (uint32_t)(32 * pl.f_tile * 4);
+    p.b_blk_bytes = (uint32_t)(32 * pl.f_tile * 4 * (x3 ? 2 : 1));
+    p.handshake = p.KW >= (x3 ? 4 : 8) ? 1 : 0;
 
     CUtensorMap tmx, tmy;
     if (g.channels_first) {
@@ -640,37 +738,8 @@ int tc2d_forward(const Geom& g, int rank, const float* x, const float* w, const 
             return QNN_E_CUDA;
         }
     }
-    Tc2dKernel kern = pick_kernel(g.act, !g.channels_first);
-    static std::mutex mu;
-    static Tc2dKernel configured[8];
-    static int n_configured = 0;
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        bool done = false;
-        for (int i = 0; i < n_configured; ++i) done |= configured[i] == kern;
-        if (!done) {
-            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
-            if (e != cudaSuccess) {
-                set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-                return QNN_E_CUDA;
-            }
-            configured[n_configured++] = kern;
-        }
-    }
-    // sub-filter pre-pass into a stream-ordered scratch (same size as the stored kernel; freed after the main kernel)
-    const size_t wp_bytes = (size_t)p.taps * Q * 4 * F * sizeof(float);
-    float* wp = nullptr;
-    {
-        int rc = stream_scratch_alloc(reinterpret_cast<void**>(&wp), wp_bytes, st);
-        if (rc) return rc;
-    }
-    cudaError_t e;
-    {
-        const int total = pl.n_ftiles * p.n_qc * p.taps * 8 * pl.f_tile;
-        k_pack_w2d<<<std::min((total + 255) / 256, 4 * num_sms()), 256, 0, st>>>(w, reinterpret_cast<float4*>(wp), p.taps, Q,
-                                                                              F, pl.f_tile);
-        count_launch();
-    }
+    Tc2dKernel kern = pick_kernel(g.act, !g.channels_first, x3 != 0, g.conj_w != 0);
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
     const int grid = std::min(p.n_items, num_sms());
     p.trace = (g_trace2d && g_trace2d_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace2d : nullptr;
     cudaLaunchConfig_t cfg{};
@@ -683,15 +752,32 @@ int tc2d_forward(const Geom& g, int rank, const float* x, const float* w, const 
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, tmx, tmy, p, (const float*)wp, bias);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmx, tmy, p, static_cast<const float*>(packed), bias);
     count_launch();
     if (e == cudaSuccess) e = cudaGetLastError();
-    cudaFreeAsync(wp, st);
     if (e != cudaSuccess) {
         set_error("channels_first tensor-core kernel launch failed: %s", cudaGetErrorString(e));
         return QNN_E_CUDA;
     }
     return QNN_OK;
+}
+
+// Stored (un-packed) kernel: pack into stream-ordered scratch, run, release (two launches; qnn_conv_forward_packed with a
+// cached image is the one-launch path).
+int tc2d_forward(const Geom& g, int rank, int x3, int transposed, const float* x, const float* w, const float* bias, float* y,
+                 cudaStream_t st) {
+    const Tc2dPlan pl = tc2d_plan(g, rank, x3);
+    if (!pl.ok) {
+        set_error("channels_first tensor-core kernel does not take this shape: %s", pl.why);
+        return QNN_E_UNSUPPORTED;
+    }
+    void* wp = nullptr;
+    int rc = stream_scratch_alloc(&wp, pl.packed_bytes, st);
+    if (rc) return rc;
+    rc = tc2d_pack(g, rank, x3, transposed, w, wp, st);
+    if (!rc) rc = tc2d_forward_packed(g, rank, x3, x, wp, bias, y, st);
+    cudaFreeAsync(wp, st);
+    return rc;
 }
 
 }  // namespace qnn

@@ -375,17 +375,6 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
 unsigned long long* g_trace_w = nullptr;
 size_t g_trace_w_bytes = 0;
 
-int num_sms() {
-    static int n = 0;
-    if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-        if (n <= 0) n = 148;
-    }
-    return n;
-}
-
 }  // namespace
 
 void wgrad_set_trace(void* device_buffer, size_t bytes) {
@@ -393,13 +382,14 @@ void wgrad_set_trace(void* device_buffer, size_t bytes) {
     g_trace_w_bytes = bytes;
 }
 
-WgradPlan wgrad_plan(const Geom& g, int rank) {
+WgradPlan wgrad_plan(const Geom& g, int rank, int x3) {
     WgradPlan pl{};
     pl.ok = 0;
     auto no = [&](const char* why) {
         pl.why = why;
         return pl;
     };
+    if (x3) return no("3xTF32 kernel gradient runs on the fp32 CUDA-core kernel");
     if (g.channels_first) return no("channels_first layout");
     if (rank != 1) return no("rank > 1");
     if (g.s[2] != 1) return no("stride != 1");
@@ -435,8 +425,8 @@ WgradPlan wgrad_plan(const Geom& g, int rank) {
 }
 
 // dw (stored-kernel shape [taps][in_q][4][F]) is OVERWRITTEN.  dz = dy * act'(y), fp32, [batch][Lo][4F].
-int wgrad_tc(const Geom& g, int rank, const float* x, const float* dz, float* dw, cudaStream_t st) {
-    const WgradPlan pl = wgrad_plan(g, rank);
+int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, float* dw, cudaStream_t st) {
+    const WgradPlan pl = wgrad_plan(g, rank, x3);
     if (!pl.ok) {
         set_error("tensor-core kernel gradient does not take this shape: %s", pl.why);
         return QNN_E_UNSUPPORTED;
@@ -504,19 +494,7 @@ int wgrad_tc(const Geom& g, int rank, const float* x, const float* dz, float* dw
         }
     }
     auto kern = g.conj_w ? k_hamilton_wgrad_tc<true> : k_hamilton_wgrad_tc<false>;
-    static std::mutex mu;
-    static bool configured[2] = {false, false};
-    {
-        std::lock_guard<std::mutex> lock(mu);
-        if (!configured[g.conj_w ? 1 : 0]) {
-            e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemLimit);
-            if (e != cudaSuccess) {
-                set_error("cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-                return QNN_E_CUDA;
-            }
-            configured[g.conj_w ? 1 : 0] = true;
-        }
-    }
+    if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
     // grid: a multiple of the number of combinations, at most one CTA per SM, no more groups than units
     int groups = std::min(num_sms() / p.n_combos, p.n_units);
     if (groups < 1) groups = 1;

@@ -3,7 +3,15 @@ C ABI -> hand-written kernels and is compared with (a) the golden vectors produc
 (b) the NumPy oracle on seeded inputs.
 
 Tolerances (stated here, as the north star asks: "within 1e-3 relative fp32 tolerance"):
-  * tensor-core kernel, math TF32 (both operands rounded to nearest tf32 = 10 mantissa bits, fp32 accumulation):
+  * THE CONTRACT (verbatim): max|y - ref| / max|ref| <= 1e-3  AND  allclose(y, ref, rtol=1e-3,
+    atol=1e-3 * rms(ref)), ref = fp64-accumulated oracle rounded to fp32.  `check_contract` asserts it; it is met by
+    math 3XTF32 (tensor cores, hi / lo operand split, three MMAs per block -- fp32-faithful like the reference's
+    arithmetic) and by math FP32 (CUDA cores).  Asserted at BASELINE cfg 2 full size, the cfg 3 stack, the cfg 5
+    slice, the north-star dense shape, the golden vectors and random shapes.
+  * math TF32 is the FAST mode: it meets the first half of the contract (max-rel ~3e-4) and misses the element-wise
+    half on a fraction of a percent of outputs (those whose value is small next to the magnitude of their own
+    products); `contract_stats` measures that rate, the tests print it and bound it (< 1 %).  What TF32 results are
+    asserted against:
         normwise      ||y - ref||_F <= 1e-3 * ||ref||_F                      (measured: ~3e-4)
         elementwise   |y - ref| <= 1e-3 * (|x| * |W_full|) + 1e-6             for every output element,
     where |x| * |W_full| is the same conv / matmul on absolute values, i.e. sum_k |x_k w_k| of that element's dot
@@ -46,6 +54,28 @@ def check(y, ref, tol, what=""):
     return emax, efro
 
 
+def contract_stats(y, ref):
+    """SURVEY 8(d)'s parity metric: (max|d| / max|ref|, number of elements violating allclose(rtol=1e-3,
+    atol=1e-3 * rms(ref)), number of elements)."""
+    y = np.asarray(y, dtype=np.float64)
+    ref = np.asarray(ref, dtype=np.float64)
+    assert y.shape == ref.shape, (y.shape, ref.shape)
+    if ref.size == 0:
+        return 0.0, 0, 0
+    d = np.abs(y - ref)
+    rms = float(np.sqrt(np.mean(ref * ref)))
+    viol = int((d > 1e-3 * rms + 1e-3 * np.abs(ref)).sum())
+    return float(d.max() / (np.abs(ref).max() + 1e-30)), viol, int(ref.size)
+
+
+def check_contract(y, ref, what=""):
+    """The contract, verbatim: max|d|/max|ref| <= 1e-3 AND allclose(rtol=1e-3, atol=1e-3*rms(ref))."""
+    emax, viol, n = contract_stats(y, ref)
+    assert emax <= 1e-3, "%s: max|d|/max|ref| = %.3e > 1e-3" % (what, emax)
+    assert viol == 0, "%s: %d of %d elements violate allclose(rtol=1e-3, atol=1e-3*rms(ref))" % (what, viol, n)
+    return emax
+
+
 def check_tf32(y, ref, bound, what=""):
     """The TF32 criterion of the module docstring; `bound` = |x| * |W_full| from the oracle."""
     y = np.asarray(y, dtype=np.float64)
@@ -58,6 +88,9 @@ def check_tf32(y, ref, bound, what=""):
     assert efro <= TF32_TOL, "%s: fro-rel %.3e > 1e-3" % (what, efro)
     assert np.all(np.abs(y - ref) <= TF32_TOL * bound + 1e-6), "%s: elementwise bound violated, worst |d|/bound %.3e" % (
         what, ratio)
+    emax, viol, n = contract_stats(y, ref)      # the fast mode against the contract: first half holds, second nearly
+    assert emax <= 1e-3, "%s: max|d|/max|ref| = %.3e > 1e-3" % (what, emax)
+    assert viol <= max(0.01 * n, 2), "%s: TF32 misses allclose(rtol=1e-3, atol=1e-3*rms) on %d of %d elements" % (what, viol, n)
     return efro, ratio
 
 
@@ -78,13 +111,15 @@ def make_conv(cnn, rank, filters, ksz, kw, kernel, bias):
     return layer, ([kernel] if bias is None else [kernel, bias])
 
 
-@pytest.mark.parametrize("algo", ["general", "auto"])
+@pytest.mark.parametrize("algo", ["general", "auto", "auto-3xtf32"])
 @pytest.mark.parametrize("case", CONV_CASES, ids=[c[0] for c in CONV_CASES])
 def test_conv_forward_vs_reference_golden(cnn, golden, monkeypatch, case, algo):
     name, rank, xs, filters, ksz, kw = case
     g = golden.load("conv_forward")
+    x3 = algo == "auto-3xtf32"
+    algo = "auto" if x3 else algo
     monkeypatch.setenv("QNN_ALGO", algo)
-    monkeypatch.setenv("QNN_MATH", "fp32" if algo == "general" else "tf32")
+    monkeypatch.setenv("QNN_MATH", "fp32" if algo == "general" else ("3xtf32" if x3 else "tf32"))
     layer, weights = make_conv(cnn, rank, filters, ksz, kw, g[name + ".kernel"], g.get(name + ".bias"))
     x = dev(g[name + ".x"])
     layer.build((None,) + tuple(x.shape[1:]))
@@ -100,7 +135,10 @@ def test_conv_forward_vs_reference_golden(cnn, golden, monkeypatch, case, algo):
                                   k["padding"], k["data_format"], k["activation"])
     uses_tc = _native.lib().qnn_conv_uses_tensor_cores(ctypes.byref(desc)) == 1
     assert uses_tc or "_tc_" not in name
-    if algo == "auto" and uses_tc:
+    if x3:
+        check_contract(y.cpu().numpy(), g[name + ".y"], name)        # 3xTF32 (or its fp32 fallback): the contract
+        check(y.cpu().numpy(), g[name + ".y"], FP32_TOL, name)       # ... and in fact fp32-faithful
+    elif algo == "auto" and uses_tc:
         bound = O.qconv_abs_bound(g[name + ".x"], g[name + ".kernel"], filters, k["strides"], k["padding"],
                                   k["data_format"], k["dilation_rate"])
         check_tf32(y.cpu().numpy(), g[name + ".y"], bound, name)
@@ -112,13 +150,15 @@ def test_conv_forward_vs_reference_golden(cnn, golden, monkeypatch, case, algo):
     np.testing.assert_array_equal(yh, y.cpu().numpy())
 
 
-@pytest.mark.parametrize("algo", ["general", "auto"])
+@pytest.mark.parametrize("algo", ["general", "auto", "auto-3xtf32"])
 @pytest.mark.parametrize("case", DENSE_CASES, ids=[c[0] for c in DENSE_CASES])
 def test_dense_forward_vs_reference_golden(cnn, golden, monkeypatch, case, algo):
     name, xs, units, kw = case
     g = golden.load("dense_forward")
+    x3 = algo == "auto-3xtf32"
+    algo = "auto" if x3 else algo
     monkeypatch.setenv("QNN_ALGO", algo)
-    monkeypatch.setenv("QNN_MATH", "fp32" if algo == "general" else "tf32")
+    monkeypatch.setenv("QNN_MATH", "fp32" if algo == "general" else ("3xtf32" if x3 else "tf32"))
     layer = cnn.QuaternionDense(units, **kw)
     layer.build((None, xs[1]))
     layer.built = True
@@ -127,7 +167,10 @@ def test_dense_forward_vs_reference_golden(cnn, golden, monkeypatch, case, algo)
     from complexnn import _native
     uses_tc = _native.lib().qnn_dense_uses_tensor_cores(xs[0], xs[1] // 4, units // 4) == 1
     assert uses_tc or not name.startswith("d_tc_")
-    if algo == "auto" and uses_tc:
+    if x3:
+        check_contract(y.cpu().numpy(), g[name + ".y"], name)
+        check(y.cpu().numpy(), g[name + ".y"], FP32_TOL, name)
+    elif algo == "auto" and uses_tc:
         check_tf32(y.cpu().numpy(), g[name + ".y"], O.qdense_abs_bound(g[name + ".x"], g[name + ".kernel"], units), name)
     else:
         check(y.cpu().numpy(), g[name + ".y"], FP32_TOL, name)
@@ -198,6 +241,14 @@ def test_tensor_core_conv1d_random_shapes_vs_oracle(cnn, native_lib, shape):
     yg = _ops.conv_forward(dev(x), Variable(kern), Variable(bias) if use_bias else None, F, (k,), (1,), pad,
                            "channels_last", (d,), act, math="fp32", algo="general")
     check(yg.cpu().numpy(), ref, FP32_TOL, "general " + str(shape))
+    # 3xTF32: the same problem on the tensor cores when the doubled (hi | lo) image fits, else on the fp32 kernel -- the
+    # contract either way; where the tensor-core kernel takes it, force it (algo tensor) so a silent fallback cannot pass
+    desc3 = _native.make_conv_desc(1, B, (T,), in_q, F, (k,), (1,), (d,), pad, "channels_last", act, math="3xtf32")
+    on_tc = native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(desc3)) == 1
+    y3 = _ops.conv_forward(dev(x), Variable(kern), Variable(bias) if use_bias else None, F, (k,), (1,), pad,
+                           "channels_last", (d,), act, math="3xtf32", algo="tensor" if on_tc else "auto")
+    check_contract(y3.cpu().numpy(), ref, "3xtf32 " + str(shape))
+    check(y3.cpu().numpy(), ref, FP32_TOL, "3xtf32 " + str(shape))
 
 
 @pytest.mark.parametrize("rows,in_q,units", [(1, 4, 64), (127, 8, 128), (129, 40, 256), (1000, 128, 512), (333, 64, 768),
@@ -211,7 +262,11 @@ def test_tensor_core_dense_vs_oracle(cnn, native_lib, rows, in_q, units):
     bias = rng.normal(0, 0.1, size=units).astype(np.float32)
     assert native_lib.qnn_dense_uses_tensor_cores(rows, in_q, units // 4) == 1
     y = _ops.dense_forward(dev(x), Variable(kern), Variable(bias), units, "relu", math="tf32", algo="tensor")
-    check_tf32(y.cpu().numpy(), O.qdense_forward(x, kern, bias, units, "relu"), O.qdense_abs_bound(x, kern, units))
+    ref = O.qdense_forward(x, kern, bias, units, "relu")
+    check_tf32(y.cpu().numpy(), ref, O.qdense_abs_bound(x, kern, units))
+    y3 = _ops.dense_forward(dev(x), Variable(kern), Variable(bias), units, "relu", math="3xtf32", algo="auto")
+    check_contract(y3.cpu().numpy(), ref, "3xtf32 dense")
+    check(y3.cpu().numpy(), ref, FP32_TOL, "3xtf32 dense")
 
 
 def test_tensor_algo_refuses_unsupported_shapes(cnn):
@@ -236,13 +291,27 @@ def test_baseline_config2_full_size(cnn):
     xd = dev(x)
     n0 = _native.launch_count()
     y = layer(xd)
-    assert _native.launch_count() == n0 + 1            # one fused launch, nothing else
+    assert _native.launch_count() == n0 + 2            # first call: kernel image pre-pass + the fused launch
+    y = layer(xd)
+    assert _native.launch_count() == n0 + 3            # steady state: ONE fused launch, the image is cached per weight version
     layer.set_weights([layer.get_weights()[0], rng.normal(0, 0.1, 256).astype(np.float32)])
     y = layer(xd)
+    assert _native.launch_count() == n0 + 5            # weights changed: re-packed once
     kern, bias = layer.get_weights()
     ref = O.qconv_forward(x, kern, bias, 64, 1, "same", "channels_last", 1, "relu")
     efro, ratio = check_tf32(y.cpu().numpy(), ref, O.qconv_abs_bound(x, kern, 64, 1, "same"), "cfg2")
-    print("cfg2 full size: fro-rel %.3e, worst |d| / sum|x||w| %.3e" % (efro, ratio))
+    emax, viol, n = contract_stats(y.cpu().numpy(), ref)
+    print("cfg2 full size, TF32: fro-rel %.3e, worst |d| / sum|x||w| %.3e, max-rel %.3e, allclose violations %d of %d (%.4f %%)"
+          % (efro, ratio, emax, viol, n, 100.0 * viol / n))
+    # the contract at full size on the tensor cores: 3xTF32
+    from complexnn import _ops
+    desc3 = _native.make_conv_desc(1, 256, (256,), 40, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")
+    assert _native.lib().qnn_conv_uses_tensor_cores(ctypes.byref(desc3)) == 1
+    y3 = _ops.conv_forward(xd, layer.kernel, layer.bias, 64, (3,), (1,), "same", "channels_last", (1,), "relu",
+                           math="3xtf32", algo="tensor")
+    emax3 = check_contract(y3.cpu().numpy(), ref, "cfg2 3xtf32")
+    check(y3.cpu().numpy(), ref, FP32_TOL, "cfg2 3xtf32")
+    print("cfg2 full size, 3xTF32: max-rel %.3e, allclose violations 0" % emax3)
     # size-independent properties at full size
     # (1) batch shards are independent: any shard reproduces the same bits (this is what data parallelism relies on)
     y_half = layer(xd[128:].contiguous())
@@ -263,10 +332,18 @@ def test_northstar_dense_full_size(cnn):
     x = rng.normal(size=(65536, 160)).astype(np.float32)
     np.random.seed(1)
     layer = cnn.QuaternionDense(256, activation="relu")
-    y = layer(dev(x))
+    xd = dev(x)
+    y = layer(xd)
     kern, bias = layer.get_weights()
-    check_tf32(y.cpu().numpy(), O.qdense_forward(x, kern, bias, 256, "relu"), O.qdense_abs_bound(x, kern, 256),
-               "dense north star")
+    ref = O.qdense_forward(x, kern, bias, 256, "relu")
+    check_tf32(y.cpu().numpy(), ref, O.qdense_abs_bound(x, kern, 256), "dense north star")
+    emax, viol, n = contract_stats(y.cpu().numpy(), ref)
+    print("dense north star, TF32: max-rel %.3e, allclose violations %d of %d" % (emax, viol, n))
+    from complexnn import _ops
+    assert torch.cuda.is_available()
+    y3 = _ops.dense_forward(xd, layer.kernel, layer.bias, 256, "relu", math="3xtf32", algo="tensor")
+    check_contract(y3.cpu().numpy(), ref, "dense north star 3xtf32")
+    check(y3.cpu().numpy(), ref, FP32_TOL, "dense north star 3xtf32")
 
 
 def test_quaternion_norm_is_multiplicative_on_gpu(cnn):
@@ -432,6 +509,16 @@ def test_baseline_config3_stack_vs_oracle(cnn):
                    "dense layer %d" % i)
         ref_chain = O.qdense_forward(ref_chain, k, b, 256, "relu")
     assert errs(h.cpu().numpy(), ref_chain)[1] <= 2e-3, "5-layer chain, Frobenius"
+    # the contract on the same stack: math 3xTF32, layer by layer and end to end (fp32-faithful, so the chain holds too)
+    from complexnn import _ops
+    h3 = dev(x)
+    for layer in layers:
+        h3 = _ops.conv_forward(h3, layer.kernel, layer.bias, 64, (3,), (1,), "same", "channels_last", (1,), "relu",
+                               math="3xtf32")
+    h3 = h3.reshape(B * T, 256)
+    for layer in dense:
+        h3 = _ops.dense_forward(h3, layer.kernel, layer.bias, 256, "relu", math="3xtf32")
+    check_contract(h3.cpu().numpy(), ref_chain, "cfg3 stack, 3xtf32, end to end")
 
 
 def _tc_cf_shapes():
@@ -477,6 +564,10 @@ def test_tensor_core_channels_first_random_shapes_vs_oracle(cnn, native_lib, sha
     yg = _ops.conv_forward(dev(x), Variable(kern), Variable(bias) if use_bias else None, F, k, ones, pad,
                            "channels_first", d, act, math="fp32", algo="general")
     check(yg.cpu().numpy(), ref, FP32_TOL, "general " + str(shape))
+    y3 = _ops.conv_forward(dev(x), Variable(kern), Variable(bias) if use_bias else None, F, k, ones, pad,
+                           "channels_first", d, act, math="3xtf32", algo="tensor")   # streamed hi | lo blocks: always fits
+    check_contract(y3.cpu().numpy(), ref, "3xtf32 " + str(shape))
+    check(y3.cpu().numpy(), ref, FP32_TOL, "3xtf32 " + str(shape))
 
 
 def test_baseline_config5_conv2d_slice_and_properties(cnn):
@@ -491,6 +582,8 @@ def test_baseline_config5_conv2d_slice_and_properties(cnn):
     n0 = _native.launch_count()
     y = layer(dev(xs))
     assert _native.launch_count() == n0 + 2            # sub-filter pre-pass + the fused kernel
+    y = layer(dev(xs))
+    assert _native.launch_count() == n0 + 3            # image cached per weight version: one launch
     k, b = layer.get_weights()
     assert k.shape == (3, 3, 64, 512)
     layer.set_weights([k, rng.normal(0, 0.1, 512).astype(np.float32)])
@@ -498,6 +591,11 @@ def test_baseline_config5_conv2d_slice_and_properties(cnn):
     y = layer(dev(xs))
     ref = O.qconv_forward(xs, k, b, 128, (1, 1), "same", "channels_first", (1, 1), "relu")
     check_tf32(y.cpu().numpy(), ref, O.qconv_abs_bound(xs, k, 128, (1, 1), "same", "channels_first", (1, 1)), "cfg5 slice")
+    from complexnn import _ops
+    y3 = _ops.conv_forward(dev(xs), layer.kernel, layer.bias, 128, (3, 3), (1, 1), "same", "channels_first", (1, 1), "relu",
+                           math="3xtf32", algo="tensor")
+    check_contract(y3.cpu().numpy(), ref, "cfg5 slice 3xtf32")
+    check(y3.cpu().numpy(), ref, FP32_TOL, "cfg5 slice 3xtf32")
     x = torch.randn(4, 256, 128, 128, device="cuda")
     yf = layer(x)
     assert tuple(yf.shape) == (4, 512, 128, 128)
@@ -562,6 +660,49 @@ def test_tensor_core_dgrad_conv1d_vs_oracle(cnn, name, xs, F, k, d, pad, act):
     check(gk.cpu().numpy(), rdk, 1e-4, "general dkernel")
 
 
+CF_BWD_CASES = [
+    # name, x shape (channels_first), F, k, d, pad, act
+    ("timit_inner_layer", (2, 128, 41, 64), 32, (3, 5), (1, 1), "same", "linear"),   # interspeech_model.py:51-61,116
+    ("cf_relu_3x3", (2, 128, 5, 64), 32, (3, 3), (1, 1), "same", "relu"),
+    ("cf_valid_d2", (1, 256, 9, 72), 64, (2, 3), (2, 1), "valid", "relu"),
+    ("cf_rank1", (3, 128, 132), 64, (4,), (1,), "same", "linear"),
+]
+
+
+@pytest.mark.parametrize("math", ["tf32", "3xtf32"])
+@pytest.mark.parametrize("name,xs,F,k,d,pad,act", CF_BWD_CASES, ids=[c[0] for c in CF_BWD_CASES])
+def test_tensor_core_dgrad_channels_first_vs_oracle(cnn, name, xs, F, k, d, pad, act, math):
+    """channels_first backward (what models/interspeech_model.py trains): dz / bias gradient in one channels_first pass,
+    data gradient = the channels_first tensor-core forward kernel on dz with the transposed, tap-flipped image and the
+    transposed sign table; the kernel gradient stays on the fp32 kernel."""
+    from complexnn import _native, _ops
+    from complexnn._layer import Variable
+    rank = len(k)
+    rng = np.random.default_rng(len(name))
+    in_q = xs[1] // 4
+    x = rng.normal(size=xs).astype(np.float32)
+    kern = (rng.normal(size=k + (in_q, 4 * F)) / np.sqrt(4 * in_q * np.prod(k))).astype(np.float32)
+    bias = rng.normal(0, 0.1, 4 * F).astype(np.float32)
+    ones = (1,) * rank
+    xd, kv, bv = dev(x), Variable(kern), Variable(bias)
+    y = _ops.conv_forward(xd, kv, bv, F, k, ones, pad, "channels_first", d, act, math="fp32", algo="general")
+    dy = rng.normal(size=tuple(y.shape)).astype(np.float32)
+    desc = _native.make_conv_desc(rank, xs[0], xs[2:], in_q, F, k, ones, d, pad, "channels_first", act, math=math)
+    a, b = ctypes.c_int32(-1), ctypes.c_int32(-1)
+    assert _native.lib().qnn_conv_backward_uses_tensor_cores(ctypes.byref(desc), ctypes.byref(a), ctypes.byref(b)) == 0
+    assert a.value == 1, "data gradient should run on the tensor cores"
+    dx, dk, db = _ops.conv_backward(xd, y, dev(dy), kv, True, F, k, ones, pad, "channels_first", d, act, math=math)
+    rdx, rdk, rdb = O.qconv_backward(x, kern, bias, F, ones, pad, "channels_first", d, act, dy)
+    if math == "3xtf32":
+        check_contract(dx.cpu().numpy(), rdx, "dx 3xtf32")
+        check(dx.cpu().numpy(), rdx, 1e-4, "dx 3xtf32")
+    else:
+        emax, efro = errs(dx.cpu().numpy(), rdx)
+        assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "dx: max-rel %.3e fro-rel %.3e" % (emax, efro)
+    check(dk.cpu().numpy(), rdk, 1e-4, "dkernel")
+    check(db.cpu().numpy(), rdb, 1e-4, "dbias")
+
+
 @pytest.mark.parametrize("rows,in_q,units,act", [(300, 64, 256, "relu"), (1000, 128, 64, "linear"), (77, 16, 512, "relu")])
 def test_tensor_core_dgrad_dense_vs_oracle(cnn, rows, in_q, units, act):
     from complexnn import _ops
@@ -601,10 +742,8 @@ def test_experimental_channels_last_conv2d_tensor_core(cnn, native_lib, shape):
     check_tf32(y.cpu().numpy(), ref, O.qconv_abs_bound(x, kern, F, (1, 1), pad, "channels_last", d), str(shape))
 
 
-@pytest.mark.skipif(os.environ.get("QNN_RUN_UNVALIDATED") != "1",
-                    reason="written after round 1's GPU budget was spent and never run on hardware: opt in with "
-                           "QNN_RUN_UNVALIDATED=1 (the CPU twin, test_timit_model_oracle_matches_the_reference_builder, runs)")
-def test_timit_model_on_gpu_matches_reference_golden(cnn, golden):
+@pytest.mark.parametrize("math", ["tf32", "3xtf32"])
+def test_timit_model_on_gpu_matches_reference_golden(cnn, golden, math):
     """BASELINE configs[2], literal reading: the reference's getTimitModel2D chain (QuaternionConv2D (3,5) channels_first +
     PReLU + MaxPooling2D + 3 x TimeDistributed(QuaternionDense(256)) + softmax) with the product kernels doing every
     quaternion layer, against the output the reference's own builder produced (tests/golden/timit_model.npz)."""
@@ -614,13 +753,16 @@ def test_timit_model_on_gpu_matches_reference_golden(cnn, golden):
 
     def conv(h, k, b, F):
         y = _ops.conv_forward(dev(np.ascontiguousarray(h, dtype=np.float32)), Variable(k), Variable(b), F, (3, 5), (1, 1),
-                              "same", "channels_first", (1, 1), "linear")
+                              "same", "channels_first", (1, 1), "linear", math=math)
         return y.cpu().numpy()
 
     def dense(h, k, b):
-        return _ops.dense_forward(dev(h), Variable(k), Variable(b), 256, "linear").cpu().numpy()
+        return _ops.dense_forward(dev(h), Variable(k), Variable(b), 256, "linear", math=math).cpu().numpy()
 
     g = golden.load("timit_model")
     pred = timit_oracle_forward(g, conv=conv, dense=dense)
     emax, efro = errs(pred, g["pred"])
-    assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "TIMIT chain: max-rel %.3e fro-rel %.3e" % (emax, efro)
+    if math == "3xtf32":
+        check_contract(pred, g["pred"], "TIMIT chain, 3xtf32")      # 9 layers deep and still inside the contract
+    else:
+        assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "TIMIT chain: max-rel %.3e fro-rel %.3e" % (emax, efro)

@@ -74,6 +74,9 @@ def test_stored_weight_layout():
                                                           "gamma_ii", "gamma_ij", "gamma_ik", "gamma_jj", "gamma_jk",
                                                           "gamma_kk", "bias"]
     assert n.gamma_rr.shape == (2 * 4,) and np.allclose(n.gamma_rr.numpy(), 1 / np.sqrt(2)) and not n.gamma_ri.numpy().any()
+    # the reference's own (odd) table, conv.py:238-251: gamma_jk gets the *diag* initialiser, gamma_kk the *off* one
+    assert np.allclose(n.gamma_jk.numpy(), 1 / np.sqrt(2)) and not n.gamma_kk.numpy().any()
+    assert np.allclose(n.gamma_ii.numpy(), 1 / np.sqrt(2)) and np.allclose(n.gamma_jj.numpy(), 1 / np.sqrt(2))
     nb = QuaternionDense(8, use_bias=False)
     nb.build((None, 12))
     assert nb.bias is None and len(nb.weights) == 1
@@ -199,7 +202,7 @@ def test_library_exports_every_declared_symbol(native_lib):
     raw = ctypes.CDLL(_native.LIB_PATH)
     for sym in declared:
         assert hasattr(raw, sym), sym
-    assert native_lib.qnn_abi_version() == 1
+    assert native_lib.qnn_abi_version() == 2
     assert native_lib.qnn_launch_count() == 0
 
 
@@ -279,9 +282,14 @@ def test_backward_kernel_selection_is_host_logic(native_lib):
     assert ask(mk(1, 256, (256,), 41, 64, (3,), (1,), (1,), "same", "channels_last", "relu")) == (0, 1)
     # cfg 2 (in_q = 40): dx needs a multiple of 16 "filters" in the transposed problem -> CUDA cores; dkernel on tensor cores
     assert ask(mk(1, 256, (256,), 40, 64, (3,), (1,), (1,), "same", "channels_last", "relu")) == (0, 1)
-    # strided, channels_first, rank 2, fp32 math, general algo: CUDA-core kernels
+    # strided, fp32 math, general algo: CUDA-core kernels
     assert ask(mk(1, 8, (64,), 64, 64, (3,), (2,), (1,), "same", "channels_last", "relu")) == (0, 0)
-    assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")) == (0, 0)
+    # channels_first rank 2 (what models/interspeech_model.py trains): the data gradient is the channels_first forward
+    # kernel on dz with the transposed, tap-flipped image; the kernel gradient has no channels_first tensor-core kernel yet
+    assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")) == (1, 0)
+    assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu", math="3xtf32")) == (1, 0)
+    # 3xTF32: data gradient on the tensor cores (three MMAs per block), kernel gradient on the fp32 kernel
+    assert ask(mk(1, 256, (256,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (1, 0)
     assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="fp32")) == (0, 0)
     assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", algo="general")) == (0, 0)
     # tanh has no fused derivative: the backward entry points refuse it, the query says "not on tensor cores"
@@ -295,3 +303,25 @@ def test_backward_kernel_selection_is_host_logic(native_lib):
     assert native_lib.qnn_dense_backward_uses_tensor_cores(325, 128, 128, ctypes.byref(a), ctypes.byref(b)) == 0
     assert (a.value, b.value) == (1, 1)          # DECODA QDNN layers 2 and 3
     assert native_lib.qnn_conv_backward_uses_tensor_cores(None, ctypes.byref(a), ctypes.byref(b)) == -1
+
+
+def test_variable_assign_after_parameter_and_device_move():
+    """set_weights after a training step (the mirror is then an autograd leaf) must not raise, and the
+    newest values must survive; `version` moves with every update (it keys the packed-weight caches)."""
+    import torch
+    from complexnn._layer import Variable
+    v = Variable(np.arange(6, dtype=np.float32).reshape(2, 3))
+    p = v.parameter("cpu")
+    assert p.requires_grad
+    v0 = v.version
+    v.assign(np.full((2, 3), 7.0, np.float32))               # used to raise: in-place copy into a leaf that requires grad
+    assert v.version == v0 + 1
+    np.testing.assert_array_equal(v.numpy(), np.full((2, 3), 7.0, np.float32))
+    np.testing.assert_array_equal(p.detach().numpy(), np.full((2, 3), 7.0, np.float32))
+    with torch.no_grad():
+        p.add_(1.0)                                          # an optimiser step on the mirror
+    v.mark_device_updated()
+    assert v.version == v0 + 2
+    np.testing.assert_array_equal(v.numpy(), np.full((2, 3), 8.0, np.float32))
+    with pytest.raises(ValueError):
+        v.assign(np.zeros((3, 2), np.float32))
