@@ -288,8 +288,10 @@ def test_backward_kernel_selection_is_host_logic(native_lib):
     # kernel on dz with the transposed, tap-flipped image; the kernel gradient has no channels_first tensor-core kernel yet
     assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")) == (1, 0)
     assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu", math="3xtf32")) == (1, 0)
-    # 3xTF32: data gradient on the tensor cores (three MMAs per block), kernel gradient on the fp32 kernel
-    assert ask(mk(1, 256, (256,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (1, 0)
+    # 3xTF32: data gradient on the tensor cores (three MMAs per block) when the doubled hi | lo image fits in shared
+    # memory (dense 64 -> 64 does, a 3-tap conv with in_q = 64 does not), kernel gradient on the fp32 kernel
+    assert ask(mk(1, 256, (256,), 64, 64, (1,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (1, 0)
+    assert ask(mk(1, 256, (256,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (0, 0)
     assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="fp32")) == (0, 0)
     assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", algo="general")) == (0, 0)
     # tanh has no fused derivative: the backward entry points refuse it, the query says "not on tensor cores"
