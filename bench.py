@@ -449,7 +449,12 @@ def time_workload(wl, steps, warmup, dist, min_sustain_s=0.25, sampler=None):
     import torch
     from complexnn import _native
     world = wl.world
-    train_multi = wl.bucket is not None and world > 1
+    # Training across ranks: by default the graph holds one step's kernels and the NCCL all-reduce of the bucket is
+    # launched after each replay (capturing it under torch's default "global" capture mode hung in round 1: NCCL's own
+    # threads make CUDA calls that mode forbids).  QNN_BENCH_NCCL_IN_GRAPH=1 captures the all-reduce too, in
+    # "thread_local" capture mode.
+    nccl_in_graph = os.environ.get("QNN_BENCH_NCCL_IN_GRAPH") == "1"
+    train_multi = wl.bucket is not None and world > 1 and not nccl_in_graph
     for i in range(max(warmup, 3)):
         wl.step(i)
         wl.exchange()
@@ -462,9 +467,11 @@ def time_workload(wl, steps, warmup, dist, min_sustain_s=0.25, sampler=None):
     l0 = _native.launch_count()
     with torch.cuda.stream(cap):
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph, stream=cap):
+        with torch.cuda.graph(graph, stream=cap, capture_error_mode="thread_local" if nccl_in_graph else "global"):
             for i in range(per_graph):
                 wl.step(i)
+                if nccl_in_graph:
+                    wl.exchange()
     launches_per_step = (_native.launch_count() - l0) / float(per_graph)
     torch.cuda.current_stream().wait_stream(cap)
 

@@ -95,8 +95,16 @@ typedef struct qnn_conv_desc {
 
 QNN_API int qnn_abi_version(void);
 QNN_API const char* qnn_last_error(void);
-/* 1 when the tensor-core kernel will be used for this descriptor under QNN_ALGO_AUTO, else 0. */
+/* 1 when a tensor-core kernel will be used for this descriptor's forward, else 0. */
 QNN_API int qnn_conv_uses_tensor_cores(const qnn_conv_desc* d);
+/* Which forward kernel the descriptor gets (host-only, needs no GPU): a qnn_kernel value, or a negative qnn_status. */
+typedef enum qnn_kernel {
+    QNN_KERNEL_GENERAL = 0,  /* CUDA cores, fp32: any rank / stride / dilation / layout                                 */
+    QNN_KERNEL_TC_ROWS = 1,  /* tcgen05, channels_last rank 1 / dense, resident sub-filters (qnn_hamilton_tc.cu)        */
+    QNN_KERNEL_TC_CF = 2,    /* tcgen05, channels_first rank 1 / 2, streamed sub-filters (qnn_hamilton_tc2d.cu)         */
+    QNN_KERNEL_SMALL_K = 3   /* CUDA cores, fp32, warp-shuffle tap reuse: in_q < 4 channels_last rank 1 (qnn_smallk.cu)  */
+} qnn_kernel;
+QNN_API int qnn_conv_forward_kernel(const qnn_conv_desc* d);
 QNN_API int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units);
 
 /* Which gradients of this layer qnn_*_backward computes on the tensor cores (1) or on the CUDA-core kernels (0) under

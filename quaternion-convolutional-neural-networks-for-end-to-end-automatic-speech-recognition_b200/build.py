@@ -6,7 +6,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libqnn_b200.so")
-SOURCES = ["qnn_api.cu", "qnn_general.cu", "qnn_hamilton_tc.cu", "qnn_hamilton_tc2d.cu", "qnn_wgrad_tc.cu"]
+SOURCES = ["qnn_api.cu", "qnn_general.cu", "qnn_smallk.cu", "qnn_hamilton_tc.cu", "qnn_hamilton_tc2d.cu", "qnn_wgrad_tc.cu"]
 HEADERS = ["qnn_common.h", "qnn_ptx.cuh", "qnn_tmap.h", os.path.join("..", "..", "include", "qnn.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-fvisibility=hidden", "-Xptxas", "-v"]

@@ -15,6 +15,7 @@ ALGO = {"auto": 0, "general": 1, "tensor": 2}
 QNN_E_INVALID, QNN_E_UNSUPPORTED = -1, -2
 ABI_VERSION = 2
 PACK_FORWARD, PACK_DGRAD = 0, 1
+KERNEL_GENERAL, KERNEL_TC_ROWS, KERNEL_TC_CF, KERNEL_SMALL_K = 0, 1, 2, 3
 
 
 class ConvDesc(ctypes.Structure):
@@ -33,6 +34,7 @@ SIGNATURES = {
     "qnn_last_error": (ctypes.c_char_p, []),
     "qnn_launch_count": (ctypes.c_uint64, []),
     "qnn_conv_uses_tensor_cores": (ctypes.c_int, [ctypes.POINTER(ConvDesc)]),
+    "qnn_conv_forward_kernel": (ctypes.c_int, [ctypes.POINTER(ConvDesc)]),
     "qnn_dense_uses_tensor_cores": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
     "qnn_conv_backward_uses_tensor_cores": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_int32),
                                                             ctypes.POINTER(ctypes.c_int32)]),

@@ -186,10 +186,13 @@ bool valid_algo(int a) { return a == QNN_ALGO_AUTO || a == QNN_ALGO_GENERAL || a
 bool al16(const void* a) { return (reinterpret_cast<uintptr_t>(a) & 15) == 0; }
 
 // Which kernel a forward problem gets: 0 = general (CUDA cores), 1 = channels_last rows (qnn_hamilton_tc.cu),
-// 2 = channels_first / rank 2 (qnn_hamilton_tc2d.cu).  Pointer alignment aside.
-enum { kKernGeneral = 0, kKernTc = 1, kKernTc2d = 2 };
+// 2 = channels_first / rank 2 (qnn_hamilton_tc2d.cu), 3 = small-K (CUDA cores with shuffle tap reuse, qnn_smallk.cu:
+// fp32 FMA, so it serves every math mode).  Pointer alignment aside.
+enum { kKernGeneral = 0, kKernTc = 1, kKernTc2d = 2, kKernSmallK = 3 };
 int forward_kernel(const Geom& g, int rank, int math, int algo) {
-    if (algo == QNN_ALGO_GENERAL || math == QNN_MATH_FP32) return kKernGeneral;
+    if (algo == QNN_ALGO_GENERAL) return kKernGeneral;
+    if (algo == QNN_ALGO_AUTO && smallk_plan(g, rank).ok) return kKernSmallK;
+    if (math == QNN_MATH_FP32) return kKernGeneral;
     const int x3 = math == QNN_MATH_3XTF32;
     if (tc_plan(g, rank, x3).ok) return kKernTc;
     if (tc2d_plan(g, rank, x3).ok) return kKernTc2d;
@@ -223,6 +226,13 @@ int run_forward(const Geom& g, int rank, int math, int algo, const float* x, con
         if (kern == kKernGeneral) kern = g.channels_first ? kKernTc2d : kKernTc;  // let the kernel's own plan report why not
     } else if (!aligned) {
         kern = kKernGeneral;
+    }
+    if (kern == kKernSmallK) {
+        if (!w) {
+            set_error("this problem runs on the small-K kernel, which needs the stored kernel (not only its packed image)");
+            return QNN_E_INVALID;
+        }
+        return smallk_forward(g, rank, x, w, bias, y, st);
     }
     if (kern == kKernGeneral) {
         if (!w) {
@@ -511,7 +521,7 @@ int forward_host(const Geom& g, int rank, int math, int algo, size_t nx, size_t 
     const int x3 = math == QNN_MATH_3XTF32;
     const int kern = forward_kernel(g, rank, math, algo);
     void* packed = nullptr;
-    if (kern != kKernGeneral) {
+    if (kern == kKernTc || kern == kKernTc2d) {
         const size_t pbytes = kern == kKernTc ? tc_packed_bytes(g, rank, x3) : tc2d_packed_bytes(g, rank, x3);
         bool fresh = false;
         rc = resident_packed(dev, w_idx, ((uint64_t)kern << 8) | (uint64_t)x3 | ((uint64_t)pbytes << 16), pbytes, st, &packed, &fresh);
@@ -668,7 +678,15 @@ int qnn_conv_uses_tensor_cores(const qnn_conv_desc* d) {
     Geom g;
     if (build_geom(d, &g)) return 0;
     if (!valid_math(d->math) || !valid_algo(d->algo) || empty_out(g)) return 0;
-    return forward_kernel(g, d->rank, d->math, d->algo) != kKernGeneral;
+    const int kern = forward_kernel(g, d->rank, d->math, d->algo);
+    return kern == kKernTc || kern == kKernTc2d;
+}
+
+int qnn_conv_forward_kernel(const qnn_conv_desc* d) {
+    Geom g;
+    if (build_geom(d, &g)) return QNN_E_INVALID;
+    if (!valid_math(d->math) || !valid_algo(d->algo)) return QNN_E_INVALID;
+    return empty_out(g) ? QNN_KERNEL_GENERAL : forward_kernel(g, d->rank, d->math, d->algo);
 }
 
 int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units) {
@@ -741,6 +759,7 @@ int packed_problem(const Geom& g, int rank, int math, int algo, int kind, Geom* 
     if (empty_out(g)) return QNN_OK;
     if (kind == QNN_PACK_FORWARD) {
         *kern = forward_kernel(g, rank, math, algo);
+        if (*kern == kKernSmallK) *kern = kKernGeneral;  // no packed form
     } else {
         int dxk = 0, dwk = 0;
         backward_selection(g, rank, math, algo, &dxk, &dwk);

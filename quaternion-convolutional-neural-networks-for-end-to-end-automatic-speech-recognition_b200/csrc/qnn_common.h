@@ -38,6 +38,16 @@ int general_forward(const Geom& g, const float* x, const float* w, const float* 
 int general_backward(const Geom& g, const float* x, const float* w, const float* y, const float* dy, float* dx, float* dw,
                      float* db, cudaStream_t st);
 
+// small-K forward (CUDA cores, warp-shuffle tap reuse): channels_last rank 1 / dense, stride 1, in_q < 4 (qnn_smallk.cu)
+struct SmallKPlan {
+    int ok;
+    int pc;  // output positions per warp run
+    size_t smem_bytes;
+    const char* why;
+};
+SmallKPlan smallk_plan(const Geom& g, int rank);
+int smallk_forward(const Geom& g, int rank, const float* x, const float* w, const float* bias, float* y, cudaStream_t st);
+
 // helper of the tensor-core backward path: dz = dy * act'(y) with the bias gradient folded in (either output may be
 // NULL); channels_last: rows x C, channels_first: [n][C][S] with S positions per channel
 int dz_bgrad(const float* y, const float* dy, float* dz, float* db, long long rows, int C, int relu, cudaStream_t st);

@@ -24,9 +24,9 @@
 //     which also clips ragged tiles.
 // Work item = (tile, filter tile of <= 64 filters); persistent CTAs stride over the items.
 //
-// Template parameter CL selects the channels_last rank-2 variant of the same main loop -- the x stage is a
-// 5-D box [8 q][4 components][128 + halo columns][1 row][1 sample] under the 128-byte swizzle (one 128-byte line per
-// position, read with 16-byte loads like qnn_hamilton_tc.cu), the epilogue stages [128 positions][32 channels] rows.
+// Template parameter CL selects the channels_last rank-2 variant of the same main loop -- the x stage is four 5-D boxes
+// (8 q, one component, 128 + halo columns, 1 row, 1 sample), dense [component][w][8 q] (no swizzle; read with 16-byte
+// loads whose order alternates between lanes), the epilogue stages [128 positions][32 channels] rows.
 // Warp roles and the TMEM plan are those of qnn_hamilton_tc.cu: warps 0-15 epilogue, 16-19 MMA issuers (one per output
 // component), 20-27 converters (two groups on alternate stages), 28 / 29 producers (x stages / sub-filter blocks); TMEM [0,256) accumulators, [256,512) eight A slots.
 #include <algorithm>
@@ -85,6 +85,7 @@ struct P2 {
     int xshift;      // the box starts xshift (0..3) columns left of the first tap: its start must be 16-byte aligned
     int x_stages, x_stage_bytes;
     int act, has_bias;
+    int comp_stride;       // channels_last: bytes between the component blocks of an x stage (wbox * 32 rounded up to 128)
     int handshake;         // KW >= A slots: converter groups hand over stage by stage (see the converter role)
     uint32_t b_blk_bytes;  // one B slot: 4 sub-filters x 2 k-groups x f_tile x 16 B (3xTF32: twice that, hi block | lo block)
 };
@@ -317,7 +318,10 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
     } else if (warp >= kWarpProd0) {
         // =========================== producers: warp 28 x stages (TMA), warp 29 sub-filter blocks (bulk copies) ===========================
         reg_dealloc<kRegsWg0>();
-        if (warp == kWarpProd0 && elect_one()) {
+        if (warp == kWarpProd0 && (CL ? (tid & 31) < 4 : elect_one())) {
+            // channels_first: one thread, one 4-D box per stage.  channels_last: lanes 0..3 load one component each (a box
+            // spanning the component axis would need a 32-byte inner row per line under a swizzle, or non-monotonic strides).
+            const int comp = CL ? (tid & 31) : 0;
             uint32_t xs = 0, xph = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const ItemPos ip = item_pos(p, item);
@@ -325,10 +329,10 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
                 for (int qc = 0; qc < p.n_qc; ++qc)
                     for (int kh = 0; kh < p.KH; ++kh) {
                         mbar_wait(&bars->x_empty[xs], xph ^ 1);
-                        mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)(32 * p.wbox * 4));
-                        if (CL)  // x[nb][H][W][4][Q]: box (8 q, 4 components, wbox columns, 1 row, 1 sample)
-                            tma_load_5d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], qc * 8, 0,
-                                        ip.w0 - p.pad_w, cy + kh * p.dh, ip.b);
+                        if (comp == 0) mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)(32 * p.wbox * 4));
+                        if (CL)  // x[nb][H][W][4][Q]: box (8 q, 1 component, wbox columns, 1 row, 1 sample) -> dense [w][8 q]
+                            tma_load_5d(x_s + (size_t)xs * p.x_stage_bytes + (size_t)comp * p.comp_stride, &tmx, &bars->x_full[xs],
+                                        qc * 8, comp, ip.w0 - p.pad_w, cy + kh * p.dh, ip.b);
                         else
                             tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], cx, cy + kh * p.dh, qc * 8, cb);
                         if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
@@ -393,40 +397,53 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
                     for (int tb = 0; tb < nb; ++tb) {
                         const uint32_t dst = t_a + lane_base + as_b * kSlotCols;
                         if (CL) {
-                            // one 128-byte line per position: [4 components][8 q], 16-byte chunks XORed with row % 8
+                            // stage = [component][w][8 q] fp32, un-swizzled: a thread's position holds 32 bytes per component.
+                            // Lanes are 32 bytes apart, so a quarter-warp's 16-byte loads of the SAME half would hit each
+                            // bank twice; lanes 4..7 of every eight read the other half first -> conflict-free.
                             const uint32_t row = (uint32_t)(r + (tap0 + tb) * p.dw);
-                            const uint8_t* xrow = x_s + (size_t)xs * p.x_stage_bytes + row * 128u;
-                            const uint32_t sw = row & 7u;
-                            if (X3) {
+                            const uint8_t* xrow = x_s + (size_t)xs * p.x_stage_bytes + row * 32u;
+                            const uint32_t comp_bytes = (uint32_t)p.comp_stride;
+                            const uint32_t flip = ((uint32_t)r >> 2) & 1u;
 #pragma unroll
-                                for (int g8 = 0; g8 < 4; ++g8) {
-                                    const uint4 v0 = *reinterpret_cast<const uint4*>(xrow + (((2 * g8) ^ sw) << 4));
-                                    const uint4 v1 = *reinterpret_cast<const uint4*>(xrow + (((2 * g8 + 1) ^ sw) << 4));
-                                    uint32_t hi[8], lo[8];
-                                    split_tf32(v0.x, hi[0], lo[0]);
-                                    split_tf32(v0.y, hi[1], lo[1]);
-                                    split_tf32(v0.z, hi[2], lo[2]);
-                                    split_tf32(v0.w, hi[3], lo[3]);
-                                    split_tf32(v1.x, hi[4], lo[4]);
-                                    split_tf32(v1.y, hi[5], lo[5]);
-                                    split_tf32(v1.z, hi[6], lo[6]);
-                                    split_tf32(v1.w, hi[7], lo[7]);
-                                    tmem_st8_nc(dst + g8 * 8, hi);
-                                    tmem_st8_nc(dst + 32 + g8 * 8, lo);
+                            for (int a2 = 0; a2 < 4; a2 += 2) {  // two components (16 columns) per store
+                                uint4 q4[2][2];
+#pragma unroll
+                                for (int aa = 0; aa < 2; ++aa) {
+                                    const uint8_t* xc = xrow + (a2 + aa) * comp_bytes;
+                                    const uint4 first = *reinterpret_cast<const uint4*>(xc + (flip << 4));
+                                    const uint4 second = *reinterpret_cast<const uint4*>(xc + ((flip ^ 1u) << 4));
+                                    q4[aa][0] = flip ? second : first;
+                                    q4[aa][1] = flip ? first : second;
                                 }
-                            } else {
+                                if (X3) {
 #pragma unroll
-                                for (int h = 0; h < 2; ++h) {
+                                    for (int aa = 0; aa < 2; ++aa) {
+                                        uint32_t hi[8], lo[8];
+                                        split_tf32(q4[aa][0].x, hi[0], lo[0]);
+                                        split_tf32(q4[aa][0].y, hi[1], lo[1]);
+                                        split_tf32(q4[aa][0].z, hi[2], lo[2]);
+                                        split_tf32(q4[aa][0].w, hi[3], lo[3]);
+                                        split_tf32(q4[aa][1].x, hi[4], lo[4]);
+                                        split_tf32(q4[aa][1].y, hi[5], lo[5]);
+                                        split_tf32(q4[aa][1].z, hi[6], lo[6]);
+                                        split_tf32(q4[aa][1].w, hi[7], lo[7]);
+                                        tmem_st8_nc(dst + (a2 + aa) * 8, hi);
+                                        tmem_st8_nc(dst + 32 + (a2 + aa) * 8, lo);
+                                    }
+                                } else {
                                     uint32_t u[16];
 #pragma unroll
-                                    for (int c4 = 0; c4 < 4; ++c4) {
-                                        const uint4 v = *reinterpret_cast<const uint4*>(xrow + (((h * 4 + c4) ^ sw) << 4));
-                                        u[4 * c4 + 0] = v.x + 0x1000u;
-                                        u[4 * c4 + 1] = v.y + 0x1000u;
-                                        u[4 * c4 + 2] = v.z + 0x1000u;
-                                        u[4 * c4 + 3] = v.w + 0x1000u;
+                                    for (int aa = 0; aa < 2; ++aa) {
+                                        u[8 * aa + 0] = q4[aa][0].x + 0x1000u;
+                                        u[8 * aa + 1] = q4[aa][0].y + 0x1000u;
+                                        u[8 * aa + 2] = q4[aa][0].z + 0x1000u;
+                                        u[8 * aa + 3] = q4[aa][0].w + 0x1000u;
+                                        u[8 * aa + 4] = q4[aa][1].x + 0x1000u;
+                                        u[8 * aa + 5] = q4[aa][1].y + 0x1000u;
+                                        u[8 * aa + 6] = q4[aa][1].z + 0x1000u;
+                                        u[8 * aa + 7] = q4[aa][1].w + 0x1000u;
                                     }
-                                    tmem_st16_nc(dst + h * 16, u);
+                                    tmem_st16_nc(dst + a2 * 8, u);
                                 }
                             }
                         } else {
@@ -601,7 +618,9 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3) {
     const int slots = x3 ? 4 : 8;
     const int f_tile = g.F % 64 == 0 ? 64 : 32;
     const size_t blk = (size_t)32 * f_tile * 4 * (x3 ? 2 : 1);
-    const size_t stage = ((size_t)32 * wbox * 4 + 1023) & ~size_t(1023);
+    // channels_last: four component blocks per stage, each starting on a 128-byte boundary (TMA destination alignment)
+    const size_t comp_stride = ((size_t)wbox * 32 + 127) & ~size_t(127);
+    const size_t stage = ((cl ? 4 * comp_stride : (size_t)32 * wbox * 4) + 1023) & ~size_t(1023);
     const size_t fixed = 1024 + slots * blk + 2 * kStagingBytes + (((size_t)g.F * 16 + 1023) & ~size_t(1023)) + 512;
     if (fixed + 2 * stage > kSmemLimit) return no("x stages do not fit in shared memory");
     pl.ok = 1;
@@ -695,6 +714,7 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
     p.has_bias = bias != nullptr;
     p.b_blk_bytes = (uint32_t)(32 * pl.f_tile * 4 * (x3 ? 2 : 1));
     p.handshake = p.KW >= (x3 ? 4 : 8) ? 1 : 0;
+    p.comp_stride = (int)(((size_t)pl.wbox * 32 + 127) & ~size_t(127));
 
     CUtensorMap tmx, tmy;
     if (g.channels_first) {
@@ -718,12 +738,14 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
             return QNN_E_CUDA;
         }
     } else {
-        // x[nb][H][W][4][Q]: box = (8 quaternion channels, 4 components, wbox positions, 1 row, 1 sample) -> one 128-byte
-        // line per position, 128B swizzle
+        // x[nb][H][W][4][Q]: box = (8 quaternion channels, ONE component, wbox positions, 1 row, 1 sample), NO swizzle; four
+        // such boxes (one per component, issued by four lanes) make a stage [component][w][8 q].  (One box over all four
+        // components would put a 32-byte inner row on a 128-byte line each under SWIZZLE_128B -- measured,
+        // profiles/r02_tma_swz_probe.log -- i.e. four times the shared memory, and 8-way bank conflicts without a swizzle.)
         const uint64_t dims[5] = {(uint64_t)Q, 4, (uint64_t)W, (uint64_t)H, (uint64_t)g.batch};
         const uint64_t str[4] = {(uint64_t)Q * 4, (uint64_t)Q * 16, (uint64_t)W * Q * 16, (uint64_t)H * W * Q * 16};
-        const uint32_t box[5] = {8, 4, (uint32_t)pl.wbox, 1, 1};
-        int e = make_tmap_f32(&tmx, x, 5, dims, str, box, true);
+        const uint32_t box[5] = {8, 1, (uint32_t)pl.wbox, 1, 1};
+        int e = make_tmap_f32(&tmx, x, 5, dims, str, box, false);
         if (e) {
             set_error("cuTensorMapEncodeTiled(x, channels_last rank 2) failed (%d)", e);
             return QNN_E_CUDA;

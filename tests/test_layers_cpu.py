@@ -252,6 +252,15 @@ def test_abi_argument_errors_and_kernel_selection(native_lib):
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cf_odd)) == 0      # row length % 4 != 0 -> general kernel
     cl2 = _native.make_conv_desc(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_last", "relu")
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cl2)) == 0         # channels_last rank 2 -> general kernel
+    # in_q < 4 (first DECODA layer, models/example_model.py:25): the small-K shuffle kernel in every math mode
+    dec = _native.make_conv_desc(1, 325, (250,), 1, 32, (3,), (1,), (1,), "same", "channels_last", "relu")
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(dec)) == _native.KERNEL_SMALL_K
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(dec)) == 0
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(cfg2)) == _native.KERNEL_TC_ROWS
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(cfg5)) == _native.KERNEL_TC_CF
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(s2)) == _native.KERNEL_GENERAL
+    dec.algo = _native.ALGO["general"]
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(dec)) == _native.KERNEL_GENERAL
     assert native_lib.qnn_allreduce_f32(None, 4, None) == -6                  # QNN_E_STATE: no communicator yet
     assert native_lib.qnn_comm_init(2, 2, None) == -1
 
