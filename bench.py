@@ -49,9 +49,19 @@ if RANK == 0:
     for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
         os.environ[_v] = str(len(ALL_CORES))
 
-# rank 0 prints ONE JSON line on stdout: keep NCCL's own "NCCL version ..." banner (NCCL_DEBUG=VERSION) off it
-if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"
+# rank 0 prints ONE JSON line on stdout.  NCCL prints its "NCCL version ..." banner on stdout at NCCL_DEBUG=VERSION and
+# WARN (the GPU boxes export VERSION) the first time ANY communicator is created in a process -- torch's or the
+# library's own: drop the variable unless the user asked for real diagnostics, and (belt and braces) point file
+# descriptor 1 of every rank at stderr for the whole run; the JSON line goes to the saved, real stdout.
+if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+    del os.environ["NCCL_DEBUG"]
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line):
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 import numpy as np
 
@@ -310,7 +320,7 @@ def run_reference(args, w):
             "cpu_baseline": {"value": val, "unit": "qMAC/s", "cores": len(ALL_CORES), "kind": "port", "sample": sample_desc},
             "e2e": {"value": val, "unit": "qMAC/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -449,11 +459,11 @@ def time_workload(wl, steps, warmup, dist, min_sustain_s=0.25, sampler=None):
     import torch
     from complexnn import _native
     world = wl.world
-    # Training across ranks: by default the graph holds one step's kernels and the NCCL all-reduce of the bucket is
-    # launched after each replay (capturing it under torch's default "global" capture mode hung in round 1: NCCL's own
-    # threads make CUDA calls that mode forbids).  QNN_BENCH_NCCL_IN_GRAPH=1 captures the all-reduce too, in
-    # "thread_local" capture mode.
-    nccl_in_graph = os.environ.get("QNN_BENCH_NCCL_IN_GRAPH") == "1"
+    # Training across ranks: the NCCL all-reduce of the gradient bucket is captured INTO the graph with the step's kernels,
+    # in "thread_local" capture mode (under torch's default "global" mode the capture hung in round 1: NCCL's own threads
+    # make CUDA calls that mode forbids while any thread captures).  QNN_BENCH_NCCL_IN_GRAPH=0: graph of one step's
+    # kernels, all-reduce launched after each replay.
+    nccl_in_graph = os.environ.get("QNN_BENCH_NCCL_IN_GRAPH", "1") == "1"
     train_multi = wl.bucket is not None and world > 1 and not nccl_in_graph
     for i in range(max(warmup, 3)):
         wl.step(i)
@@ -518,8 +528,9 @@ def time_workload(wl, steps, warmup, dist, min_sustain_s=0.25, sampler=None):
            "sustained_seconds": float(per.sum() * steps / 1e3), "launches_per_step": launches_per_step,
            "window": (t_win0, t_win1),
            "launch": ("CUDA graph of one step replayed %d times, all-reduce launched after each replay" % steps) if train_multi
-           else "ONE CUDA graph holding all %d steps (inputs rotate over %d sets); %d untimed steps queued right before "
-                "the timed replay" % (steps, wl.n_sets, pre * steps)}
+           else "ONE CUDA graph holding all %d steps%s (inputs rotate over %d sets); %d untimed steps queued right before "
+                "the timed replay" % (steps, " incl. the NCCL all-reduce of every step" if wl.bucket is not None and world > 1
+                                      else "", wl.n_sets, pre * steps)}
     return out
 
 
@@ -819,7 +830,7 @@ def run_ours(args, w):
         "cpu_baseline": cpu_block,
         "secondary": secondary,
     }
-    print(json.dumps(line))
+    emit(line)
     if sampler:
         sampler.stop()
     if world > 1:

@@ -53,6 +53,8 @@ int smallk_forward(const Geom& g, int rank, const float* x, const float* w, cons
 int dz_bgrad(const float* y, const float* dy, float* dz, float* db, long long rows, int C, int relu, cudaStream_t st);
 int dz_bgrad_cf(const float* y, const float* dy, float* dz, float* db, int batch, int C, long long S, int relu,
                 cudaStream_t st);
+// [batch][C][S] -> [batch][S][C]: channels_last scratch copies of channels_first tensors for the kernel gradient
+int cf_to_cl(const float* in, float* out, int batch, int C, long long S, cudaStream_t st);
 
 // tensor-core kernel (tcgen05 / TMEM / TMA): channels_last rows with taps along the innermost spatial axis.
 // `x3` selects 3xTF32 arithmetic (hi / lo operand split, three MMAs per block) instead of plain TF32.
@@ -103,6 +105,7 @@ struct Tc2dPlan {
     int f_tile, n_ftiles;
     int wbox;        // x box per channel: one row of 128 + halo positions (rounded up to 4)
     int xshift;      // columns the box starts left of the first tap (16-byte alignment of the TMA start)
+    int pad_rows;    // channels_first row length % 4 != 0: x / y go through row-padded scratch copies
     int x_stages;
     size_t x_stage_bytes, smem_bytes;
     size_t packed_bytes;  // packed kernel image (hi [+ lo] blocks per (filter tile, 8-channel chunk, tap))

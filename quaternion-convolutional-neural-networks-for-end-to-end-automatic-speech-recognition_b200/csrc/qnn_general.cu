@@ -357,6 +357,31 @@ __global__ void __launch_bounds__(256) k_dz_bgrad_cf(const float* __restrict__ y
     }
 }
 
+// [n][C][S] (channels_first) -> [n][S][C] (channels_last), 32 x 32 tiles through shared memory: both sides coalesced
+__global__ void __launch_bounds__(256) k_cf_to_cl(const float* __restrict__ in, float* __restrict__ out, int C, long long S,
+                                                  long long tiles_s, long long n_tiles) {
+    __shared__ float tile[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+    const long long tiles_c = (C + 31) / 32;
+    for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const long long ts = t % tiles_s, tc = (t / tiles_s) % tiles_c, n = t / (tiles_s * tiles_c);
+        const float* src = in + (size_t)n * C * S;
+        float* dst = out + (size_t)n * C * S;
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const long long c = tc * 32 + ty + j, sidx = ts * 32 + tx;
+            if (c < C && sidx < S) tile[ty + j][tx] = __ldg(src + c * S + sidx);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 32; j += 8) {
+            const long long sidx = ts * 32 + ty + j, c = tc * 32 + tx;
+            if (c < C && sidx < S) dst[sidx * C + c] = tile[tx][ty + j];
+        }
+        __syncthreads();
+    }
+}
+
 inline int grid_for(int64_t total, int block) {
     int64_t b = (total + block - 1) / block;
     const int64_t cap = 148LL * 16;
@@ -422,6 +447,19 @@ int dz_bgrad_cf(const float* y, const float* dy, float* dz, float* db, int batch
     e = cudaGetLastError();
     if (e != cudaSuccess) {
         set_error("dz/bgrad (channels_first) launch failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    return QNN_OK;
+}
+
+int cf_to_cl(const float* in, float* out, int batch, int C, long long S, cudaStream_t st) {
+    const long long tiles_s = (S + 31) / 32, n_tiles = (long long)batch * ((C + 31) / 32) * tiles_s;
+    if (n_tiles == 0) return QNN_OK;
+    k_cf_to_cl<<<(unsigned)std::min<long long>(n_tiles, 148LL * 16), 256, 0, st>>>(in, out, C, S, tiles_s, n_tiles);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("layout transposition launch failed: %s", cudaGetErrorString(e));
         return QNN_E_CUDA;
     }
     return QNN_OK;

@@ -871,8 +871,9 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
     p.has_bias = bias != nullptr;
     p.w_bytes = (uint32_t)pl.w_bytes;
     p.w_img_bytes = (uint32_t)(pl.w_bytes * (x3 ? 2 : 1));
-    // the image load is cut into at most 32 bulk copies (one per lane of the issuing warp), 2 KB granules
-    p.w_chunk = (uint32_t)(((p.w_img_bytes + 31) / 32 + 2047) & ~2047u);
+    // the image load is cut into at most 8 bulk copies (one per lane of the issuing warp; issuing a copy costs ~100 cycles
+    // whatever its size -- 30 copies of 4 KB kept the warp busy for ~2.9 k cycles before the TMEM allocation), 2 KB granules
+    p.w_chunk = (uint32_t)(((p.w_img_bytes + 7) / 8 + 2047) & ~2047u);
     p.handshake = p.taps >= (x3 ? 4 : 8) ? 1 : 0;
 
     CUtensorMap tmx, tmy;

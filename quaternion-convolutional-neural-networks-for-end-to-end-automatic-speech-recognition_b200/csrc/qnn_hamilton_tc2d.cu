@@ -30,7 +30,6 @@
 // Warp roles and the TMEM plan are those of qnn_hamilton_tc.cu: warps 0-15 epilogue, 16-19 MMA issuers (one per output
 // component), 20-27 converters (two groups on alternate stages), 28 / 29 producers (x stages / sub-filter blocks); TMEM [0,256) accumulators, [256,512) eight A slots.
 #include <algorithm>
-#include <cstdlib>
 #include <mutex>
 #include "qnn_common.h"
 #include "qnn_ptx.cuh"
@@ -562,6 +561,30 @@ __global__ void __launch_bounds__(256) k_pack_w2d(const float* __restrict__ w, f
     }
 }
 
+// [rows][w_in] -> [rows][w_out] (w_out > w_in: zero-filled tail = padding; w_out < w_in: tail dropped)
+__global__ void __launch_bounds__(256) k_copy_rows(const float* __restrict__ in, float* __restrict__ out, long long rows,
+                                                   int w_in, int w_out) {
+    const long long total = rows * w_out;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / w_out;
+        const int c = (int)(i - r * w_out);
+        out[i] = c < w_in ? __ldg(in + r * w_in + c) : 0.f;
+    }
+}
+
+int copy_rows(const float* in, float* out, long long rows, int w_in, int w_out, cudaStream_t st) {
+    const long long total = rows * w_out;
+    if (total == 0) return QNN_OK;
+    k_copy_rows<<<(unsigned)std::min<long long>((total + 255) / 256, 16LL * num_sms()), 256, 0, st>>>(in, out, rows, w_in, w_out);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("row padding launch failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    return QNN_OK;
+}
+
 typedef void (*Tc2dKernel)(const CUtensorMap, const CUtensorMap, const P2, const float*, const float*);
 
 unsigned long long* g_trace2d = nullptr;
@@ -594,20 +617,16 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3) {
         return pl;
     };
     const bool cl = !g.channels_first;
-    if (cl && rank != 2) return no("channels_last rank 1 / 3");  // rank 1 belongs to qnn_hamilton_tc.cu
-    if (cl) {
-        static const bool enabled = [] {
-            const char* e = getenv("QNN_EXPERIMENTAL_CL2D");
-            return e && e[0] == '1';
-        }();
-        if (!enabled) return no("channels_last rank 2 (variant under validation: QNN_EXPERIMENTAL_CL2D=1)");
-    }
+    // channels_last rank 1 is the one-row case of rank 2 (qnn_hamilton_tc.cu, which keeps the sub-filters resident, is
+    // preferred when its image fits in shared memory; this kernel streams them, so it takes what that one cannot)
     if (rank > 2) return no("rank 3");
     if (g.conj_w && g.act != QNN_ACT_LINEAR) return no("transposed sign table with an activation");
     if (g.s[1] != 1 || g.s[2] != 1) return no("stride != 1");
     if (g.in_q % 8) return no("in_q not a multiple of 8");
     if (g.F % 32) return no("filters not a multiple of 32");
-    if (!cl && (g.in_sp[2] % 4 || g.out_sp[2] % 4)) return no("row length not a multiple of 4 (TMA stride alignment)");
+    // channels_first rows whose length is not a multiple of 4 (TMA strides must be multiples of 16 bytes; the reference's
+    // TIMIT model has a free time axis, models/interspeech_model.py:81) run on row-padded scratch copies of x and y
+    pl.pad_rows = (!cl && (g.in_sp[2] % 4 || g.out_sp[2] % 4)) ? 1 : 0;
     if (g.out_sp[2] < 1 || g.out_sp[1] < 1 || g.batch < 1) return no("empty problem");
     // channels_first: un-swizzled TMA boxes must start on a 16-byte boundary of the innermost axis (measured: an odd start
     // column is an illegal instruction, profiles/r01_tma_box_probe.log), so the box starts up to 3 columns early.
@@ -679,6 +698,23 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
     if (!pl.ok) {
         set_error("channels_first tensor-core kernel does not take this shape: %s", pl.why);
         return QNN_E_UNSUPPORTED;
+    }
+    if (pl.pad_rows) {
+        // ragged rows: x -> row-padded copy, kernel on the padded geometry (the extra input columns are zeros = the
+        // convolution's own padding, the extra output columns are dropped), y <- un-padded copy
+        Geom gp = g;
+        gp.in_sp[2] = (g.in_sp[2] + 3) & ~3;
+        gp.out_sp[2] = (g.out_sp[2] + 3) & ~3;
+        const long long rows_x = (long long)g.batch * 4 * g.in_q * g.in_sp[1], rows_y = (long long)g.batch * 4 * g.F * g.out_sp[1];
+        float *xp = nullptr, *yp = nullptr;
+        int rc = stream_scratch_alloc(reinterpret_cast<void**>(&xp), (size_t)rows_x * gp.in_sp[2] * sizeof(float), st);
+        if (!rc) rc = stream_scratch_alloc(reinterpret_cast<void**>(&yp), (size_t)rows_y * gp.out_sp[2] * sizeof(float), st);
+        if (!rc) rc = copy_rows(x, xp, rows_x, g.in_sp[2], gp.in_sp[2], st);
+        if (!rc) rc = tc2d_forward_packed(gp, rank, x3, xp, packed, bias, yp, st);
+        if (!rc) rc = copy_rows(yp, y, rows_y, gp.out_sp[2], g.out_sp[2], st);
+        if (xp) cudaFreeAsync(xp, st);
+        if (yp) cudaFreeAsync(yp, st);
+        return rc;
     }
     if ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y) | reinterpret_cast<uintptr_t>(packed)) & 15) {
         set_error("tensor-core kernel needs 16-byte aligned x, packed kernel and y");

@@ -53,25 +53,34 @@ struct Gather<Q, 4 * Q> {
     __device__ static __forceinline__ void run(const float4&, int, float (&)[4 * Q]) {}
 };
 
-template <int Q, int ACT>
+// TAPS > 0: the lane's taps * Q * 4 sub-filter weights live in registers for the whole run (ncu on the first version:
+// the kernel is issue-bound, 181 instructions per position, a third of them shared-memory weight loads and sign
+// multiplies); TAPS == 0: any tap count, weights re-read from shared memory per position.
+template <int Q, int TAPS>
 __global__ void __launch_bounds__(kWarps * 32) k_smallk_fwd(const SmallK p, const float* __restrict__ x,
                                                             const float* __restrict__ w, const float* __restrict__ bias,
                                                             float* __restrict__ y) {
     extern __shared__ float smem[];
-    float* w_s = smem;                                   // [tap][q][c][F], as stored
-    float* b_s = smem + (size_t)p.taps * Q * 4 * p.F;    // [c][F]
-    const int n_w = p.taps * Q * 4 * p.F;
-    for (int i = threadIdx.x; i < n_w; i += blockDim.x) w_s[i] = __ldg(w + i);
-    for (int i = threadIdx.x; i < 4 * p.F; i += blockDim.x) b_s[i] = p.has_bias ? __ldg(bias + i) : 0.f;
+    float* w_s = smem;                                   // [tap][q][c][F], as stored, i / j / k already carrying the
+    float* b_s = smem + (size_t)p.taps * Q * 4 * p.F;    // dense-convention sign;  bias [c][F]
+    const int n_w = p.taps * Q * 4 * p.F, F = p.F;
+    // dense convention y = conj(W) (x) x (complexnn/dense.py:139-143): the imaginary sub-filters enter negated
+    for (int i = threadIdx.x; i < n_w; i += blockDim.x) {
+        const float v = __ldg(w + i);
+        w_s[i] = (p.conj_w && ((i / F) & 3)) ? -v : v;
+    }
+    for (int i = threadIdx.x; i < 4 * F; i += blockDim.x) b_s[i] = p.has_bias ? __ldg(bias + i) : 0.f;
     __syncthreads();
 
     constexpr int C = 4 * Q;
+    constexpr int NT = TAPS > 0 ? TAPS : 1;
     const int lane = threadIdx.x & 31;
     const long long warp0 = (long long)blockIdx.x * kWarps + (threadIdx.x >> 5), n_warps = (long long)gridDim.x * kWarps;
-    const int F = p.F;
-    const float cs = p.conj_w ? -1.f : 1.f;  // dense convention y = conj(W) (x) x (complexnn/dense.py:139-143)
+    const bool relu = p.act == QNN_ACT_RELU, generic_act = p.act != QNN_ACT_RELU && p.act != QNN_ACT_LINEAR;
     // this lane's slice of the window: floats [4*lane, 4*lane + 4) = channels wch..wch+3 of position woff (C % 4 == 0)
     const int woff = (4 * lane) / C, wch = (4 * lane) % C;
+    int fg_loaded = -1;
+    float wreg[NT * Q][4];
     for (long long task = warp0; task < p.n_tasks; task += n_warps) {
         const int fg = (int)(task % p.n_fg);
         const long long t2 = task / p.n_fg;
@@ -84,47 +93,70 @@ __global__ void __launch_bounds__(kWarps * 32) k_smallk_fwd(const SmallK p, cons
         const int f = fg * 32 + lane;
         const bool fv = f < F;
         const int fc = fv ? f : F - 1;
+        if (TAPS > 0 && fg != fg_loaded) {  // (warp-uniform) this lane's filter changed: reload its weights
+#pragma unroll
+            for (int i = 0; i < NT * Q; ++i)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) wreg[i][c] = w_s[((size_t)i * 4 + c) * F + fc];
+            fg_loaded = fg;
+        }
         const float b0 = b_s[fc], b1 = b_s[F + fc], b2 = b_s[2 * F + fc], b3 = b_s[3 * F + fc];
         const int n_pos = min(p.pc, p.Lo - t0);
         float* o = y + ((size_t)n * p.Lo + t0) * 4 * F + f;
         for (int j = 0; j < n_pos; ++j, o += 4 * F) {
             float yr = b0, yi = b1, yj = b2, yk = b3;
-            for (int tap = 0; tap < p.taps; ++tap) {
-                float xv[C];
-                Gather<Q, 0>::run(v, (j + tap * p.dil) * Q, xv);   // the position's first float4 is in lane position * C / 4
-                const float* wt = w_s + (size_t)tap * Q * 4 * F + fc;
+            auto qmac = [&](const float (&xv)[C], int q, float wr, float wi, float wj, float wk) {
+                const float xr = xv[q], xi = xv[Q + q], xj = xv[2 * Q + q], xk = xv[3 * Q + q];
+                // y += w (x) x  (Hamilton product, weight on the left: complexnn/conv.py:327-331)
+                yr += xr * wr - xi * wi - xj * wj - xk * wk;
+                yi += xr * wi + xi * wr - xj * wk + xk * wj;
+                yj += xr * wj + xi * wk + xj * wr - xk * wi;
+                yk += xr * wk - xi * wj + xj * wi + xk * wr;
+            };
+            if (TAPS > 0) {
 #pragma unroll
-                for (int q = 0; q < Q; ++q) {
-                    const float xr = xv[q], xi = xv[Q + q], xj = xv[2 * Q + q], xk = xv[3 * Q + q];
-                    const float* wq = wt + (size_t)q * 4 * F;
-                    const float wr = wq[0], wi = cs * wq[F], wj = cs * wq[2 * F], wk = cs * wq[3 * F];
-                    // y += w (x) x  (Hamilton product, weight on the left: complexnn/conv.py:327-331)
-                    yr += xr * wr - xi * wi - xj * wj - xk * wk;
-                    yi += xr * wi + xi * wr - xj * wk + xk * wj;
-                    yj += xr * wj + xi * wk + xj * wr - xk * wi;
-                    yk += xr * wk - xi * wj + xj * wi + xk * wr;
+                for (int tap = 0; tap < NT; ++tap) {
+                    float xv[C];
+                    Gather<Q, 0>::run(v, (j + tap * p.dil) * Q, xv);  // the position's first float4 is in lane position * C / 4
+#pragma unroll
+                    for (int q = 0; q < Q; ++q)
+                        qmac(xv, q, wreg[tap * Q + q][0], wreg[tap * Q + q][1], wreg[tap * Q + q][2], wreg[tap * Q + q][3]);
+                }
+            } else {
+                for (int tap = 0; tap < p.taps; ++tap) {
+                    float xv[C];
+                    Gather<Q, 0>::run(v, (j + tap * p.dil) * Q, xv);
+                    const float* wt = w_s + (size_t)tap * Q * 4 * F + fc;
+#pragma unroll
+                    for (int q = 0; q < Q; ++q) {
+                        const float* wq = wt + (size_t)q * 4 * F;
+                        qmac(xv, q, wq[0], wq[F], wq[2 * F], wq[3 * F]);
+                    }
                 }
             }
-            if (fv) {
-                if (ACT == 0) {
-                    o[0] = yr, o[F] = yi, o[2 * F] = yj, o[3 * F] = yk;
-                } else if (ACT == 1) {
-                    o[0] = fmaxf(yr, 0.f), o[F] = fmaxf(yi, 0.f), o[2 * F] = fmaxf(yj, 0.f), o[3 * F] = fmaxf(yk, 0.f);
-                } else {
-                    o[0] = act_apply(yr, p.act), o[F] = act_apply(yi, p.act), o[2 * F] = act_apply(yj, p.act),
-                    o[3 * F] = act_apply(yk, p.act);
-                }
+            if (relu) {
+                yr = fmaxf(yr, 0.f), yi = fmaxf(yi, 0.f), yj = fmaxf(yj, 0.f), yk = fmaxf(yk, 0.f);
+            } else if (generic_act) {
+                yr = act_apply(yr, p.act), yi = act_apply(yi, p.act), yj = act_apply(yj, p.act), yk = act_apply(yk, p.act);
             }
+            if (fv) o[0] = yr, o[F] = yi, o[2 * F] = yj, o[3 * F] = yk;
         }
     }
 }
 
 typedef void (*SmallKKernel)(const SmallK, const float*, const float*, const float*, float*);
 template <int Q>
-SmallKKernel pick_q(int act) {
-    return act == QNN_ACT_LINEAR ? k_smallk_fwd<Q, 0> : act == QNN_ACT_RELU ? k_smallk_fwd<Q, 1> : k_smallk_fwd<Q, 2>;
+SmallKKernel pick_q(int taps) {
+    switch (taps) {
+        case 1: return k_smallk_fwd<Q, 1>;
+        case 2: return k_smallk_fwd<Q, 2>;
+        case 3: return k_smallk_fwd<Q, 3>;
+        case 4: return k_smallk_fwd<Q, 4>;
+        case 5: return k_smallk_fwd<Q, 5>;
+        default: return k_smallk_fwd<Q, 0>;
+    }
 }
-SmallKKernel pick_kernel(int in_q, int act) { return in_q == 1 ? pick_q<1>(act) : in_q == 2 ? pick_q<2>(act) : pick_q<3>(act); }
+SmallKKernel pick_kernel(int in_q, int taps) { return in_q == 1 ? pick_q<1>(taps) : in_q == 2 ? pick_q<2>(taps) : pick_q<3>(taps); }
 
 }  // namespace
 
@@ -179,7 +211,7 @@ int smallk_forward(const Geom& g, int rank, const float* x, const float* w, cons
     p.act = g.act;
     p.conj_w = g.conj_w;
     p.has_bias = bias != nullptr;
-    SmallKKernel kern = pick_kernel(g.in_q, g.act);
+    SmallKKernel kern = pick_kernel(g.in_q, g.k[2]);
     if (pl.smem_bytes > 48 * 1024)
         if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)pl.smem_bytes)) return rc;
     // persistent warps: a multiple of the SM count, enough resident warps to cover the load latency, never more blocks

@@ -18,6 +18,10 @@
 //       walks its share of the position sub-tiles; CTAs that own different combinations walk the same sub-tiles at the
 //       same time, so x / dz come from HBM once.  At the end every CTA adds its partial sums into dW with 16-byte
 //       vector reductions (red.global.add.v4.f32).
+// Rank 2 (channels_last): one launch per kernel ROW kh -- for a fixed kh the problem is the rank-1 one over "sequences"
+// (sample, output row ho) whose input sequence is image row ho + kh*dh - pad_h (TMA zero-fills rows outside the image),
+// taps = the kernel columns; dz is shared by the launches, the launch writes dW[kh].  channels_first tensors are
+// transposed to channels_last scratch copies first (qnn_api.cu).
 // Warps: 0-15 packers then epilogue, 16-19 MMA issuers (one per D_c), 20-27 converters (two groups on alternate
 // k-steps), 28 x producer.  TMEM: [0,256) the four accumulators, [256,512) eight A slots.
 #include <algorithm>
@@ -69,6 +73,7 @@ struct WP {
     int in_q, F, f_tile, R;      // in_q as the kernel sees x (padded to 4); R = taps * in_q rows
     int in_q_out;                // the layer's real in_q: rows with q >= in_q_out are padding and are not written
     int Lo;
+    int Ho, h_off;               // rank 2: sequence s = (sample n, output row ho) reads input row ho + h_off (zero when outside)
     int rows, x_stages, x_stage_bytes;
     uint32_t b_stage_bytes;
 };
@@ -170,11 +175,12 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
             uint32_t xs = 0, xph = 0;
             for (int i = 0; i < my_units; ++i) {
                 const int unit = cgroup + i * n_groups;
-                const int n = unit / p.units_per_seq, t0 = (unit - n * p.units_per_seq) * kSub;
+                const int seq = unit / p.units_per_seq, t0 = (unit - seq * p.units_per_seq) * kSub;
+                const int n = seq / p.Ho, ho = seq - n * p.Ho;
                 mbar_wait(&bars->x_empty[xs], xph ^ 1);
                 if (i < 24) trace(p, 8 + 8 * i + 6);
                 mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)(p.rows * 4 * p.in_q * 4));
-                tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], 0, 0, t0 - p.pad_lo, n);
+                tma_load_5d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], 0, 0, t0 - p.pad_lo, ho + p.h_off, n);
                 if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
             }
         }
@@ -390,14 +396,15 @@ WgradPlan wgrad_plan(const Geom& g, int rank, int x3) {
         return pl;
     };
     if (x3) return no("3xTF32 kernel gradient runs on the fp32 CUDA-core kernel");
-    if (g.channels_first) return no("channels_first layout");
-    if (rank != 1) return no("rank > 1");
-    if (g.s[2] != 1) return no("stride != 1");
+    // channels_first: the caller transposes x and dz to channels_last scratch copies (run_backward); rank 2: one launch
+    // per kernel row
+    if (rank > 2) return no("rank 3");
+    if (g.s[1] != 1 || g.s[2] != 1) return no("stride != 1");
     if (g.in_q < 4) return no("fewer than 4 quaternion input channels");
     const int xq = (g.in_q + 3) & ~3;  // in_q % 4 != 0: channel-padding pre-pass (TMA alignment of the component blocks)
     if (xq > 256) return no("more than 256 quaternion input channels (TMA box limit)");
     if (g.F % 16) return no("filters not a multiple of 16");
-    if (g.out_sp[2] < 1 || g.batch < 1) return no("empty problem");
+    if (g.out_sp[2] < 1 || g.out_sp[1] < 1 || g.batch < 1) return no("empty problem");
     const int taps = g.k[2];
     const int rows = kSub + (taps - 1) * g.d[2];
     if (rows > 256) return no("halo exceeds the 256-row TMA box");
@@ -424,7 +431,8 @@ WgradPlan wgrad_plan(const Geom& g, int rank, int x3) {
     return pl;
 }
 
-// dw (stored-kernel shape [taps][in_q][4][F]) is OVERWRITTEN.  dz = dy * act'(y), fp32, [batch][Lo][4F].
+// dw (stored-kernel shape [KH][KW][in_q][4][F]) is OVERWRITTEN.  x and dz are CHANNELS_LAST here whatever g.channels_first
+// says (the caller hands over transposed copies): x [batch][H][W][4 in_q], dz = dy * act'(y) [batch][Ho][Wo][4F], fp32.
 int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, float* dw, cudaStream_t st) {
     const WgradPlan pl = wgrad_plan(g, rank, x3);
     if (!pl.ok) {
@@ -435,8 +443,8 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
         set_error("tensor-core kernel gradient needs 16-byte aligned x, dz and dkernel");
         return QNN_E_UNSUPPORTED;
     }
-    const int L = g.in_sp[2], Lo = g.out_sp[2], taps = g.k[2];
-    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)taps * g.in_q * 4 * g.F * sizeof(float), st);
+    const int H = g.in_sp[1], L = g.in_sp[2], Ho = g.out_sp[1], Lo = g.out_sp[2], KH = g.k[1], taps = g.k[2];
+    cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)KH * taps * g.in_q * 4 * g.F * sizeof(float), st);
     if (e != cudaSuccess) {
         set_error("dkernel memset failed: %s", cudaGetErrorString(e));
         return QNN_E_CUDA;
@@ -444,7 +452,7 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
     const int xq = (g.in_q + 3) & ~3;
     float* xp = nullptr;
     if (pl.pad_x) {
-        const long long rows = (long long)g.batch * L;
+        const long long rows = (long long)g.batch * H * L;
         int rc = stream_scratch_alloc(reinterpret_cast<void**>(&xp), (size_t)rows * 4 * xq * sizeof(float), st);
         if (!rc) rc = pad_x_channels(x, xp, rows, g.in_q, xq, st);
         if (rc) {
@@ -460,7 +468,7 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
     } free_xp{xp, st};
     WP p{};
     p.units_per_seq = (Lo + kSub - 1) / kSub;
-    const long long nu = (long long)g.batch * p.units_per_seq;
+    const long long nu = (long long)g.batch * Ho * p.units_per_seq;
     if (nu > 0x7fffffffLL) {
         set_error("too many position sub-tiles");
         return QNN_E_UNSUPPORTED;
@@ -477,17 +485,18 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
     p.f_tile = pl.f_tile;
     p.R = taps * xq;
     p.Lo = Lo;
+    p.Ho = Ho;
     p.rows = pl.rows;
     p.x_stages = pl.x_stages;
     p.x_stage_bytes = (int)pl.x_stage_bytes;
     p.b_stage_bytes = (uint32_t)(4 * 8 * pl.f_tile * 16);
     CUtensorMap tmx;
     {
-        // x[nb][L][4][in_q]: one box = (all in_q channels, the 4 components, 32 + halo rows, one sample), no swizzle
-        const uint64_t dims[4] = {(uint64_t)xq, 4, (uint64_t)L, (uint64_t)g.batch};
-        const uint64_t str[3] = {(uint64_t)xq * 4, (uint64_t)xq * 16, (uint64_t)L * xq * 16};
-        const uint32_t box[4] = {(uint32_t)xq, 4, (uint32_t)pl.rows, 1};
-        int rc = make_tmap_f32(&tmx, x, 4, dims, str, box, false);
+        // x[nb][H][L][4][in_q]: one box = (all in_q channels, the 4 components, 32 + halo columns, one row, one sample), no swizzle
+        const uint64_t dims[5] = {(uint64_t)xq, 4, (uint64_t)L, (uint64_t)H, (uint64_t)g.batch};
+        const uint64_t str[4] = {(uint64_t)xq * 4, (uint64_t)xq * 16, (uint64_t)L * xq * 16, (uint64_t)H * L * xq * 16};
+        const uint32_t box[5] = {(uint32_t)xq, 4, (uint32_t)pl.rows, 1, 1};
+        int rc = make_tmap_f32(&tmx, x, 5, dims, str, box, false);
         if (rc) {
             set_error("cuTensorMapEncodeTiled(x, wgrad) failed (%d)", rc);
             return QNN_E_CUDA;
@@ -499,22 +508,25 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
     int groups = std::min(num_sms() / p.n_combos, p.n_units);
     if (groups < 1) groups = 1;
     p.trace = (g_trace_w && g_trace_w_bytes >= (size_t)groups * p.n_combos * kTraceSlots * 8) ? g_trace_w : nullptr;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(groups * p.n_combos);
-    cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = pl.smem_bytes;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    e = cudaLaunchKernelEx(&cfg, kern, tmx, p, dz, dw);
-    count_launch();
-    if (e == cudaSuccess) e = cudaGetLastError();
-    if (e != cudaSuccess) {
-        set_error("tensor-core kernel gradient launch failed: %s", cudaGetErrorString(e));
-        return QNN_E_CUDA;
+    for (int kh = 0; kh < KH; ++kh) {  // one launch per kernel row (rank 1: one launch)
+        p.h_off = kh * g.d[1] - g.pad_lo[1];
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(groups * p.n_combos);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = pl.smem_bytes;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        e = cudaLaunchKernelEx(&cfg, kern, tmx, p, dz, dw + (size_t)kh * taps * g.in_q * 4 * g.F);
+        count_launch();
+        if (e == cudaSuccess) e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_error("tensor-core kernel gradient launch failed: %s", cudaGetErrorString(e));
+            return QNN_E_CUDA;
+        }
     }
     return QNN_OK;
 }

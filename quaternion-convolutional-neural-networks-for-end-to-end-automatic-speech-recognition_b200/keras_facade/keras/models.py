@@ -24,10 +24,11 @@ class _QuaternionOp(torch.autograd.Function):
     def forward(ctx, x, kernel, bias, layer, act_name):
         x = x.contiguous()
         if isinstance(layer, QuaternionDense):
-            y = _ops.dense_forward(x, layer.kernel, layer.bias, layer.units, act_name)
+            y = _ops.dense_forward(x, layer.kernel, layer.bias, layer.units, act_name, packed=layer._packed_kernels())
         else:
             y = _ops.conv_forward(x, layer.kernel, layer.bias, layer.filters, layer.kernel_size, layer.strides,
-                                  layer.padding, layer.data_format, layer.dilation_rate, act_name)
+                                  layer.padding, layer.data_format, layer.dilation_rate, act_name,
+                                  packed=layer._packed_kernels())
         ctx.layer, ctx.act_name = layer, act_name
         ctx.save_for_backward(x, y)
         return y
@@ -38,11 +39,12 @@ class _QuaternionOp(torch.autograd.Function):
         layer, dy = ctx.layer, dy.contiguous()
         if isinstance(layer, QuaternionDense):
             dx, dk, db = _ops.dense_backward(x, y, dy, layer.kernel, layer.bias is not None, layer.units, ctx.act_name,
-                                             need_dx=ctx.needs_input_grad[0])
+                                             need_dx=ctx.needs_input_grad[0], packed=layer._packed_kernels())
         else:
             dx, dk, db = _ops.conv_backward(x, y, dy, layer.kernel, layer.bias is not None, layer.filters,
                                             layer.kernel_size, layer.strides, layer.padding, layer.data_format,
-                                            layer.dilation_rate, ctx.act_name, need_dx=ctx.needs_input_grad[0])
+                                            layer.dilation_rate, ctx.act_name, need_dx=ctx.needs_input_grad[0],
+                                            packed=layer._packed_kernels())
         return dx, dk, db, None, None
 
 
@@ -186,6 +188,7 @@ class Model(object):
             pass
         h = History()
         h.history = history
+        self.history = h          # Keras keeps the last History on the model
         return h
 
     # ------------------------------------------------------------------------------------------------ bookkeeping

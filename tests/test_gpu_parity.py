@@ -589,7 +589,7 @@ def _tc_cf_shapes():
         k = tuple(int(v) for v in rng.integers(1, 5, size=rank))
         d = tuple(int(v) for v in rng.integers(1, 3, size=rank))
         pad = str(rng.choice(["same", "valid"]))
-        W = int(rng.choice([4, 40, 64, 128, 132, 200, 260]))
+        W = int(rng.choice([4, 40, 41, 64, 128, 131, 132, 200, 257, 260]))     # ragged rows (% 4 != 0): padded scratch copies
         sp = (W,) if rank == 1 else (int(rng.choice([1, 3, 7, 12])), W)
         if pad == "valid":
             sp = tuple(max(n, (kk - 1) * dd + 2) for n, kk, dd in zip(sp, k, d))
@@ -721,6 +721,7 @@ CF_BWD_CASES = [
     ("cf_relu_3x3", (2, 128, 5, 64), 32, (3, 3), (1, 1), "same", "relu"),
     ("cf_valid_d2", (1, 256, 9, 72), 64, (2, 5), (2, 1), "valid", "relu"),     # rows of 72 in, 68 out: both multiples of 4
     ("cf_rank1", (3, 128, 132), 64, (4,), (1,), "same", "linear"),
+    ("timit_ragged_T", (2, 128, 41, 77), 32, (3, 5), (1, 1), "same", "linear"),      # free time axis: T = 77
 ]
 
 
@@ -754,7 +755,44 @@ def test_tensor_core_dgrad_channels_first_vs_oracle(cnn, name, xs, F, k, d, pad,
     else:
         emax, efro = errs(dx.cpu().numpy(), rdx)
         assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "dx: max-rel %.3e fro-rel %.3e" % (emax, efro)
-    check(dk.cpu().numpy(), rdk, 1e-4, "dkernel")
+    if math == "3xtf32":
+        assert b.value == 0                      # 3xTF32: kernel gradient on the fp32 kernel
+        check(dk.cpu().numpy(), rdk, 1e-4, "dkernel")
+    else:
+        assert b.value == 1, "kernel gradient should run on the tensor cores (per-kernel-row launches, transposed copies)"
+        emax, efro = errs(dk.cpu().numpy(), rdk)
+        assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "dkernel: max-rel %.3e fro-rel %.3e" % (emax, efro)
+    check(db.cpu().numpy(), rdb, 1e-4, "dbias")
+
+
+@pytest.mark.parametrize("name,xs,F,k,d,pad,act", [
+    ("cl2_3x3_relu", (2, 6, 70, 128), 32, (3, 3), (1, 1), "same", "relu"),
+    ("cl2_valid_d2", (1, 9, 40, 64), 64, (2, 3), (2, 1), "valid", "linear"),
+    ("cl2_ragged_q", (2, 5, 33, 20), 16, (3, 2), (1, 1), "same", "relu"),          # in_q = 5: channel-padding pre-pass
+], ids=lambda v: v if isinstance(v, str) else None)
+def test_tensor_core_backward_channels_last_conv2d_vs_oracle(cnn, name, xs, F, k, d, pad, act):
+    """QuaternionConv2D channels_last backward: kernel gradient = one position-contraction launch per kernel row, data
+    gradient = the streamed-sub-filter kernel on dz where the transposed problem qualifies (else the fp32 kernel)."""
+    from complexnn import _native, _ops
+    from complexnn._layer import Variable
+    rng = np.random.default_rng(len(name))
+    in_q = xs[-1] // 4
+    x = rng.normal(size=xs).astype(np.float32)
+    kern = (rng.normal(size=k + (in_q, 4 * F)) / np.sqrt(4 * in_q * np.prod(k))).astype(np.float32)
+    bias = rng.normal(0, 0.1, 4 * F).astype(np.float32)
+    xd, kv, bv = dev(x), Variable(kern), Variable(bias)
+    y = _ops.conv_forward(xd, kv, bv, F, k, (1, 1), pad, "channels_last", d, act, math="fp32", algo="general")
+    dy = rng.normal(size=tuple(y.shape)).astype(np.float32)
+    desc = _native.make_conv_desc(2, xs[0], xs[1:3], in_q, F, k, (1, 1), d, pad, "channels_last", act)
+    a, b = ctypes.c_int32(-1), ctypes.c_int32(-1)
+    assert _native.lib().qnn_conv_backward_uses_tensor_cores(ctypes.byref(desc), ctypes.byref(a), ctypes.byref(b)) == 0
+    assert b.value == 1
+    dx, dk, db = _ops.conv_backward(xd, y, dev(dy), kv, True, F, k, (1, 1), pad, "channels_last", d, act, math="tf32")
+    rdx, rdk, rdb = O.qconv_backward(x, kern, bias, F, (1, 1), pad, "channels_last", d, act, dy)
+    emax, efro = errs(dk.cpu().numpy(), rdk)
+    assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "dkernel: max-rel %.3e fro-rel %.3e" % (emax, efro)
+    emax, efro = errs(dx.cpu().numpy(), rdx)
+    assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "dx: max-rel %.3e fro-rel %.3e" % (emax, efro)
     check(db.cpu().numpy(), rdb, 1e-4, "dbias")
 
 
@@ -778,23 +816,49 @@ def test_tensor_core_dgrad_dense_vs_oracle(cnn, rows, in_q, units, act):
     check(db.cpu().numpy(), rdb, 1e-4, "dbias")
 
 
-@pytest.mark.skipif(os.environ.get("QNN_EXPERIMENTAL_CL2D") != "1",
-                    reason="experimental channels_last rank-2 tensor-core variant: written after round 1's GPU budget was "
-                           "spent, never run on hardware; opt in with QNN_EXPERIMENTAL_CL2D=1 (run it in its own process)")
-@pytest.mark.parametrize("shape", [(1, (4, 128), 8, 32, (3, 3), (1, 1), "same"), (2, (5, 131), 16, 64, (3, 5), (1, 1), "same"),
-                                   (1, (9, 70), 8, 128, (3, 2), (2, 1), "valid")])
-def test_experimental_channels_last_conv2d_tensor_core(cnn, native_lib, shape):
-    from complexnn import _ops
+def _tc_cl2_shapes():
+    """Seeded random channels_last rank-2 problems (plus channels_last rank-1 ones whose sub-filters do not fit in shared
+    memory) for the streamed-sub-filter tensor-core kernel."""
+    rng = np.random.default_rng(21)
+    out = [(1, (4, 128), 8, 32, (3, 3), (1, 1), "same", "relu", True), (2, (5, 131), 16, 64, (3, 5), (1, 1), "same", "relu", True),
+           (1, (9, 70), 8, 128, (3, 2), (2, 1), "valid", "relu", True),
+           (2, (300,), 128, 128, (5,), (1,), "same", "relu", True)]      # rank 1: 1.3 MB of sub-filters, streamed
+    while len(out) < 14:
+        in_q = int(rng.choice([8, 16, 24, 40]))
+        F = int(rng.choice([32, 64, 96, 128]))
+        k = tuple(int(v) for v in rng.integers(1, 5, size=2))
+        d = tuple(int(v) for v in rng.integers(1, 3, size=2))
+        pad = str(rng.choice(["same", "valid"]))
+        sp = (int(rng.choice([1, 3, 7, 12])), int(rng.choice([5, 40, 64, 129, 131, 200, 257])))
+        if pad == "valid":
+            sp = tuple(max(n, (kk - 1) * dd + 2) for n, kk, dd in zip(sp, k, d))
+        out.append((int(rng.integers(1, 4)), sp, in_q, F, k, d, pad, str(rng.choice(["relu", "linear", "tanh"])),
+                    bool(rng.integers(0, 2))))
+    return out
+
+
+@pytest.mark.parametrize("shape", _tc_cl2_shapes(), ids=lambda s: "B%d_%s_q%d_F%d_k%s_d%s_%s_%s_b%d" % s)
+def test_tensor_core_channels_last_conv2d_vs_oracle(cnn, native_lib, shape):
+    """QuaternionConv2D with the Keras default data_format (channels_last, complexnn/conv.py:527-658) on the
+    streamed-sub-filter tensor-core kernel, TF32 and 3xTF32; any row length (the channel axis is the contiguous one)."""
+    from complexnn import _native, _ops
     from complexnn._layer import Variable
-    B, sp, in_q, F, k, d, pad = shape
-    rng = np.random.default_rng(B + in_q + F)
+    B, sp, in_q, F, k, d, pad, act, use_bias = shape
+    rank = len(sp)
+    rng = np.random.default_rng(B + in_q + F + sum(sp))
     x = rng.normal(size=(B,) + sp + (4 * in_q,)).astype(np.float32)
     kern = (rng.normal(size=k + (in_q, 4 * F)) / np.sqrt(4 * in_q * np.prod(k))).astype(np.float32)
-    bias = rng.normal(0, 0.1, size=4 * F).astype(np.float32)
-    y = _ops.conv_forward(dev(x), Variable(kern), Variable(bias), F, k, (1, 1), pad, "channels_last", d, "relu",
-                          math="tf32", algo="tensor")
-    ref = O.qconv_forward(x, kern, bias, F, (1, 1), pad, "channels_last", d, "relu")
-    check_tf32(y.cpu().numpy(), ref, O.qconv_abs_bound(x, kern, F, (1, 1), pad, "channels_last", d), str(shape))
+    bias = rng.normal(0, 0.1, size=4 * F).astype(np.float32) if use_bias else None
+    ones = (1,) * rank
+    desc = _native.make_conv_desc(rank, B, sp, in_q, F, k, ones, d, pad, "channels_last", act)
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(desc)) == _native.KERNEL_TC_CF
+    bv = Variable(bias) if use_bias else None
+    y = _ops.conv_forward(dev(x), Variable(kern), bv, F, k, ones, pad, "channels_last", d, act, math="tf32", algo="tensor")
+    ref = O.qconv_forward(x, kern, bias, F, ones, pad, "channels_last", d, act)
+    check_tf32(y.cpu().numpy(), ref, O.qconv_abs_bound(x, kern, F, ones, pad, "channels_last", d), str(shape))
+    y3 = _ops.conv_forward(dev(x), Variable(kern), bv, F, k, ones, pad, "channels_last", d, act, math="3xtf32", algo="tensor")
+    check_contract(y3.cpu().numpy(), ref, "3xtf32 " + str(shape))
+    check(y3.cpu().numpy(), ref, FP32_TOL, "3xtf32 " + str(shape))
 
 
 @pytest.mark.parametrize("math", ["tf32", "3xtf32"])

@@ -249,9 +249,17 @@ def test_abi_argument_errors_and_kernel_selection(native_lib):
     cfg5 = _native.make_conv_desc(2, 128, (128, 128), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cfg5)) == 1        # BASELINE config 5
     cf_odd = _native.make_conv_desc(2, 8, (16, 18), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")
-    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cf_odd)) == 0      # row length % 4 != 0 -> general kernel
-    cl2 = _native.make_conv_desc(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_last", "relu")
-    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cl2)) == 0         # channels_last rank 2 -> general kernel
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cf_odd)) == 1      # row length % 4 != 0: row-padded scratch copies
+    timit_t = _native.make_conv_desc(2, 4, (41, 333), 32, 32, (3, 5), (1, 1), (1, 1), "same", "channels_first", "linear")
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(timit_t)) == _native.KERNEL_TC_CF   # free time axis, T = 333
+    cl2 = _native.make_conv_desc(2, 8, (16, 17), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_last", "relu")
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(cl2)) == _native.KERNEL_TC_CF   # channels_last rank 2, any row length
+    big = _native.make_conv_desc(1, 8, (300,), 128, 128, (5,), (1,), (1,), "same", "channels_last", "relu")
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(big)) == _native.KERNEL_TC_CF   # rank 1 whose sub-filters (1.3 MB)
+    #                                                                                         cannot stay resident: streamed
+    x3 = _native.make_conv_desc(1, 256, (256,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(x3)) == _native.KERNEL_TC_CF    # cfg 3 layer under 3xTF32 (hi | lo
+    #                                                                                         image 393 KB): streamed too
     # in_q < 4 (first DECODA layer, models/example_model.py:25): the small-K shuffle kernel in every math mode
     dec = _native.make_conv_desc(1, 325, (250,), 1, 32, (3,), (1,), (1,), "same", "channels_last", "relu")
     assert native_lib.qnn_conv_forward_kernel(ctypes.byref(dec)) == _native.KERNEL_SMALL_K
@@ -294,13 +302,17 @@ def test_backward_kernel_selection_is_host_logic(native_lib):
     # strided, fp32 math, general algo: CUDA-core kernels
     assert ask(mk(1, 8, (64,), 64, 64, (3,), (2,), (1,), "same", "channels_last", "relu")) == (0, 0)
     # channels_first rank 2 (what models/interspeech_model.py trains): the data gradient is the channels_first forward
-    # kernel on dz with the transposed, tap-flipped image; the kernel gradient has no channels_first tensor-core kernel yet
-    assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")) == (1, 0)
+    # kernel on dz with the transposed, tap-flipped image; the kernel gradient runs the position-contraction kernel once
+    # per kernel row on channels_last scratch copies of x and dz
+    assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")) == (1, 1)
+    assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_last", "relu")) == (1, 1)
+    # the TIMIT layers of models/interspeech_model.py:51-61,116: QuaternionConv2D(32, (3, 5), same, channels_first), in_q = 32
+    assert ask(mk(2, 4, (41, 200), 32, 32, (3, 5), (1, 1), (1, 1), "same", "channels_first", "linear")) == (1, 1)
     assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu", math="3xtf32")) == (1, 0)
-    # 3xTF32: data gradient on the tensor cores (three MMAs per block) when the doubled hi | lo image fits in shared
-    # memory (dense 64 -> 64 does, a 3-tap conv with in_q = 64 does not), kernel gradient on the fp32 kernel
+    # 3xTF32: data gradient on the tensor cores (three MMAs per block; the streamed-sub-filter kernel takes what does not
+    # fit resident: a 3-tap conv with in_q = 64 needs a 393 KB hi | lo image), kernel gradient on the fp32 kernel
     assert ask(mk(1, 256, (256,), 64, 64, (1,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (1, 0)
-    assert ask(mk(1, 256, (256,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (0, 0)
+    assert ask(mk(1, 256, (256,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (1, 0)
     assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="fp32")) == (0, 0)
     assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", algo="general")) == (0, 0)
     # tanh has no fused derivative: the backward entry points refuse it, the query says "not on tensor cores"

@@ -14,7 +14,7 @@ else
   # first failure in isolation with a full trace
   timeout 300 python -m pytest tests -m gpu -x -q --tb=long 2>&1 | tail -n 150 > $OUT/${TAG}_fail.log
 fi
-QNN_EXPERIMENTAL_CL2D=1 timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -x -q -k "experimental_channels_last" > $OUT/${TAG}_cl2d.log 2>&1
 timeout 200 python tools/bench_smallk.py > $OUT/${TAG}_smallk.json 2> $OUT/${TAG}_smallk.err
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:k_smallk -c 1 -o $OUT/${TAG}_smallk_prof python tools/bench_smallk.py > /dev/null 2>&1
+timeout 120 python tools/tc_trace.py cfg2 > $OUT/${TAG}_tc_trace_cfg2.log 2>&1
+timeout 120 python tools/tc_trace.py dense > $OUT/${TAG}_tc_trace_dense.log 2>&1
 echo done > $OUT/${TAG}_done
