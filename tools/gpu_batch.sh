@@ -17,4 +17,8 @@ fi
 timeout 200 python tools/bench_smallk.py > $OUT/${TAG}_smallk.json 2> $OUT/${TAG}_smallk.err
 timeout 120 python tools/tc_trace.py cfg2 > $OUT/${TAG}_tc_trace_cfg2.log 2>&1
 timeout 120 python tools/tc_trace.py dense > $OUT/${TAG}_tc_trace_dense.log 2>&1
+if [ -f baseline/_ref/working_example.py ]; then
+  timeout 900 python tools/run_working_example.py --model QDNN > $OUT/${TAG}_working_example_qdnn.json 2> $OUT/${TAG}_working_example_qdnn.log
+  timeout 900 python tools/run_working_example.py --model QCNN > $OUT/${TAG}_working_example_qcnn.json 2> $OUT/${TAG}_working_example_qcnn.log
+fi
 echo done > $OUT/${TAG}_done
