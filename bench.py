@@ -727,9 +727,35 @@ def run_ours(args, w):
             t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             e2e_s = float(t.item())
+        # the copy floor of this box at this N: the same bytes, pinned, H2D and D2H on two streams at once, no kernel --
+        # every rank at the same time (the ranks share the host's PCIe root complexes and memory controllers)
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        x_dev, y_dev2 = torch.empty_like(wl.xs[0]), torch.empty(tuple(y_dev.shape), device="cuda")
+        def copies():
+            with torch.cuda.stream(s_in):
+                x_dev.copy_(xh_t, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                yh_t.copy_(y_dev2, non_blocking=True)
+            s_in.synchronize()
+            s_out.synchronize()
+        copies()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            copies()
+        floor_s = (time.perf_counter() - t0) / e2e_steps
+        if world > 1:
+            t = torch.tensor([floor_s], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            floor_s = float(t.item())
+        del x_dev, y_dev2
         e2e = {"value": world * qmacs(w) / e2e_s, "unit": "qMAC/s",
                "h2d_bytes_per_step": int(xh_t.numel() * 4), "d2h_bytes_per_step": int(yh_t.numel() * 4),
                "ms_per_step": e2e_s * 1e3, "steps": e2e_steps,
+               "copy_floor_ms": floor_s * 1e3, "frac_of_copy_floor": floor_s / e2e_s,
+               "copy_floor": "the same H2D + D2H bytes from / to pinned memory on two streams at once, no kernel, all %d "
+                             "ranks simultaneously (max over ranks): what the host side of this box allows at this N" % world,
                "weights": "kernel + bias stay resident on the device between calls (keyed by host pointer + content hash)"}
     else:
         # the stack / training step through the public layer API with HOST inputs: pinned x -> H2D -> step -> D2H of the result

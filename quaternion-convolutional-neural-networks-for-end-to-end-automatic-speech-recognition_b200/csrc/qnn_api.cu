@@ -171,6 +171,7 @@ int build_dense_geom(int64_t rows, int in_q, int q_units, int act, Geom* g) {
     g->F = q_units;
     g->act = act;
     g->conj_w = 1;
+    g->dense = 1;
     for (int a = 0; a < 3; ++a) {
         g->in_sp[a] = g->out_sp[a] = g->k[a] = g->s[a] = g->d[a] = 1;
         g->pad_lo[a] = 0;
@@ -194,8 +195,15 @@ int forward_kernel(const Geom& g, int rank, int math, int algo) {
     if (algo == QNN_ALGO_AUTO && smallk_plan(g, rank).ok) return kKernSmallK;
     if (math == QNN_MATH_FP32) return kKernGeneral;
     const int x3 = math == QNN_MATH_3XTF32;
-    if (tc_plan(g, rank, x3).ok) return kKernTc;
+    // Resident sub-filters (one launch keeps the whole image in shared memory) win when the image fits with 64-filter
+    // tiles or the layer is one tile; when it only fits with 32-filter tiles the kernel makes twice the passes over x with
+    // N = 32 MMAs that cost as much as N = 64 ones (measured: cfg 3 conv layers 60 us vs ~35 us) -- the streamed-sub-filter
+    // kernel then takes the problem if it qualifies (in_q % 8 == 0, F % 32 == 0).
+    const TcPlan tcp = tc_plan(g, rank, x3);
+    const bool resident_good = tcp.ok && (tcp.n_ftiles == 1 || tcp.f_tile >= 64);
+    if (resident_good) return kKernTc;
     if (tc2d_plan(g, rank, x3).ok) return kKernTc2d;
+    if (tcp.ok) return kKernTc;
     return kKernGeneral;
 }
 
@@ -273,10 +281,7 @@ void backward_selection(const Geom& g, int rank, int math, int algo, int* dx_ker
     const int x3 = math == QNN_MATH_3XTF32;
     const Geom gt = transposed_geom(g);
     // the transposed problem must reproduce the input extent exactly (true for stride 1)
-    if (tc_plan(gt, rank, x3).ok)
-        *dx_kern = kKernTc;
-    else if (tc2d_plan(gt, rank, x3).ok)
-        *dx_kern = kKernTc2d;
+    *dx_kern = forward_kernel(gt, rank, math, QNN_ALGO_TENSOR);  // (TENSOR: never the small-K kernel, which has no transposed form)
     *dw_tc = wgrad_plan(g, rank, x3).ok;
 }
 
@@ -315,12 +320,22 @@ int run_backward(const Geom& g, int rank, int math, int algo, const float* x, co
     const bool relu = g.act == QNN_ACT_RELU;
     float* dz = nullptr;
     int rc = QNN_OK;
-    if (relu && (rc = stream_scratch_alloc(reinterpret_cast<void**>(&dz), (size_t)rows * C * sizeof(float), st))) return rc;
+    // relu layer, channels_last rank 1 / dense, kernel gradient on the tensor cores: the kernel-gradient kernel reads dy
+    // and y itself, forms dz = relu'(y) * dy in its packers, writes it out for the data gradient and accumulates the bias
+    // gradient -- no separate pass over y and dy (it was 28 % of the training step).
+    const bool fused = relu && tc_dw && !g.channels_first && g.k[0] == 1 && g.k[1] == 1 && al16(y);
+    const bool need_dz = relu && (!fused || dx);
+    if (need_dz && (rc = stream_scratch_alloc(reinterpret_cast<void**>(&dz), (size_t)rows * C * sizeof(float), st))) return rc;
     const float* dzc = relu ? dz : dy;
     Geom gl = g;
     gl.act = QNN_ACT_LINEAR;  // dz already carries the activation derivative
-    if (relu || db) rc = g.channels_first ? dz_bgrad_cf(y, dy, dz, db, g.batch, C, P, relu ? 1 : 0, st)
-                                         : dz_bgrad(y, dy, dz, db, rows, C, relu ? 1 : 0, st);
+    if (fused) {
+        rc = wgrad_tc(g, rank, x3, x, dy, dw, st, y, dz, db);
+        dw = nullptr;  // done
+    } else if (relu || db) {
+        rc = g.channels_first ? dz_bgrad_cf(y, dy, dz, db, g.batch, C, P, relu ? 1 : 0, st)
+                              : dz_bgrad(y, dy, dz, db, rows, C, relu ? 1 : 0, st);
+    }
     if (!rc && dx) {
         if (tc_dx == kKernTc)
             rc = packed_dgrad ? tc_forward_packed(gt, rank, x3, dzc, packed_dgrad, nullptr, dx, st)

@@ -18,6 +18,8 @@ struct Geom {
     int channels_first;
     int act;
     int conj_w;  // 1 = dense convention y = conj(W) (x) x  (complexnn/dense.py:139-143), 0 = conv  y = W (x) x
+    int dense;   // 1 = a QuaternionDense problem (or its transposed data-gradient problem): kernel selection for it must not
+                 // depend on the activation, which the packed-image queries of the dense ABI do not carry
 };
 
 void set_error(const char* fmt, ...);
@@ -97,7 +99,8 @@ struct WgradPlan {
 };
 WgradPlan wgrad_plan(const Geom& g, int rank, int x3);
 void wgrad_set_trace(void* device_buffer, size_t bytes);
-int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, float* dw, cudaStream_t st);
+int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, float* dw, cudaStream_t st,
+             const float* yfwd = nullptr, float* dz_out = nullptr, float* db = nullptr);
 
 // tensor-core kernel for channels_first tensors (rank 1 / 2, stride 1): streamed sub-filters, transposing converters
 struct Tc2dPlan {

@@ -415,7 +415,8 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 accph ^= 1;
             }
         }
-        __syncthreads();  // every role is done with this f-tile's sub-filters
+        named_bar_sync(14, kThreads);  // every role is done with this f-tile's sub-filters (one barrier, three call
+                                       // sites: a named barrier, not __syncthreads, which wants ONE call site per block)
       }
     } else if (warp >= kWarpConv0) {
       reg_dealloc<kRegsWg1>();
@@ -549,7 +550,8 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 }
             }
         }
-        __syncthreads();  // every role is done with this f-tile's sub-filters
+        named_bar_sync(14, kThreads);  // every role is done with this f-tile's sub-filters (one barrier, three call
+                                       // sites: a named barrier, not __syncthreads, which wants ONE call site per block)
       }
     } else {
       reg_alloc<kRegsEpi>();
@@ -623,7 +625,8 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             }
             if (r == 0) tma_store_wait_read<0>();  // smem may be released; completion of the writes is the kernel's end
         }
-        __syncthreads();  // every role is done with this f-tile's sub-filters
+        named_bar_sync(14, kThreads);  // every role is done with this f-tile's sub-filters (one barrier, three call
+                                       // sites: a named barrier, not __syncthreads, which wants ONE call site per block)
       }
     }
 

@@ -75,8 +75,9 @@ enum { kTrStart = 0, kTrSetup = 1, kTrEnd = 2, kTrItem = 8 /* + 4*item: mma acc_
 struct P2 {
     unsigned long long* trace;
     int n_items, n_ftiles;
-    int tiles_w, Ho;
+    int tiles_w, Ho, Do;   // Do = 1 below rank 3
     int KH, KW, taps, dh, dw, pad_h, pad_w;
+    int KD, dd, pad_d, rank3;  // rank 3 (channels_first only): a third, outermost spatial axis -- 5-D tensor maps
     int n_qc;      // 8-channel chunks per item
     int n_stages;  // x stages per item = n_qc * KH: one kernel row of one chunk each
     int F, f_tile;
@@ -168,7 +169,7 @@ __device__ __forceinline__ void stage_chunk_rows(const uint32_t (&v)[32], const 
 }
 
 struct ItemPos {
-    int ft, b, ho, w0;
+    int ft, b, dpos, ho, w0;
 };
 __device__ __forceinline__ ItemPos item_pos(const P2& p, int item) {
     ItemPos ip;
@@ -176,7 +177,9 @@ __device__ __forceinline__ ItemPos item_pos(const P2& p, int item) {
     ip.ft = item - tile * p.n_ftiles;
     const int wt = tile % p.tiles_w, t2 = tile / p.tiles_w;
     ip.ho = t2 % p.Ho;
-    ip.b = t2 / p.Ho;
+    const int t3 = t2 / p.Ho;
+    ip.dpos = t3 % p.Do;
+    ip.b = t3 / p.Do;
     ip.w0 = wt * kTileM;
     return ip;
 }
@@ -201,6 +204,8 @@ __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn,
     if (mine && r == 0) {
         if (CL)
             tma_store_4d(tmy, st, ch0, ip.w0, ip.ho, ip.b);  // y[nb][Ho][Wo][4F]: box (32 channels, 128 positions, 1, 1)
+        else if (p.rank3)  // y[nb][4F][Do][Ho][Wo]: box (128 positions, 1, 1, 32 channels, 1 sample)
+            tma_store_5d(tmy, st, ip.w0, ip.ho, ip.dpos, ch0, ip.b);
         else
             tma_store_4d(tmy, st, ip.w0, ip.ho, ch0, ip.b);
         tma_store_commit();
@@ -324,14 +329,18 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
             uint32_t xs = 0, xph = 0;
             for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
                 const ItemPos ip = item_pos(p, item);
-                const int cx = ip.w0 - p.pad_w - p.xshift, cy = ip.ho - p.pad_h, cb = 4 * ip.b;
+                const int cx = ip.w0 - p.pad_w - p.xshift, cy = ip.ho - p.pad_h, cz = ip.dpos - p.pad_d, cb = 4 * ip.b;
                 for (int qc = 0; qc < p.n_qc; ++qc)
-                    for (int kh = 0; kh < p.KH; ++kh) {
+                    for (int kr = 0; kr < p.KD * p.KH; ++kr) {  // kernel planes x kernel rows: one stage each
+                        const int kd = kr / p.KH, kh = kr - kd * p.KH;
                         mbar_wait(&bars->x_empty[xs], xph ^ 1);
                         if (comp == 0) mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)(32 * p.wbox * 4));
                         if (CL)  // x[nb][H][W][4][Q]: box (8 q, 1 component, wbox columns, 1 row, 1 sample) -> dense [w][8 q]
                             tma_load_5d(x_s + (size_t)xs * p.x_stage_bytes + (size_t)comp * p.comp_stride, &tmx, &bars->x_full[xs],
                                         qc * 8, comp, ip.w0 - p.pad_w, cy + kh * p.dh, ip.b);
+                        else if (p.rank3)  // x[nb*4][Q][D][H][W]: box (wbox positions, 1 row, 1 plane, 8 q, 4 components)
+                            tma_load_5d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], cx, cy + kh * p.dh,
+                                        cz + kd * p.dd, qc * 8, cb);
                         else
                             tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], cx, cy + kh * p.dh, qc * 8, cb);
                         if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
@@ -619,15 +628,17 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3) {
     const bool cl = !g.channels_first;
     // channels_last rank 1 is the one-row case of rank 2 (qnn_hamilton_tc.cu, which keeps the sub-filters resident, is
     // preferred when its image fits in shared memory; this kernel streams them, so it takes what that one cannot)
-    if (rank > 2) return no("rank 3");
-    if (g.conj_w && g.act != QNN_ACT_LINEAR) return no("transposed sign table with an activation");
-    if (g.s[1] != 1 || g.s[2] != 1) return no("stride != 1");
+    if (rank == 3 && cl) return no("channels_last rank 3 (a six-axis view: beyond the five TMA axes)");
+    // the transposed sign table is instantiated without an epilogue activation: it serves the data gradient of a
+    // convolution; a dense layer's own forward (conj table + activation) stays on the resident-sub-filter kernel
+    if (g.conj_w && (g.dense || g.act != QNN_ACT_LINEAR)) return no("dense-layer forward (transposed sign table with an activation)");
+    if (g.s[0] != 1 || g.s[1] != 1 || g.s[2] != 1) return no("stride != 1");
     if (g.in_q % 8) return no("in_q not a multiple of 8");
     if (g.F % 32) return no("filters not a multiple of 32");
     // channels_first rows whose length is not a multiple of 4 (TMA strides must be multiples of 16 bytes; the reference's
     // TIMIT model has a free time axis, models/interspeech_model.py:81) run on row-padded scratch copies of x and y
     pl.pad_rows = (!cl && (g.in_sp[2] % 4 || g.out_sp[2] % 4)) ? 1 : 0;
-    if (g.out_sp[2] < 1 || g.out_sp[1] < 1 || g.batch < 1) return no("empty problem");
+    if (g.out_sp[2] < 1 || g.out_sp[1] < 1 || g.out_sp[0] < 1 || g.batch < 1) return no("empty problem");
     // channels_first: un-swizzled TMA boxes must start on a 16-byte boundary of the innermost axis (measured: an odd start
     // column is an illegal instruction, profiles/r01_tma_box_probe.log), so the box starts up to 3 columns early.
     // channels_last: the column axis is not the innermost one, any start works.
@@ -650,7 +661,7 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3) {
     pl.x_stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / stage);
     pl.x_stage_bytes = stage;
     pl.smem_bytes = fixed + (size_t)pl.x_stages * stage;
-    pl.packed_bytes = (size_t)g.k[1] * g.k[2] * g.in_q * 4 * g.F * sizeof(float) * (x3 ? 2 : 1);
+    pl.packed_bytes = (size_t)g.k[0] * g.k[1] * g.k[2] * g.in_q * 4 * g.F * sizeof(float) * (x3 ? 2 : 1);
     pl.why = "";
     return pl;
 }
@@ -672,7 +683,7 @@ int tc2d_pack(const Geom& g, int rank, int x3, int transposed, const float* w, v
         set_error("packed kernel image must be 16-byte aligned and the kernel non-NULL");
         return QNN_E_INVALID;
     }
-    const int taps = g.k[1] * g.k[2], Q = g.in_q, F = g.F, parts = x3 ? 2 : 1;
+    const int taps = g.k[0] * g.k[1] * g.k[2], Q = g.in_q, F = g.F, parts = x3 ? 2 : 1;
     long long s_tap, s_q, s_c, s_f;
     if (!transposed) {
         s_tap = (long long)Q * 4 * F, s_q = 4LL * F, s_c = F, s_f = 1;
@@ -705,7 +716,8 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
         Geom gp = g;
         gp.in_sp[2] = (g.in_sp[2] + 3) & ~3;
         gp.out_sp[2] = (g.out_sp[2] + 3) & ~3;
-        const long long rows_x = (long long)g.batch * 4 * g.in_q * g.in_sp[1], rows_y = (long long)g.batch * 4 * g.F * g.out_sp[1];
+        const long long rows_x = (long long)g.batch * 4 * g.in_q * g.in_sp[0] * g.in_sp[1],
+                        rows_y = (long long)g.batch * 4 * g.F * g.out_sp[0] * g.out_sp[1];
         float *xp = nullptr, *yp = nullptr;
         int rc = stream_scratch_alloc(reinterpret_cast<void**>(&xp), (size_t)rows_x * gp.in_sp[2] * sizeof(float), st);
         if (!rc) rc = stream_scratch_alloc(reinterpret_cast<void**>(&yp), (size_t)rows_y * gp.out_sp[2] * sizeof(float), st);
@@ -720,12 +732,18 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
         set_error("tensor-core kernel needs 16-byte aligned x, packed kernel and y");
         return QNN_E_UNSUPPORTED;
     }
-    const int H = g.in_sp[1], W = g.in_sp[2], Ho = g.out_sp[1], Wo = g.out_sp[2], Q = g.in_q, F = g.F;
+    const int D = g.in_sp[0], H = g.in_sp[1], W = g.in_sp[2], Do = g.out_sp[0], Ho = g.out_sp[1], Wo = g.out_sp[2], Q = g.in_q,
+              F = g.F;
     P2 p{};
     p.tiles_w = (Wo + kTileM - 1) / kTileM;
     p.Ho = Ho;
+    p.Do = Do;
+    p.rank3 = rank == 3 ? 1 : 0;
+    p.KD = g.k[0];
+    p.dd = g.d[0];
+    p.pad_d = g.pad_lo[0];
     p.n_ftiles = pl.n_ftiles;
-    const long long ni = (long long)g.batch * Ho * p.tiles_w * pl.n_ftiles;
+    const long long ni = (long long)g.batch * Do * Ho * p.tiles_w * pl.n_ftiles;
     if (ni > 0x7fffffffLL / 64) {
         set_error("too many tiles");
         return QNN_E_UNSUPPORTED;
@@ -733,13 +751,13 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
     p.n_items = (int)ni;
     p.KH = g.k[1];
     p.KW = g.k[2];
-    p.taps = g.k[1] * g.k[2];
+    p.taps = g.k[0] * g.k[1] * g.k[2];
     p.dh = g.d[1];
     p.dw = g.d[2];
     p.pad_h = g.pad_lo[1];
     p.pad_w = g.pad_lo[2];
     p.n_qc = Q / 8;
-    p.n_stages = p.n_qc * p.KH;
+    p.n_stages = p.n_qc * p.KD * p.KH;
     p.F = F;
     p.f_tile = pl.f_tile;
     p.wbox = pl.wbox;
@@ -753,7 +771,27 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
     p.comp_stride = (int)(((size_t)pl.wbox * 32 + 127) & ~size_t(127));
 
     CUtensorMap tmx, tmy;
-    if (g.channels_first) {
+    if (g.channels_first && rank == 3) {
+        // x[nb][4][Q][D][H][W] seen as [nb*4][Q][D][H][W]: box = (wbox positions, 1 row, 1 plane, 8 quaternion channels, the
+        // 4 components of one sample), no swizzle; y[nb][4F][Do][Ho][Wo]: box = (128 positions, 1, 1, 32 channels, 1 sample)
+        const uint64_t dims[5] = {(uint64_t)W, (uint64_t)H, (uint64_t)D, (uint64_t)Q, (uint64_t)4 * g.batch};
+        const uint64_t str[4] = {(uint64_t)W * 4, (uint64_t)H * W * 4, (uint64_t)D * H * W * 4, (uint64_t)Q * D * H * W * 4};
+        const uint32_t box[5] = {(uint32_t)pl.wbox, 1, 1, 8, 4};
+        int e = make_tmap_f32(&tmx, x, 5, dims, str, box, false);
+        if (e) {
+            set_error("cuTensorMapEncodeTiled(x, channels_first rank 3) failed (%d)", e);
+            return QNN_E_CUDA;
+        }
+        const uint64_t ydims[5] = {(uint64_t)Wo, (uint64_t)Ho, (uint64_t)Do, (uint64_t)4 * F, (uint64_t)g.batch};
+        const uint64_t ystr[4] = {(uint64_t)Wo * 4, (uint64_t)Ho * Wo * 4, (uint64_t)Do * Ho * Wo * 4,
+                                  (uint64_t)4 * F * Do * Ho * Wo * 4};
+        const uint32_t ybox[5] = {(uint32_t)kTileM, 1, 1, 32, 1};
+        e = make_tmap_f32(&tmy, y, 5, ydims, ystr, ybox, false);
+        if (e) {
+            set_error("cuTensorMapEncodeTiled(y, channels_first rank 3) failed (%d)", e);
+            return QNN_E_CUDA;
+        }
+    } else if (g.channels_first) {
         // x[nb][4][Q][H][W] seen as [nb*4][Q][H][W]: box = (wbox positions, 1 row, 8 quaternion channels, the 4
         // components of one sample), no swizzle
         const uint64_t dims[4] = {(uint64_t)W, (uint64_t)H, (uint64_t)Q, (uint64_t)4 * g.batch};

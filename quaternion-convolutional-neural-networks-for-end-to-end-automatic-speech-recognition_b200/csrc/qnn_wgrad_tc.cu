@@ -118,9 +118,13 @@ __device__ __forceinline__ float4 rn4(float a, float b, float c, float d) {
                        __uint_as_float(__float_as_uint(c) + 0x1000u), __uint_as_float(__float_as_uint(d) + 0x1000u));
 }
 
-template <bool CONJ>
+// FUSED: `dz` is dy and `yfwd` the layer's relu output; the packers form dz = (y > 0 ? dy : 0) on the fly (the B operand),
+// the CTAs of row block 0 also write it out for the data gradient (dz_out, may be NULL) and accumulate the bias gradient
+// (db, may be NULL; pre-zeroed) -- the separate dz / bias-gradient pass over y and dy disappears.
+template <bool CONJ, bool FUSED>
 __global__ void __launch_bounds__(kThreads, 1)
-k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const float* __restrict__ dz, float* __restrict__ dw) {
+k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const float* __restrict__ dz, float* __restrict__ dw,
+                    const float* __restrict__ yfwd, float* __restrict__ dz_out, float* __restrict__ db) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_s = smem;                                         // kBStages transposed dz sub-tiles
@@ -287,12 +291,27 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
         const int fg = e % f4_per, bcomp = (e / f4_per) & 3, pg = e / (4 * f4_per);
         const bool active = e < blocks;
         const size_t C = (size_t)4 * p.F;
-        const float* col = dz + (size_t)bcomp * p.F + (size_t)ft * Ft + fg * 4;
+        const size_t col_off = (size_t)bcomp * p.F + (size_t)ft * Ft + fg * 4;
+        const float* col = dz + col_off;
         float4* dst0 = reinterpret_cast<float4*>(b_s) + ((bcomp * 8 + pg) * Ft + fg * 4);
-        auto load_unit = [&](int i, float4 (&v)[4]) {
+        // element offset of the first of this thread's 4 positions of unit i (rows past the end of a sequence are masked)
+        auto unit_pos = [&](int i, int& t) {
             const int unit = cgroup + i * n_groups;
-            const int n = unit / p.units_per_seq, t = (unit - n * p.units_per_seq) * kSub + pg * 4;
-            const float* src = col + ((size_t)n * p.Lo + t) * C;
+            const int n = unit / p.units_per_seq;
+            t = (unit - n * p.units_per_seq) * kSub + pg * 4;
+            return ((size_t)n * p.Lo + t) * C;
+        };
+        auto load_unit = [&](int i, float4 (&v)[4]) {
+            int t;
+            const float* src = col + unit_pos(i, t);
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                v[j] = (active && i < my_units && t + j < p.Lo) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)j * C))
+                                                                  : make_float4(0.f, 0.f, 0.f, 0.f);
+        };
+        auto load_unit_y = [&](int i, float4 (&v)[4]) {  // FUSED: the forward output at the same elements
+            int t;
+            const float* src = yfwd + col_off + unit_pos(i, t);
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 v[j] = (active && i < my_units && t + j < p.Lo) ? __ldg(reinterpret_cast<const float4*>(src + (size_t)j * C))
@@ -323,21 +342,84 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
             ++ucount;
             if (++bs == kBStages) { bs = 0; bph ^= 1; }
         };
-        // three sub-tiles of dz in flight per thread (global-load latency is ~2 sub-tiles of MMA time)
-        float4 v0[4], v1[4], v2[4];
-        load_unit(0, v0);
-        load_unit(1, v1);
-        load_unit(2, v2);
-        for (int i = 0; i < my_units; i += 3) {
-            store_unit(v0);
-            load_unit(i + 3, v0);
-            if (i + 1 < my_units) {
-                store_unit(v1);
-                load_unit(i + 4, v1);
+        if (!FUSED) {
+            // three sub-tiles of dz in flight per thread (global-load latency is ~2 sub-tiles of MMA time)
+            float4 v0[4], v1[4], v2[4];
+            load_unit(0, v0);
+            load_unit(1, v1);
+            load_unit(2, v2);
+            for (int i = 0; i < my_units; i += 3) {
+                store_unit(v0);
+                load_unit(i + 3, v0);
+                if (i + 1 < my_units) {
+                    store_unit(v1);
+                    load_unit(i + 4, v1);
+                }
+                if (i + 2 < my_units) {
+                    store_unit(v2);
+                    load_unit(i + 5, v2);
+                }
             }
-            if (i + 2 < my_units) {
-                store_unit(v2);
-                load_unit(i + 5, v2);
+        } else {
+            // two sub-tiles of (dy, y) in flight per thread (the same 32 data registers per sub-tile pair as above + 16);
+            // dz = relu'(y) * dy is formed when the sub-tile is packed
+            const bool writer = mblk == 0 && active;  // one row block's CTAs cover every column of dz exactly once
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            auto fuse = [&](int i, float4 (&g)[4], const float4 (&yv)[4]) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    g[j].x = yv[j].x > 0.f ? g[j].x : 0.f;
+                    g[j].y = yv[j].y > 0.f ? g[j].y : 0.f;
+                    g[j].z = yv[j].z > 0.f ? g[j].z : 0.f;
+                    g[j].w = yv[j].w > 0.f ? g[j].w : 0.f;
+                    acc.x += g[j].x, acc.y += g[j].y, acc.z += g[j].z, acc.w += g[j].w;
+                }
+                if (writer && dz_out) {
+                    int t;
+                    float* o = dz_out + col_off + unit_pos(i, t);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (t + j < p.Lo) *reinterpret_cast<float4*>(o + (size_t)j * C) = g[j];
+                }
+            };
+            float4 d0[4], y0[4], d1[4], y1[4];
+            load_unit(0, d0);
+            load_unit_y(0, y0);
+            load_unit(1, d1);
+            load_unit_y(1, y1);
+            for (int i = 0; i < my_units; i += 2) {
+                fuse(i, d0, y0);
+                store_unit(d0);
+                load_unit(i + 2, d0);
+                load_unit_y(i + 2, y0);
+                if (i + 1 < my_units) {
+                    fuse(i + 1, d1, y1);
+                    store_unit(d1);
+                    load_unit(i + 3, d1);
+                    load_unit_y(i + 3, y1);
+                }
+            }
+            if (db && mblk == 0) {  // (uniform per CTA) bias gradient: column sums of dz over this CTA's positions
+                mbar_wait_sleep(&bars->acc_full, 0);  // every MMA has read its dz stage: the B ring is free scratch now
+                float4* red = reinterpret_cast<float4*>(b_s);
+                red[e] = active ? acc : make_float4(0.f, 0.f, 0.f, 0.f);
+                asm volatile("bar.sync 1, %0;" ::"n"(kPackThreads) : "memory");
+                if (e < 4 * f4_per) {  // e = bcomp * f4_per + fg: sum over the 8 position groups
+                    float4 sum = red[e];
+                    for (int g8 = 1; g8 < 8; ++g8) {
+                        const int idx = g8 * 4 * f4_per + e;
+                        if (idx < blocks) {
+                            const float4 o = red[idx];
+                            sum.x += o.x, sum.y += o.y, sum.z += o.z, sum.w += o.w;
+                        }
+                    }
+                    float* o = db + (size_t)(e / f4_per) * p.F + (size_t)ft * Ft + (e % f4_per) * 4;
+                    atomicAdd(o + 0, sum.x);
+                    atomicAdd(o + 1, sum.y);
+                    atomicAdd(o + 2, sum.z);
+                    atomicAdd(o + 3, sum.w);
+                }
+                asm volatile("bar.sync 1, %0;" ::"n"(kPackThreads) : "memory");
             }
         }
         // ---- epilogue: D_c (rows (tap, q), columns f) -> dW[tap][q][c][ft*Ft + f] with vector reductions
@@ -433,7 +515,10 @@ WgradPlan wgrad_plan(const Geom& g, int rank, int x3) {
 
 // dw (stored-kernel shape [KH][KW][in_q][4][F]) is OVERWRITTEN.  x and dz are CHANNELS_LAST here whatever g.channels_first
 // says (the caller hands over transposed copies): x [batch][H][W][4 in_q], dz = dy * act'(y) [batch][Ho][Wo][4F], fp32.
-int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, float* dw, cudaStream_t st) {
+// Fused form (yfwd != NULL; rank 1 / dense only): `dz` is dy, yfwd the relu output of the forward; the kernel forms
+// dz = relu'(y) * dy itself, writes it to dz_out (if not NULL) and adds its column sums to db (if not NULL; zeroed here).
+int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, float* dw, cudaStream_t st, const float* yfwd,
+             float* dz_out, float* db) {
     const WgradPlan pl = wgrad_plan(g, rank, x3);
     if (!pl.ok) {
         set_error("tensor-core kernel gradient does not take this shape: %s", pl.why);
@@ -447,6 +532,19 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
     cudaError_t e = cudaMemsetAsync(dw, 0, (size_t)KH * taps * g.in_q * 4 * g.F * sizeof(float), st);
     if (e != cudaSuccess) {
         set_error("dkernel memset failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    const bool fused = yfwd != nullptr;
+    if (fused && KH != 1) {
+        set_error("the fused dz / bias-gradient form of the kernel gradient is rank 1 / dense only");
+        return QNN_E_UNSUPPORTED;
+    }
+    if (fused && ((reinterpret_cast<uintptr_t>(yfwd) | reinterpret_cast<uintptr_t>(dz_out)) & 15)) {
+        set_error("tensor-core kernel gradient needs 16-byte aligned y and dz");
+        return QNN_E_UNSUPPORTED;
+    }
+    if (fused && db && (e = cudaMemsetAsync(db, 0, (size_t)4 * g.F * sizeof(float), st)) != cudaSuccess) {
+        set_error("dbias memset failed: %s", cudaGetErrorString(e));
         return QNN_E_CUDA;
     }
     const int xq = (g.in_q + 3) & ~3;
@@ -502,7 +600,8 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
             return QNN_E_CUDA;
         }
     }
-    auto kern = g.conj_w ? k_hamilton_wgrad_tc<true> : k_hamilton_wgrad_tc<false>;
+    auto kern = fused ? (g.conj_w ? k_hamilton_wgrad_tc<true, true> : k_hamilton_wgrad_tc<false, true>)
+                      : (g.conj_w ? k_hamilton_wgrad_tc<true, false> : k_hamilton_wgrad_tc<false, false>);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
     // grid: a multiple of the number of combinations, at most one CTA per SM, no more groups than units
     int groups = std::min(num_sms() / p.n_combos, p.n_units);
@@ -520,7 +619,7 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
         attr[0].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        e = cudaLaunchKernelEx(&cfg, kern, tmx, p, dz, dw + (size_t)kh * taps * g.in_q * 4 * g.F);
+        e = cudaLaunchKernelEx(&cfg, kern, tmx, p, dz, dw + (size_t)kh * taps * g.in_q * 4 * g.F, yfwd, dz_out, db);
         count_launch();
         if (e == cudaSuccess) e = cudaGetLastError();
         if (e != cudaSuccess) {

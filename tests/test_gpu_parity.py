@@ -625,6 +625,41 @@ def test_tensor_core_channels_first_random_shapes_vs_oracle(cnn, native_lib, sha
     check(y3.cpu().numpy(), ref, FP32_TOL, "3xtf32 " + str(shape))
 
 
+@pytest.mark.parametrize("shape", [
+    (1, (3, 5, 40), 8, 32, (2, 3, 3), (1, 1, 1), "same", "relu"),
+    (2, (4, 3, 132), 32, 64, (3, 1, 2), (1, 2, 1), "valid", "linear"),      # + data gradient on tensor cores
+    (1, (2, 6, 77), 8, 64, (2, 2, 5), (2, 1, 1), "same", "tanh"),          # ragged rows, 5 taps along the row
+], ids=lambda s: "B%d_%s_q%d_F%d_k%s_d%s_%s_%s" % s)
+def test_tensor_core_conv3d_channels_first_vs_oracle(cnn, native_lib, shape):
+    """QuaternionConv3D (complexnn/conv.py:661-794), channels_first: the streamed-sub-filter tensor-core kernel with 5-D
+    tensor maps (kernel planes x kernel rows = x stages); TF32, 3xTF32 and the data gradient."""
+    from complexnn import _native, _ops
+    from complexnn._layer import Variable
+    B, sp, in_q, F, k, d, pad, act = shape
+    rng = np.random.default_rng(B + in_q + F + sum(sp))
+    x = rng.normal(size=(B, 4 * in_q) + sp).astype(np.float32)
+    kern = (rng.normal(size=k + (in_q, 4 * F)) / np.sqrt(4 * in_q * np.prod(k))).astype(np.float32)
+    bias = rng.normal(0, 0.1, size=4 * F).astype(np.float32)
+    ones = (1, 1, 1)
+    desc = _native.make_conv_desc(3, B, sp, in_q, F, k, ones, d, pad, "channels_first", act)
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(desc)) == _native.KERNEL_TC_CF
+    kv, bv = Variable(kern), Variable(bias)
+    y = _ops.conv_forward(dev(x), kv, bv, F, k, ones, pad, "channels_first", d, act, math="tf32", algo="tensor")
+    ref = O.qconv_forward(x, kern, bias, F, ones, pad, "channels_first", d, act)
+    check_tf32(y.cpu().numpy(), ref, O.qconv_abs_bound(x, kern, F, ones, pad, "channels_first", d), str(shape))
+    y3 = _ops.conv_forward(dev(x), kv, bv, F, k, ones, pad, "channels_first", d, act, math="3xtf32", algo="tensor")
+    check_contract(y3.cpu().numpy(), ref, "3xtf32 " + str(shape))
+    check(y3.cpu().numpy(), ref, FP32_TOL, "3xtf32 " + str(shape))
+    if act in ("relu", "linear") and F % 8 == 0 and in_q % 32 == 0:
+        yg = _ops.conv_forward(dev(x), kv, bv, F, k, ones, pad, "channels_first", d, act, math="fp32", algo="general")
+        dy = rng.normal(size=tuple(yg.shape)).astype(np.float32)
+        dx, dk, db = _ops.conv_backward(dev(x), yg, dev(dy), kv, True, F, k, ones, pad, "channels_first", d, act, math="tf32")
+        rdx, rdk, rdb = O.qconv_backward(x, kern, bias, F, ones, pad, "channels_first", d, act, dy)
+        emax, efro = errs(dx.cpu().numpy(), rdx)
+        assert efro <= TF32_TOL and emax <= 2 * TF32_TOL
+        check(dk.cpu().numpy(), rdk, 1e-4, "dkernel")
+
+
 def test_baseline_config5_conv2d_slice_and_properties(cnn):
     """BASELINE.json configs[4]: QuaternionConv2D(128, 3x3, same) on channels_first [B, 4*64, 128, 128] on the
     channels_first tensor-core kernel (one weight pre-pass + one fused launch).  Oracle parity on a B=1 slice of reduced
