@@ -105,6 +105,8 @@ typedef enum qnn_kernel {
     QNN_KERNEL_SMALL_K = 3   /* CUDA cores, fp32, warp-shuffle tap reuse: in_q < 4 channels_last rank 1 (qnn_smallk.cu)  */
 } qnn_kernel;
 QNN_API int qnn_conv_forward_kernel(const qnn_conv_desc* d);
+QNN_API int qnn_dense_forward_kernel(int64_t rows, int32_t in_q, int32_t q_units, int32_t activation, int32_t math,
+                             int32_t algo);
 QNN_API int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units);
 
 /* Which gradients of this layer qnn_*_backward computes on the tensor cores (1) or on the CUDA-core kernels (0) under

@@ -35,6 +35,8 @@ SIGNATURES = {
     "qnn_launch_count": (ctypes.c_uint64, []),
     "qnn_conv_uses_tensor_cores": (ctypes.c_int, [ctypes.POINTER(ConvDesc)]),
     "qnn_conv_forward_kernel": (ctypes.c_int, [ctypes.POINTER(ConvDesc)]),
+    "qnn_dense_forward_kernel": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                                ctypes.c_int32, ctypes.c_int32]),
     "qnn_dense_uses_tensor_cores": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),
     "qnn_conv_backward_uses_tensor_cores": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_int32),
                                                             ctypes.POINTER(ctypes.c_int32)]),

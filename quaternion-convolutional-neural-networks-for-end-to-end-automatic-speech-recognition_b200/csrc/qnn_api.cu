@@ -728,6 +728,13 @@ int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units) {
     return tc_plan(g, 1, 0).ok;
 }
 
+int qnn_dense_forward_kernel(int64_t rows, int32_t in_q, int32_t q_units, int32_t activation, int32_t math, int32_t algo) {
+    Geom g;
+    if (build_dense_geom(rows, in_q, q_units, activation, &g)) return QNN_E_INVALID;
+    if (!valid_math(math) || !valid_algo(algo)) return QNN_E_INVALID;
+    return empty_out(g) ? QNN_KERNEL_GENERAL : forward_kernel(g, 1, math, algo);
+}
+
 int qnn_conv_backward_uses_tensor_cores(const qnn_conv_desc* d, int32_t* dx_tc, int32_t* dkernel_tc) {
     Geom g;
     int rc = build_geom(d, &g);

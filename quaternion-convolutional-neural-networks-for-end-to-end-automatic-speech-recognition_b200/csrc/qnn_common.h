@@ -68,6 +68,7 @@ struct TcPlan {
     int pad_x;        // in_q % 4 != 0: x goes through a channel-padding pre-pass
     int rows_in;      // 128 + (taps-1)*dilation
     int x_stages;
+    int n_st;         // output staging tiles (2, 4 or 8)
     size_t smem_bytes;
     size_t w_bytes;       // one part (hi or lo) of one filter tile's packed image
     size_t packed_bytes;  // whole packed kernel image (all filter tiles, hi [+ lo])

@@ -39,6 +39,7 @@
 // TMEM columns: [0,256) four fp32 accumulators y_r|y_i|y_j|y_k (<= 64 filters per pass), [256,512) the A ring
 // (TF32: eight 32-column slots; 3xTF32: four 64-column slots, hi | lo).
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include "qnn_common.h"
 #include "qnn_ptx.cuh"
@@ -100,6 +101,7 @@ struct TcParams {
     uint32_t w_img_bytes;  // what one pass keeps resident: w_bytes (TF32) or 2 * w_bytes (3xTF32: hi | lo)
     uint32_t w_chunk;      // bulk-copy granule of the image load (multiple of 16 bytes)
     int handshake;         // taps >= A slots: converter groups hand over stage by stage (see the converter role)
+    int n_st;              // output staging tiles: 2 (group pairs take turns), 4 (one per epilogue group) or 8 (one per chunk)
 };
 
 struct __align__(8) Barriers {
@@ -256,8 +258,8 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* w_s = smem;                                               // resident sub-filter image of the current f-tile
     uint8_t* x_s = w_s + ((p.w_img_bytes + 1023u) & ~1023u);           // x ring
-    uint8_t* y_s = x_s + (size_t)p.x_stages * p.x_stage_bytes;         // 2 staging tiles (one per epilogue group pair)
-    float* bias_s = reinterpret_cast<float*>(y_s + 2 * kStagingBytes); // 4 * f_tile floats
+    uint8_t* y_s = x_s + (size_t)p.x_stages * p.x_stage_bytes;         // n_st staging tiles
+    float* bias_s = reinterpret_cast<float*>(y_s + (size_t)p.n_st * kStagingBytes); // 4 * f_tile floats
     Barriers* bars = reinterpret_cast<Barriers*>(reinterpret_cast<uint8_t*>(bias_s) + 1024);
 
     const int tid = threadIdx.x;
@@ -583,7 +585,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 tc_fence_before_sync();
                 mbar_arrive(&bars->acc_empty);  // accumulators are in registers: the next tile's MMAs may start
                 if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 3);
-                if (tile + (int)gridDim.x >= p.n_tiles && ft == p.n_ftiles - 1 &&
+                if (p.n_st == 2 && tile + (int)gridDim.x >= p.n_tiles && ft == p.n_ftiles - 1 &&
                     (size_t)p.x_stages * p.x_stage_bytes >= 4 * (size_t)kStagingBytes) {
                     // Last tile of this CTA in the last pass: every x stage has been consumed and every MMA has read its
                     // sub-filters, so the x ring and the sub-filter region are free: each group gets two private staging
@@ -599,6 +601,40 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                             if (r == 0) tma_store_wait_read<0>();
                             named_bar_sync(1 + grp, 128);
                         }
+                        if (which == 0)
+                            stage_chunk<ACT>(v0, bias_s + c * 32, sto, r, p.act);
+                        else
+                            stage_chunk<ACT>(v1, bias_s + c * 32, sto, r, p.act);
+                        fence_proxy_async_smem();
+                        named_bar_sync(1 + grp, 128);
+                        if (r == 0) {
+                            const int col = c * 32;
+                            tma_store_3d(&tmy, sto, (col / Fp) * p.F + ft * Fp + (col % Fp), t0, b);
+                            tma_store_commit();
+                        }
+                    }
+                    if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 4);
+                    accph ^= 1;
+                    continue;
+                }
+                if (p.n_st >= 4) {
+                    // Private staging: with 8 tiles every (group, chunk) owns one, with 4 every group owns one and re-uses
+                    // it for its second chunk.  No turn taking between groups: the only wait is for this thread's own earlier
+                    // store out of the same tile to have finished READING shared memory -- one tile period ago (8 tiles),
+                    // or the chunk just issued (4 tiles).  (Round 1's two shared tiles made the epilogue 8 k cycles per
+                    // tile: each chunk's store had to drain before the partner group could stage the next one.)
+#pragma unroll
+                    for (int which = 0; which < 2; ++which) {
+                        const int c = grp + 4 * which;
+                        if (c >= n_out) break;
+                        uint8_t* sto = y_s + (size_t)(p.n_st == 8 ? c : grp) * kStagingBytes;
+                        if (r == 0) {
+                            if (which == 1 && p.n_st == 8)
+                                tma_store_wait_read<1>();  // chunk 0's store of this tile may still be reading its own tile
+                            else
+                                tma_store_wait_read<0>();
+                        }
+                        named_bar_sync(1 + grp, 128);
                         if (which == 0)
                             stage_chunk<ACT>(v0, bias_s + c * 32, sto, r, p.act);
                         else
@@ -757,18 +793,33 @@ TcPlan tc_plan(const Geom& g, int rank, int x3) {
     // Filters per pass: the whole layer when it fits (<= 64, accumulators 4 x f_tile TMEM columns); otherwise a
     // divisor that is a multiple of 32, so that every 32-column store chunk stays inside one output component.
     // 3xTF32 keeps twice the image (hi | lo) resident, so it usually settles on a smaller tile.
-    int f_tile = 0, stages = 0;
+    int f_tile = 0, stages = 0, n_st = 2;
     size_t fixed = 0, w_bytes = 0;
     const int cand[3] = {g.F <= 64 ? g.F : 0, 64, 32};
+    // Staging tiles / x stages, in order of preference.  Measured (profiles/r02_staging_sweep.json): private staging tiles
+    // (4 or 8) buy nothing -- dense north-star 24.5 us with 4 + 4 vs 24.4 us with 2 + 4: the tile period is the SM's
+    // store / HBM share, not the turn taking -- while dropping from 4 to 2 x stages costs 25 % (cfg 2: 31.0 -> 39.2 us).
+    // So: two shared staging tiles and as many x stages as fit; QNN_TC_STAGING / QNN_TC_XSTAGES force other splits for
+    // experiments.
+    static const int forced_st = [] { const char* e = getenv("QNN_TC_STAGING"); return e ? atoi(e) : 0; }();
+    static const int forced_xs = [] { const char* e = getenv("QNN_TC_XSTAGES"); return e ? atoi(e) : 0; }();
+    const int pref[][2] = {{2, 4}, {2, 2}, {4, 4}, {4, 2}, {8, 4}, {8, 2}};
     for (int ci = 0; ci < 3 && !f_tile; ++ci) {
         const int ft = cand[ci];
         if (ft <= 0 || ft > g.F || g.F % ft || (ft != g.F && ft % 32)) continue;
         w_bytes = (size_t)taps * 4 * in_q_pad * ft * 4;
         const size_t w_pad = ((w_bytes * (x3 ? 2 : 1)) + 1023) & ~size_t(1023);
-        fixed = 1024 /*align slack*/ + w_pad + 2 * kStagingBytes + 1024 /*bias*/ + 512 /*barriers*/;
-        if (fixed + 2 * stage > kSmemLimit) continue;
-        f_tile = ft;
-        stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / stage) & ~1;  // even: 2 or 4 (slot ownership)
+        for (const auto& pr : pref) {
+            if ((forced_st && pr[0] != forced_st) || (forced_xs && pr[1] != forced_xs)) continue;
+            if (!forced_st && pr[0] != 2) continue;
+            const size_t fx = 1024 /*align slack*/ + w_pad + (size_t)pr[0] * kStagingBytes + 1024 /*bias*/ + 512 /*barriers*/;
+            if (fx + (size_t)pr[1] * stage > kSmemLimit) continue;
+            f_tile = ft;
+            fixed = fx;
+            n_st = pr[0];
+            stages = pr[1];
+            break;
+        }
     }
     if (!f_tile) return no("sub-filters do not fit in shared memory for any admissible filter tile");
     pl.ok = 1;
@@ -778,6 +829,7 @@ TcPlan tc_plan(const Geom& g, int rank, int x3) {
     pl.pad_x = (g.in_q % 4) ? 1 : 0;
     pl.rows_in = rows_in;
     pl.x_stages = stages;
+    pl.n_st = n_st;
     pl.smem_bytes = fixed + (size_t)stages * stage;
     pl.w_bytes = w_bytes;
     pl.packed_bytes = w_bytes * (x3 ? 2 : 1) * (size_t)(g.F / f_tile);
@@ -878,6 +930,7 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
     // whatever its size -- 30 copies of 4 KB kept the warp busy for ~2.9 k cycles before the TMEM allocation), 2 KB granules
     p.w_chunk = (uint32_t)(((p.w_img_bytes + 7) / 8 + 2047) & ~2047u);
     p.handshake = p.taps >= (x3 ? 4 : 8) ? 1 : 0;
+    p.n_st = pl.n_st;
 
     CUtensorMap tmx, tmy;
     if (p.flat) {

@@ -348,3 +348,39 @@ def test_variable_assign_after_parameter_and_device_move():
     np.testing.assert_array_equal(v.numpy(), np.full((2, 3), 8.0, np.float32))
     with pytest.raises(ValueError):
         v.assign(np.zeros((3, 2), np.float32))
+
+
+def test_packed_image_queries_agree_with_kernel_selection(native_lib):
+    """The packed kernel image a caller builds must be the one the forward will read: `*_packed_bytes` > 0 exactly when a
+    tensor-core kernel takes the problem, for every activation and math mode -- and a dense layer's kernel must not depend
+    on its activation (the dense packing ABI does not carry it; a rule that did once packed the streamed layout for a
+    resident-kernel run)."""
+    from complexnn import _native
+    tc = (_native.KERNEL_TC_ROWS, _native.KERNEL_TC_CF)
+    rng = np.random.default_rng(0)
+    for _ in range(300):
+        rank = int(rng.integers(1, 4))
+        cf = bool(rng.integers(0, 2))
+        in_q = int(rng.choice([1, 3, 4, 8, 16, 41, 64, 128]))
+        F = int(rng.choice([8, 16, 32, 48, 64, 128]))
+        k = tuple(int(v) for v in rng.integers(1, 6, size=rank))
+        sp = tuple(int(v) for v in rng.choice([1, 7, 40, 131, 256], size=rank))
+        act = str(rng.choice(["relu", "linear", "tanh"]))
+        math = str(rng.choice(["tf32", "3xtf32", "fp32"]))
+        pad = str(rng.choice(["same", "valid"]))
+        d = _native.make_conv_desc(rank, 2, sp, in_q, F, k, (1,) * rank, (1,) * rank, pad,
+                                   "channels_first" if cf else "channels_last", act, math=math)
+        kern = native_lib.qnn_conv_forward_kernel(ctypes.byref(d))
+        nbytes = native_lib.qnn_conv_packed_bytes(ctypes.byref(d), _native.PACK_FORWARD)
+        assert (nbytes > 0) == (kern in tc), (rank, cf, in_q, F, k, sp, act, math, kern, nbytes)
+        if kern in tc:
+            per_part = int(np.prod(k)) * (-(-in_q // 8) * 8 if kern == _native.KERNEL_TC_ROWS else in_q) * 4 * F * 4
+            assert nbytes == per_part * (2 if math == "3xtf32" else 1)
+    for in_q, q_units in ((40, 64), (128, 128), (250, 128), (64, 16), (3, 64), (16, 100)):
+        for math in ("tf32", "3xtf32", "fp32"):
+            m = _native.MATH[math]
+            kerns = {native_lib.qnn_dense_forward_kernel(1000, in_q, q_units, _native.ACT[a], m, 0)
+                     for a in ("linear", "relu", "tanh", "selu")}
+            assert len(kerns) == 1, (in_q, q_units, math, kerns)
+            nbytes = native_lib.qnn_dense_packed_bytes(1000, in_q, q_units, m, 0, _native.PACK_FORWARD)
+            assert (nbytes > 0) == (kerns.pop() in tc), (in_q, q_units, math)
