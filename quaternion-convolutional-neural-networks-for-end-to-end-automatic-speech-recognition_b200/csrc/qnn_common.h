@@ -66,7 +66,8 @@ struct TcPlan {
     int n_ftiles;
     int in_q_pad;     // in_q rounded up to 8
     int pad_x;        // in_q % 4 != 0: x goes through a channel-padding pre-pass
-    int rows_in;      // 128 + (taps-1)*dilation
+    int rows_in;      // input rows per tile: 127 * stride + (taps-1) * dilation + 1 (rounded up to whole boxes)
+    int box_rows;     // rows per TMA box (<= 256)
     int x_stages;
     int n_st;         // output staging tiles (2, 4 or 8)
     size_t smem_bytes;

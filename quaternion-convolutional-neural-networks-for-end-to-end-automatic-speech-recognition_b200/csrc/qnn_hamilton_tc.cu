@@ -89,6 +89,8 @@ struct TcParams {
     unsigned long long* trace;
     int n_tiles, tiles_per_seq;
     int taps, dil, pad_lo;
+    int stride;    // output position t reads input rows t * stride + tap * dil - pad_lo
+    int box_rows;  // an x stage is ceil(rows_in / box_rows) TMA boxes of box_rows rows (a box has at most 256 rows)
     int in_q, in_q_pad;
     int flat;      // 1: stages walk the flat 4*in_q channel axis (in_q % 8 == 0); 0: per component, padded to 8
     int n_stages;  // x stages (TMA boxes) per tile
@@ -239,6 +241,18 @@ __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn,
     named_bar_sync(5 + pair, 256);
 }
 
+// one x stage (32 channels x rows_in rows starting at input row `row0`) = one or more row boxes into consecutive shared memory
+__device__ __forceinline__ void load_x_stage(const TcParams& p, const CUtensorMap* tmx, uint8_t* dst, uint64_t* bar, int s, int row0,
+                                             int b) {
+    mbar_arrive_expect_tx(bar, (uint32_t)p.rows_in * 128u);
+    for (int r0 = 0; r0 < p.rows_in; r0 += p.box_rows) {  // (rows_in is a multiple of box_rows)
+        if (p.flat)
+            tma_load_3d(dst + (size_t)r0 * 128, tmx, bar, s * 32, row0 + r0, b);
+        else
+            tma_load_4d(dst + (size_t)r0 * 128, tmx, bar, (s % p.n_chunks) * 32, s / p.n_chunks, row0 + r0, b);
+    }
+}
+
 // the resident image of filter tile `ft`: bulk copies of w_chunk bytes, chunk `i` of `n` (the last one may be shorter)
 __device__ __forceinline__ void load_w_chunk(const TcParams& p, const uint8_t* wp, uint8_t* w_s, uint64_t* bar, int ft, int i) {
     const uint32_t off = (uint32_t)i * p.w_chunk;
@@ -302,12 +316,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             const int j = lane / p.n_stages, s = lane - j * p.n_stages;
             const int tile = (int)blockIdx.x + j * (int)gridDim.x;
             const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
-            mbar_arrive_expect_tx(&bars->x_full[lane], (uint32_t)p.rows_in * 128u);
-            uint8_t* dst = x_s + (size_t)lane * p.x_stage_bytes;
-            if (p.flat)
-                tma_load_3d(dst, &tmx, &bars->x_full[lane], s * 32, t0 - p.pad_lo, b);
-            else
-                tma_load_4d(dst, &tmx, &bars->x_full[lane], (s % p.n_chunks) * 32, s / p.n_chunks, t0 - p.pad_lo, b);
+            load_x_stage(p, &tmx, x_s + (size_t)lane * p.x_stage_bytes, &bars->x_full[lane], s, t0 * p.stride - p.pad_lo, b);
             if (lane == 0) trace(p, kTrFirstTma);
         }
         // Every CTA wants the same image at the same moment: each CTA starts at a different chunk so that the requests
@@ -439,12 +448,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 const int j = i / p.n_stages, s = i - j * p.n_stages;
                 const int tile = (int)blockIdx.x + j * (int)gridDim.x;
                 const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
-                mbar_arrive_expect_tx(&bars->x_full[slot], (uint32_t)p.rows_in * 128u);
-                uint8_t* dst = x_s + (size_t)slot * p.x_stage_bytes;
-                if (p.flat)
-                    tma_load_3d(dst, &tmx, &bars->x_full[slot], s * 32, t0 - p.pad_lo, b);
-                else
-                    tma_load_4d(dst, &tmx, &bars->x_full[slot], (s % p.n_chunks) * 32, s / p.n_chunks, t0 - p.pad_lo, b);
+                load_x_stage(p, &tmx, x_s + (size_t)slot * p.x_stage_bytes, &bars->x_full[slot], s, t0 * p.stride - p.pad_lo, b);
             };
             // prologue: fill this group's slots (x_stages is even; every pass starts at an even stage).  The first
             // pass' prologue was issued at kernel start by the barrier-initialising thread.
@@ -491,7 +495,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                         if (p.handshake && tap0 + nb >= p.taps && stage_i + 1 < total_stages) named_bar_arrive(12 + cgrp, 256);
                         as_b = as;
                         for (int tb = 0; tb < nb; ++tb) {
-                            const uint32_t row = (uint32_t)(r + (tap0 + tb) * p.dil);
+                            const uint32_t row = (uint32_t)(r * p.stride + (tap0 + tb) * p.dil);
                             const uint8_t* xrow = xb + row * 128u;
                             const uint32_t sw = row & 7u;
                             const uint32_t dst = t_a + lane_base + as_b * kASlotCols;
@@ -779,14 +783,20 @@ TcPlan tc_plan(const Geom& g, int rank, int x3) {
     };
     if (g.channels_first) return no("channels_first layout");
     if (rank != 1) return no("rank > 1");
-    if (g.s[2] != 1) return no("stride != 1");
+    if (g.s[2] > 4) return no("stride > 4");
     if (g.in_q < 4) return no("fewer than 4 quaternion input channels (contraction too short for the tensor cores)");
     // in_q % 4 != 0: the component blocks of x do not start on 16-byte boundaries (TMA needs that), so x goes through a
     // channel-padding pre-pass first (tc_forward); the packed kernel image is zero-padded by the pack pre-pass
     if (g.F % 16) return no("filters not a multiple of 16");
     const int taps = g.k[2];
-    const int rows_in = kTileM + (taps - 1) * g.d[2];
-    if (rows_in > 256) return no("halo exceeds the 256-row TMA box");
+    // input rows one tile of 128 outputs touches; more than 256 (strides > 1) are fetched as several row boxes
+    int rows_in = (kTileM - 1) * g.s[2] + (taps - 1) * g.d[2] + 1, box_rows = rows_in;
+    if (rows_in > 256) {
+        const int n_box = (rows_in + 255) / 256;
+        box_rows = ((rows_in + n_box - 1) / n_box + 7) & ~7;  // multiple of 8 rows: every box starts on a swizzle period
+        rows_in = box_rows * n_box;
+    }
+    if (rows_in > 1024) return no("halo too large");
     if (g.out_sp[2] < 1 || g.batch < 1) return no("empty problem");
     const int in_q_pad = (g.in_q + 7) & ~7;
     const size_t stage = ((size_t)rows_in * 128 + 1023) & ~size_t(1023);
@@ -828,6 +838,7 @@ TcPlan tc_plan(const Geom& g, int rank, int x3) {
     pl.in_q_pad = in_q_pad;
     pl.pad_x = (g.in_q % 4) ? 1 : 0;
     pl.rows_in = rows_in;
+    pl.box_rows = box_rows;
     pl.x_stages = stages;
     pl.n_st = n_st;
     pl.smem_bytes = fixed + (size_t)stages * stage;
@@ -910,6 +921,8 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
     p.taps = g.k[2];
     p.dil = g.d[2];
     p.pad_lo = g.pad_lo[2];
+    p.stride = g.s[2];
+    p.box_rows = pl.box_rows;
     p.in_q = g.in_q;
     p.in_q_pad = pl.in_q_pad;
     p.flat = (xq % 8 == 0) ? 1 : 0;
@@ -936,7 +949,7 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
     if (p.flat) {
         const uint64_t dims[3] = {(uint64_t)xq * 4, (uint64_t)L, (uint64_t)g.batch};
         const uint64_t str[2] = {(uint64_t)xq * 16, (uint64_t)L * xq * 16};
-        const uint32_t box[3] = {32, (uint32_t)pl.rows_in, 1};
+        const uint32_t box[3] = {32, (uint32_t)pl.box_rows, 1};
         int e = make_tmap_f32(&tmx, x, 3, dims, str, box, true);
         if (e) {
             set_error("cuTensorMapEncodeTiled(x) failed (%d)", e);
@@ -945,7 +958,7 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
     } else {
         const uint64_t dims[4] = {(uint64_t)xq, 4, (uint64_t)L, (uint64_t)g.batch};
         const uint64_t str[3] = {(uint64_t)xq * 4, (uint64_t)xq * 16, (uint64_t)L * xq * 16};
-        const uint32_t box[4] = {32, 1, (uint32_t)pl.rows_in, 1};
+        const uint32_t box[4] = {32, 1, (uint32_t)pl.box_rows, 1};
         int e = make_tmap_f32(&tmx, x, 4, dims, str, box, true);
         if (e) {
             set_error("cuTensorMapEncodeTiled(x) failed (%d)", e);

@@ -322,10 +322,34 @@ def test_small_k_dense_vs_oracle(cnn, rows, in_q, units):
     check(y.cpu().numpy(), O.qdense_forward(x, kern, bias, units, "relu"), FP32_TOL, "small-K dense")
 
 
+@pytest.mark.parametrize("shape", [
+    (2, 300, 40, 64, 3, 2, 1, "same", "relu"), (3, 257, 16, 32, 5, 2, 2, "valid", "linear"), (1, 1000, 64, 64, 3, 3, 1, "causal", "relu"),
+    (2, 129, 8, 128, 2, 4, 1, "same", "tanh"), (4, 64, 41, 64, 3, 2, 1, "same", "relu"),
+], ids=lambda s: "B%d_T%d_q%d_F%d_k%d_s%d_d%d_%s_%s" % s)
+def test_tensor_core_strided_conv1d_vs_oracle(cnn, native_lib, shape):
+    """strides 2..4 on the resident-sub-filter tensor-core kernel (the converter reads row r * stride + tap * dilation of
+    an x stage made of several TMA row boxes), TF32 and 3xTF32."""
+    from complexnn import _native, _ops
+    from complexnn._layer import Variable
+    B, T, in_q, F, k, s_, d, pad, act = shape
+    rng = np.random.default_rng(T + in_q + F)
+    x = rng.normal(size=(B, T, 4 * in_q)).astype(np.float32)
+    kern = (rng.normal(size=(k, in_q, 4 * F)) / np.sqrt(4 * in_q * k)).astype(np.float32)
+    bias = rng.normal(0, 0.1, size=4 * F).astype(np.float32)
+    desc = _native.make_conv_desc(1, B, (T,), in_q, F, (k,), (s_,), (d,), pad, "channels_last", act)
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(desc)) == _native.KERNEL_TC_ROWS
+    kv, bv = Variable(kern), Variable(bias)
+    y = _ops.conv_forward(dev(x), kv, bv, F, (k,), (s_,), pad, "channels_last", (d,), act, math="tf32", algo="tensor")
+    ref = O.qconv_forward(x, kern, bias, F, s_, pad, "channels_last", d, act)
+    check_tf32(y.cpu().numpy(), ref, O.qconv_abs_bound(x, kern, F, s_, pad, "channels_last", d), str(shape))
+    y3 = _ops.conv_forward(dev(x), kv, bv, F, (k,), (s_,), pad, "channels_last", (d,), act, math="3xtf32", algo="auto")
+    check_contract(y3.cpu().numpy(), ref, "3xtf32 " + str(shape))
+
+
 def test_tensor_algo_refuses_unsupported_shapes(cnn):
     from complexnn import _ops
     from complexnn._layer import Variable
-    x = dev(np.zeros((2, 10, 12), np.float32))          # stride 2 is outside the tensor-core kernel
+    x = dev(np.zeros((2, 10, 12), np.float32))          # in_q = 3 is outside the tensor-core kernels
     with pytest.raises(NotImplementedError, match="tensor-core kernel"):
         _ops.conv_forward(x, Variable(np.zeros((3, 3, 64), np.float32)), None, 16, (3,), (2,), "same", "channels_last",
                           (1,), "relu", algo="tensor")

@@ -243,7 +243,10 @@ def test_abi_argument_errors_and_kernel_selection(native_lib):
     tim = _native.make_conv_desc(1, 256, (256,), 41, 64, (3,), (1,), (1,), "same", "channels_last", "relu")
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(tim)) == 1      # cfg 3 first layer (TIMIT, in_q = 41)
     s2 = _native.make_conv_desc(1, 8, (64,), 40, 64, (3,), (2,), (1,), "same", "channels_last", "relu")
-    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(s2)) == 0
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(s2)) == 1          # strides 2..4: several row boxes per x stage
+    s5 = _native.make_conv_desc(1, 8, (64,), 40, 64, (3,), (5,), (1,), "same", "channels_last", "relu")
+    assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(s5)) == 0
+    s2cf = _native.make_conv_desc(2, 8, (16, 16), 64, 128, (3, 3), (2, 2), (1, 1), "same", "channels_first", "relu")
     cf = _native.make_conv_desc(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cf)) == 1          # channels_first tensor-core kernel
     cfg5 = _native.make_conv_desc(2, 128, (128, 128), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")
@@ -266,7 +269,8 @@ def test_abi_argument_errors_and_kernel_selection(native_lib):
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(dec)) == 0
     assert native_lib.qnn_conv_forward_kernel(ctypes.byref(cfg2)) == _native.KERNEL_TC_ROWS
     assert native_lib.qnn_conv_forward_kernel(ctypes.byref(cfg5)) == _native.KERNEL_TC_CF
-    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(s2)) == _native.KERNEL_GENERAL
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(s2)) == _native.KERNEL_TC_ROWS
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(s2cf)) == _native.KERNEL_GENERAL   # strided 2-D: general kernel
     dec.algo = _native.ALGO["general"]
     assert native_lib.qnn_conv_forward_kernel(ctypes.byref(dec)) == _native.KERNEL_GENERAL
     assert native_lib.qnn_allreduce_f32(None, 4, None) == -6                  # QNN_E_STATE: no communicator yet
