@@ -66,7 +66,7 @@ typedef enum qnn_activation {
  * 3XTF32 (parity-safe): every operand split into hi = rn_tf32(v) and lo = rn_tf32(v - hi), each block is
  *        x_lo.w_hi + x_hi.w_lo + x_hi.w_hi on the tensor cores (three MMAs) -- fp32-faithful like the reference's
  *        arithmetic (complexnn/conv.py:334, dense.py:149); shapes no tensor-core kernel takes run the FP32 kernel.
- *        The kernel gradient under 3XTF32 runs on the FP32 kernel.
+ *        Forward, data gradient and kernel gradient all have it.
  * FP32:  CUDA-core FMA. */
 typedef enum qnn_math { QNN_MATH_TF32 = 0, QNN_MATH_FP32 = 1, QNN_MATH_3XTF32 = 2 } qnn_math;
 
@@ -156,8 +156,8 @@ QNN_API int qnn_dense_forward_packed(int64_t rows, int32_t in_q, int32_t q_units
  * point into a flat gradient bucket that qnn_allreduce_f32 then reduces.
  * math / algo as in the forward: under TF32 / 3XTF32 + AUTO the data gradient of a stride-1 layer runs on the tensor
  * cores (the forward kernel on dz with the transposed, tap-flipped kernel image -- channels_last rank 1 / dense and
- * channels_first rank 1 / 2); the kernel gradient of a channels_last rank-1 / dense layer does under TF32; FP32 or
- * GENERAL selects the CUDA-core kernels.  The *_packed variants take the caller's cached DGRAD image (or NULL). */
+ * channels_first rank 1 / 2 / 3); so does the kernel gradient (rank 1 / 2, both layouts; for a relu layer it forms
+ * dz = relu'(y) * dy and the bias gradient in the same kernel); FP32 or GENERAL selects the CUDA-core kernels.  The *_packed variants take the caller's cached DGRAD image (or NULL). */
 QNN_API int qnn_conv_backward(const qnn_conv_desc* d, const float* x, const float* kernel, const float* y, const float* dy,
                       float* dx, float* dkernel, float* dbias, void* stream);
 QNN_API int qnn_dense_backward(int64_t rows, int32_t in_q, int32_t q_units, const float* x, const float* kernel,

@@ -37,15 +37,14 @@ using namespace ptx;
 constexpr int kSub = 32;  // positions per sub-tile (4 k-steps of 8)
 constexpr int kThreads = 1024;
 constexpr int kPackThreads = 512;
-constexpr int kSlots = 8;
-constexpr int kSlotCols = 32;
+constexpr int kMaxSlots = 8;   // TF32: eight 32-column A slots; 3xTF32: four 64-column ones (hi | lo)
 constexpr int kAccCols = 256;
-constexpr int kBStages = 3;
+constexpr int kMaxBStages = 3; // TF32: three dz stages; 3xTF32: two (each holds a hi and a lo image)
 constexpr int kMaxXStages = 4;
 constexpr uint32_t kSmemLimit = 232448;
 constexpr int kRegsWg0 = 24, kRegsWg1 = 48, kRegsEpi = 88;
 static_assert(256 * kRegsWg0 + 256 * kRegsWg1 + 512 * kRegsEpi <= 1024 * 64, "register pool");
-static_assert(kSlots % (kSub / 8) == 0, "a unit's A slots must not wrap around the ring");
+static_assert(4 % (kSub / 8) == 0, "a unit's A slots must not wrap around the ring (4 or 8 slots)");
 
 constexpr uint32_t kNegConv = (1u << 4) | (1u << 7) | (1u << 8) | (1u << 9) | (1u << 12) | (1u << 14);
 constexpr uint32_t transpose_bits(uint32_t m) {
@@ -80,8 +79,8 @@ struct WP {
 
 struct __align__(8) Bars {
     uint64_t x_full[kMaxXStages], x_empty[kMaxXStages];
-    uint64_t a_full[kSlots], a_empty[kSlots];
-    uint64_t b_full[kBStages], b_empty[kBStages];
+    uint64_t a_full[kMaxSlots], a_empty[kMaxSlots];
+    uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
     uint64_t acc_full;
     uint32_t tmem_base;
 };
@@ -113,6 +112,21 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
     asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+__device__ __forceinline__ void split_tf32(uint32_t v, uint32_t& hi, uint32_t& lo) {
+    hi = (v + 0x1000u) & 0xffffe000u;                                          // rn_tf32(v), low bits cleared
+    lo = __float_as_uint(__uint_as_float(v) - __uint_as_float(hi)) + 0x1000u;  // rn_tf32(v - hi)
+}
+// hi / lo parts of four values (3xTF32)
+__device__ __forceinline__ void split4(float a, float b, float c, float d, float4& hi, float4& lo) {
+    uint32_t h[4], l[4];
+    split_tf32(__float_as_uint(a), h[0], l[0]);
+    split_tf32(__float_as_uint(b), h[1], l[1]);
+    split_tf32(__float_as_uint(c), h[2], l[2]);
+    split_tf32(__float_as_uint(d), h[3], l[3]);
+    hi = make_float4(__uint_as_float(h[0]), __uint_as_float(h[1]), __uint_as_float(h[2]), __uint_as_float(h[3]));
+    lo = make_float4(__uint_as_float(l[0]), __uint_as_float(l[1]), __uint_as_float(l[2]), __uint_as_float(l[3]));
+}
+
 __device__ __forceinline__ float4 rn4(float a, float b, float c, float d) {
     return make_float4(__uint_as_float(__float_as_uint(a) + 0x1000u), __uint_as_float(__float_as_uint(b) + 0x1000u),
                        __uint_as_float(__float_as_uint(c) + 0x1000u), __uint_as_float(__float_as_uint(d) + 0x1000u));
@@ -121,10 +135,15 @@ __device__ __forceinline__ float4 rn4(float a, float b, float c, float d) {
 // FUSED: `dz` is dy and `yfwd` the layer's relu output; the packers form dz = (y > 0 ? dy : 0) on the fly (the B operand),
 // the CTAs of row block 0 also write it out for the data gradient (dz_out, may be NULL) and accumulate the bias gradient
 // (db, may be NULL; pre-zeroed) -- the separate dz / bias-gradient pass over y and dy disappears.
-template <bool CONJ, bool FUSED>
+// X3: 3xTF32 -- x^T and dz are split into hi = rn_tf32(v), lo = rn_tf32(v - hi); every block is x_lo.dz_hi + x_hi.dz_lo +
+// x_hi.dz_hi (three MMAs into the same accumulator).
+template <bool CONJ, bool FUSED, bool X3>
 __global__ void __launch_bounds__(kThreads, 1)
 k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const float* __restrict__ dz, float* __restrict__ dw,
                     const float* __restrict__ yfwd, float* __restrict__ dz_out, float* __restrict__ db) {
+    constexpr int kSlots = X3 ? 4 : 8;
+    constexpr int kSlotCols = X3 ? 64 : 32;
+    constexpr int kBStages = X3 ? 2 : 3;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* b_s = smem;                                         // kBStages transposed dz sub-tiles
@@ -218,15 +237,30 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
                 for (int kk = 0; kk < 2; ++kk) {
                     const float* xk = xb + (2 * cgrp + kk) * 8 * pitch;
                     const uint32_t dst = t_a + lane_base + (s0 + kk) * kSlotCols;
+                    if (X3) {
 #pragma unroll
-                    for (int h = 0; h < 2; ++h) {  // components 2h, 2h+1: 16 columns
-                        uint32_t u[16];
+                        for (int a = 0; a < 4; ++a) {  // one component (8 positions) at a time: hi and lo halves of the slot
+                            uint32_t hi[8], lo[8];
 #pragma unroll
-                        for (int a2 = 0; a2 < 2; ++a2)
+                            for (int j = 0; j < 8; ++j) {
+                                split_tf32(__float_as_uint(xk[j * pitch + a * p.in_q]), hi[j], lo[j]);
+                                hi[j] &= vmask;
+                                lo[j] &= vmask;
+                            }
+                            tmem_st8_nc(dst + a * 8, hi);
+                            tmem_st8_nc(dst + 32 + a * 8, lo);
+                        }
+                    } else {
 #pragma unroll
-                            for (int j = 0; j < 8; ++j)
-                                u[a2 * 8 + j] = (__float_as_uint(xk[j * pitch + (2 * h + a2) * p.in_q]) + 0x1000u) & vmask;
-                        tmem_st16_nc(dst + h * 16, u);
+                        for (int h = 0; h < 2; ++h) {  // components 2h, 2h+1: 16 columns
+                            uint32_t u[16];
+#pragma unroll
+                            for (int a2 = 0; a2 < 2; ++a2)
+#pragma unroll
+                                for (int j = 0; j < 8; ++j)
+                                    u[a2 * 8 + j] = (__float_as_uint(xk[j * pitch + (2 * h + a2) * p.in_q]) + 0x1000u) & vmask;
+                            tmem_st16_nc(dst + h * 16, u);
+                        }
                     }
                 }
                 tmem_wait_st();
@@ -252,6 +286,7 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
         const uint32_t comp_stride = 8u * Ft;             // 16-byte units between the dz components of a stage
         const uint32_t kstep_stride = 2u * Ft;            // ... between k-steps (2 position groups of 4)
         const uint32_t stage_stride = p.b_stage_bytes >> 4;
+        const uint32_t lo_off = p.b_stage_bytes >> 5;     // 3xTF32: the lo image follows the hi image inside a stage
         constexpr uint32_t neg_table = CONJ ? kNegDense : kNegConv;
         uint32_t as = 0, aph = 0, bs = 0, bph = 0, accumulate = 0;
         for (int i = 0; i < my_units; ++i) {
@@ -266,8 +301,14 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         const int b = a ^ c;
-                        mma_ts(t_acc + c * Ft, a_col + a * 8, k_lo + b * comp_stride, desc_hi,
-                               ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos, accumulate);
+                        const uint32_t idesc = ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos;
+                        if (X3) {  // x_lo.dz_hi + x_hi.dz_lo + x_hi.dz_hi
+                            mma_ts(t_acc + c * Ft, a_col + 32 + a * 8, k_lo + b * comp_stride, desc_hi, idesc, accumulate);
+                            mma_ts(t_acc + c * Ft, a_col + a * 8, k_lo + lo_off + b * comp_stride, desc_hi, idesc, 1);
+                            mma_ts(t_acc + c * Ft, a_col + a * 8, k_lo + b * comp_stride, desc_hi, idesc, 1);
+                        } else {
+                            mma_ts(t_acc + c * Ft, a_col + a * 8, k_lo + b * comp_stride, desc_hi, idesc, accumulate);
+                        }
                         accumulate = 1;
                     }
                     mma_commit(&bars->a_empty[as]);
@@ -322,7 +363,22 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
         auto store_unit = [&](const float4 (&v)[4]) {
             mbar_wait(&bars->b_empty[bs], bph ^ 1);
             if (e == 0 && ucount < 24) trace(p, 8 + 8 * ucount + 2);
-            if (active) {
+            if (active && X3) {
+                float4* d = dst0 + (size_t)bs * (p.b_stage_bytes >> 4);
+                float4* dl = d + (p.b_stage_bytes >> 5);
+                const int rot = (fg >> 1) & 3;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const int k = (i + rot) & 3;  // (see the TF32 branch for the rotation)
+                    float4 hi, lo;
+                    if (k == 0) split4(v[0].x, v[1].x, v[2].x, v[3].x, hi, lo);
+                    else if (k == 1) split4(v[0].y, v[1].y, v[2].y, v[3].y, hi, lo);
+                    else if (k == 2) split4(v[0].z, v[1].z, v[2].z, v[3].z, hi, lo);
+                    else split4(v[0].w, v[1].w, v[2].w, v[3].w, hi, lo);
+                    d[k] = hi;
+                    dl[k] = lo;
+                }
+            } else if (active) {
                 float4* d = dst0 + (size_t)bs * (p.b_stage_bytes >> 4);
                 const float4 o0 = rn4(v[0].x, v[1].x, v[2].x, v[3].x), o1 = rn4(v[0].y, v[1].y, v[2].y, v[3].y),
                              o2 = rn4(v[0].z, v[1].z, v[2].z, v[3].z), o3 = rn4(v[0].w, v[1].w, v[2].w, v[3].w);
@@ -477,7 +533,6 @@ WgradPlan wgrad_plan(const Geom& g, int rank, int x3) {
         pl.why = why;
         return pl;
     };
-    if (x3) return no("3xTF32 kernel gradient runs on the fp32 CUDA-core kernel");
     // channels_first: the caller transposes x and dz to channels_last scratch copies (run_backward); rank 2: one launch
     // per kernel row
     if (rank > 2) return no("rank 3");
@@ -496,9 +551,9 @@ WgradPlan wgrad_plan(const Geom& g, int rank, int x3) {
     const int R = taps * xq;
     const int n_mblk = (R + 127) / 128, n_ft = g.F / f_tile;
     if (n_mblk * n_ft > 148) return no("more (row block, filter tile) combinations than SMs");
-    const size_t b_stage = (size_t)4 * 8 * f_tile * 16;
+    const size_t b_stage = (size_t)4 * 8 * f_tile * 16 * (x3 ? 2 : 1);
     const size_t x_stage = ((size_t)rows * 4 * xq * 4 + 1023) & ~size_t(1023);
-    const size_t fixed = 1024 + kBStages * b_stage + 512;
+    const size_t fixed = 1024 + (x3 ? 2 : 3) * b_stage + 512;
     if (fixed + 2 * x_stage > kSmemLimit) return no("x stages do not fit in shared memory");
     pl.ok = 1;
     pl.f_tile = f_tile;
@@ -587,7 +642,7 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
     p.rows = pl.rows;
     p.x_stages = pl.x_stages;
     p.x_stage_bytes = (int)pl.x_stage_bytes;
-    p.b_stage_bytes = (uint32_t)(4 * 8 * pl.f_tile * 16);
+    p.b_stage_bytes = (uint32_t)(4 * 8 * pl.f_tile * 16 * (x3 ? 2 : 1));
     CUtensorMap tmx;
     {
         // x[nb][H][L][4][in_q]: one box = (all in_q channels, the 4 components, 32 + halo columns, one row, one sample), no swizzle
@@ -600,8 +655,14 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
             return QNN_E_CUDA;
         }
     }
-    auto kern = fused ? (g.conj_w ? k_hamilton_wgrad_tc<true, true> : k_hamilton_wgrad_tc<false, true>)
-                      : (g.conj_w ? k_hamilton_wgrad_tc<true, false> : k_hamilton_wgrad_tc<false, false>);
+    typedef void (*WKernel)(const CUtensorMap, const WP, const float*, float*, const float*, float*, float*);
+    WKernel kern;
+    if (x3)
+        kern = fused ? (g.conj_w ? k_hamilton_wgrad_tc<true, true, true> : k_hamilton_wgrad_tc<false, true, true>)
+                     : (g.conj_w ? k_hamilton_wgrad_tc<true, false, true> : k_hamilton_wgrad_tc<false, false, true>);
+    else
+        kern = fused ? (g.conj_w ? k_hamilton_wgrad_tc<true, true, false> : k_hamilton_wgrad_tc<false, true, false>)
+                     : (g.conj_w ? k_hamilton_wgrad_tc<true, false, false> : k_hamilton_wgrad_tc<false, false, false>);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
     // grid: a multiple of the number of combinations, at most one CTA per SM, no more groups than units
     int groups = std::min(num_sms() / p.n_combos, p.n_units);

@@ -772,6 +772,11 @@ def test_tensor_core_dgrad_conv1d_vs_oracle(cnn, name, xs, F, k, d, pad, act):
     assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "dkernel: max-rel %.3e fro-rel %.3e" % (emax, efro)
     check(db.cpu().numpy(), rdb, 1e-4, "dbias")
     check(gk.cpu().numpy(), rdk, 1e-4, "general dkernel")
+    # 3xTF32: every gradient inside the contract (and fp32-faithful), still on the tensor cores where the plan fits
+    dx3, dk3, db3 = _ops.conv_backward(*args, math="3xtf32", algo="auto")
+    for got, want, what in ((dx3, rdx, "dx"), (dk3, rdk, "dkernel"), (db3, rdb, "dbias")):
+        check_contract(got.cpu().numpy(), want, "3xtf32 " + what)
+        check(got.cpu().numpy(), want, 1e-4, "3xtf32 " + what)
 
 
 CF_BWD_CASES = [
@@ -815,8 +820,9 @@ def test_tensor_core_dgrad_channels_first_vs_oracle(cnn, name, xs, F, k, d, pad,
         emax, efro = errs(dx.cpu().numpy(), rdx)
         assert efro <= TF32_TOL and emax <= 2 * TF32_TOL, "dx: max-rel %.3e fro-rel %.3e" % (emax, efro)
     if math == "3xtf32":
-        assert b.value == 0                      # 3xTF32: kernel gradient on the fp32 kernel
-        check(dk.cpu().numpy(), rdk, 1e-4, "dkernel")
+        assert b.value == 1                      # 3xTF32 kernel gradient: hi | lo split of x^T and dz, three MMAs per block
+        check(dk.cpu().numpy(), rdk, 1e-4, "dkernel 3xtf32")
+        check_contract(dk.cpu().numpy(), rdk, "dkernel 3xtf32")
     else:
         assert b.value == 1, "kernel gradient should run on the tensor cores (per-kernel-row launches, transposed copies)"
         emax, efro = errs(dk.cpu().numpy(), rdk)

@@ -312,11 +312,12 @@ def test_backward_kernel_selection_is_host_logic(native_lib):
     assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_last", "relu")) == (1, 1)
     # the TIMIT layers of models/interspeech_model.py:51-61,116: QuaternionConv2D(32, (3, 5), same, channels_first), in_q = 32
     assert ask(mk(2, 4, (41, 200), 32, 32, (3, 5), (1, 1), (1, 1), "same", "channels_first", "linear")) == (1, 1)
-    assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu", math="3xtf32")) == (1, 0)
-    # 3xTF32: data gradient on the tensor cores (three MMAs per block; the streamed-sub-filter kernel takes what does not
-    # fit resident: a 3-tap conv with in_q = 64 needs a 393 KB hi | lo image), kernel gradient on the fp32 kernel
-    assert ask(mk(1, 256, (256,), 64, 64, (1,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (1, 0)
-    assert ask(mk(1, 256, (256,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (1, 0)
+    assert ask(mk(2, 8, (16, 16), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu", math="3xtf32")) == (1, 1)
+    # 3xTF32: both gradients on the tensor cores with three MMAs per block (data gradient: the streamed-sub-filter kernel
+    # takes what does not fit resident -- a 3-tap conv with in_q = 64 needs a 393 KB hi | lo image; kernel gradient: hi | lo
+    # A slots and dz stages)
+    assert ask(mk(1, 256, (256,), 64, 64, (1,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (1, 1)
+    assert ask(mk(1, 256, (256,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="3xtf32")) == (1, 1)
     assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", math="fp32")) == (0, 0)
     assert ask(mk(1, 8, (64,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu", algo="general")) == (0, 0)
     # tanh has no fused derivative: the backward entry points refuse it, the query says "not on tensor cores"
