@@ -65,7 +65,8 @@ struct TcPlan {
     int f_tile;       // filters per pass (<= 64)
     int n_ftiles;
     int in_q_pad;     // in_q rounded up to 8
-    int pad_x;        // in_q % 4 != 0: x goes through a channel-padding pre-pass
+    int pad_x;        // (unused since round 2: ragged channel counts are read in place)
+    int ragged;       // in_q % 4 != 0: un-swizzled 36-channel boxes of the flat row, 4-byte converter loads
     int rows_in;      // input rows per tile: 127 * stride + (taps-1) * dilation + 1 (rounded up to whole boxes)
     int box_rows;     // rows per TMA box (<= 256)
     int x_stages;
@@ -94,7 +95,8 @@ struct WgradPlan {
     int ok;
     int f_tile, n_ftiles, n_mblk;
     int rows;  // x stage rows: 32 + (taps - 1) * dilation
-    int pad_x;  // in_q % 4 != 0: x goes through the channel-padding pre-pass
+    int pad_x;  // in_q % 4 != 0 and 4 in_q > 256: x goes through the channel-padding pre-pass
+    int flat_x; // in_q % 4 != 0 and 4 in_q <= 256: the x stage is the flat channel row (no pre-pass)
     int x_stages;
     size_t x_stage_bytes, smem_bytes;
     const char* why;

@@ -93,6 +93,10 @@ struct TcParams {
     int box_rows;  // an x stage is ceil(rows_in / box_rows) TMA boxes of box_rows rows (a box has at most 256 rows)
     int in_q, in_q_pad;
     int flat;      // 1: stages walk the flat 4*in_q channel axis (in_q % 8 == 0); 0: per component, padded to 8
+    int ragged;    // in_q % 4 != 0: the component blocks of a row are not 16-byte aligned -- a stage is an un-swizzled box of
+                   // 36 flat channels starting at the aligned channel at or below the chunk's first one (row pitch 144 bytes),
+                   // the converter reads 4-byte words at the remaining shift (0..3 channels)
+    int x_pitch;   // bytes per row of an x stage: 128 (swizzled) or 144 (ragged)
     int n_stages;  // x stages (TMA boxes) per tile
     int n_chunks;  // padded mode: 32-channel chunks per component
     int m8;        // flat mode: k-steps (8 channels) per component = in_q / 8
@@ -244,10 +248,12 @@ __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn,
 // one x stage (32 channels x rows_in rows starting at input row `row0`) = one or more row boxes into consecutive shared memory
 __device__ __forceinline__ void load_x_stage(const TcParams& p, const CUtensorMap* tmx, uint8_t* dst, uint64_t* bar, int s, int row0,
                                              int b) {
-    mbar_arrive_expect_tx(bar, (uint32_t)p.rows_in * 128u);
+    mbar_arrive_expect_tx(bar, (uint32_t)(p.rows_in * p.x_pitch));
     for (int r0 = 0; r0 < p.rows_in; r0 += p.box_rows) {  // (rows_in is a multiple of box_rows)
         if (p.flat)
             tma_load_3d(dst + (size_t)r0 * 128, tmx, bar, s * 32, row0 + r0, b);
+        else if (p.ragged)  // flat channel axis, box of 36 from the aligned channel at or below component * in_q + chunk * 32
+            tma_load_3d(dst + (size_t)r0 * 144, tmx, bar, ((s / p.n_chunks) * p.in_q + (s % p.n_chunks) * 32) & ~3, row0 + r0, b);
         else
             tma_load_4d(dst + (size_t)r0 * 128, tmx, bar, (s % p.n_chunks) * 32, s / p.n_chunks, row0 + r0, b);
     }
@@ -460,12 +466,14 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             int stage_i = 0;  // stage number inside this pass
             for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
                 const bool detail = r == 0 && ft == 0 && tile == (int)(blockIdx.x + gridDim.x);
-                int cch = 0;  // padded mode: chunk inside the component
+                int cch = 0, ca = 0;  // padded mode: chunk inside the component, component
                 for (int s = 0; s < p.n_stages; ++s, ++stage_i) {
-                    int kc = 32;
+                    int kc = 32, shift = 0, kvalid = 32;
                     if (!p.flat) {
                         kc = min(32, p.in_q_pad - cch * 32);
-                        if (++cch == p.n_chunks) cch = 0;
+                        shift = (ca * p.in_q + cch * 32) & 3;   // ragged: channels the box starts below the chunk's first one
+                        kvalid = p.in_q - cch * 32;             // channels of the chunk that belong to this component
+                        if (++cch == p.n_chunks) { cch = 0; ++ca; }
                     }
                     if ((stage_i & 1) != cgrp) {  // the other group's stage: just advance the ring positions
                         if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
@@ -499,7 +507,30 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                             const uint8_t* xrow = xb + row * 128u;
                             const uint32_t sw = row & 7u;
                             const uint32_t dst = t_a + lane_base + as_b * kASlotCols;
-                            if (X3) {
+                            if (p.ragged) {
+                                // un-swizzled rows of 144 bytes; 4-byte loads at any channel shift (lanes 36 words apart:
+                                // 4-way bank conflicts, the price of skipping the padding pass over x).  Channels past the
+                                // component's end hold the NEXT component's data: zeroed (their weights are zero rows, but
+                                // 0 x inf would still poison the sum).
+                                const uint32_t* xw = reinterpret_cast<const uint32_t*>(xb + row * 144u) + shift;
+                                for (int k0 = 0; k0 < kc; k0 += 8) {
+                                    uint32_t v[8];
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k)  // unconditional loads (always inside the 36-channel box), then mask
+                                        v[k] = xw[k0 + k] & (k0 + k < kvalid ? 0xffffffffu : 0u);
+                                    if (X3) {
+                                        uint32_t hi[8], lo[8];
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k) split_tf32(v[k], hi[k], lo[k]);
+                                        tmem_st8_nc(dst + k0, hi);
+                                        tmem_st8_nc(dst + 32 + k0, lo);
+                                    } else {
+#pragma unroll
+                                        for (int k = 0; k < 8; ++k) v[k] = rn_tf32(v[k]);
+                                        tmem_st8_nc(dst + k0, v);
+                                    }
+                                }
+                            } else if (X3) {
                                 for (int k0 = 0; k0 < kc; k0 += 8) {  // 8 columns at a time: hi and lo halves of the slot
                                     const uint4 v0 = *reinterpret_cast<const uint4*>(xrow + ((((k0 >> 2)) ^ sw) << 4));
                                     const uint4 v1 = *reinterpret_cast<const uint4*>(xrow + ((((k0 >> 2) + 1) ^ sw) << 4));
@@ -799,7 +830,8 @@ TcPlan tc_plan(const Geom& g, int rank, int x3) {
     if (rows_in > 1024) return no("halo too large");
     if (g.out_sp[2] < 1 || g.batch < 1) return no("empty problem");
     const int in_q_pad = (g.in_q + 7) & ~7;
-    const size_t stage = ((size_t)rows_in * 128 + 1023) & ~size_t(1023);
+    const bool ragged = (g.in_q % 4) != 0;
+    const size_t stage = ((size_t)rows_in * (ragged ? 144 : 128) + 1023) & ~size_t(1023);
     // Filters per pass: the whole layer when it fits (<= 64, accumulators 4 x f_tile TMEM columns); otherwise a
     // divisor that is a multiple of 32, so that every 32-column store chunk stays inside one output component.
     // 3xTF32 keeps twice the image (hi | lo) resident, so it usually settles on a smaller tile.
@@ -836,7 +868,8 @@ TcPlan tc_plan(const Geom& g, int rank, int x3) {
     pl.f_tile = f_tile;
     pl.n_ftiles = g.F / f_tile;
     pl.in_q_pad = in_q_pad;
-    pl.pad_x = (g.in_q % 4) ? 1 : 0;
+    pl.pad_x = 0;  // (round 1 padded x in a pre-pass when in_q % 4 != 0; the ragged stage mode reads x in place)
+    pl.ragged = ragged ? 1 : 0;
     pl.rows_in = rows_in;
     pl.box_rows = box_rows;
     pl.x_stages = stages;
@@ -891,25 +924,7 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
         return QNN_E_UNSUPPORTED;
     }
     const int L = g.in_sp[2], Lo = g.out_sp[2];
-    // ragged channel count: pad x to a multiple of 4 channels per component in a stream-ordered scratch
-    const int xq = (g.in_q + 3) & ~3;
-    float* xp = nullptr;
-    if (pl.pad_x) {
-        const long long rows = (long long)g.batch * L;
-        int rc = stream_scratch_alloc(reinterpret_cast<void**>(&xp), (size_t)rows * 4 * xq * sizeof(float), st);
-        if (rc) return rc;
-        rc = pad_x_channels(x, xp, rows, g.in_q, xq, st);
-        if (rc) {
-            cudaFreeAsync(xp, st);
-            return rc;
-        }
-        x = xp;
-    }
-    struct FreeOnExit {
-        float* p;
-        cudaStream_t st;
-        ~FreeOnExit() { if (p) cudaFreeAsync(p, st); }
-    } free_xp{xp, st};
+    const int xq = g.in_q;  // (x is read in place whatever in_q is)
     TcParams p{};
     p.tiles_per_seq = (Lo + kTileM - 1) / kTileM;
     const long long nt = (long long)g.batch * p.tiles_per_seq;
@@ -926,6 +941,8 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
     p.in_q = g.in_q;
     p.in_q_pad = pl.in_q_pad;
     p.flat = (xq % 8 == 0) ? 1 : 0;
+    p.ragged = pl.ragged;
+    p.x_pitch = pl.ragged ? 144 : 128;
     p.n_chunks = (pl.in_q_pad + 31) / 32;
     p.m8 = xq / 8;
     p.n_stages = p.flat ? xq / 8 : 4 * p.n_chunks;
@@ -934,7 +951,7 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
     p.n_ftiles = pl.n_ftiles;
     p.rows_in = pl.rows_in;
     p.x_stages = pl.x_stages;
-    p.x_stage_bytes = (int)(((size_t)pl.rows_in * 128 + 1023) & ~size_t(1023));
+    p.x_stage_bytes = (int)(((size_t)pl.rows_in * p.x_pitch + 1023) & ~size_t(1023));
     p.act = g.act;
     p.has_bias = bias != nullptr;
     p.w_bytes = (uint32_t)pl.w_bytes;
@@ -953,6 +970,16 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
         int e = make_tmap_f32(&tmx, x, 3, dims, str, box, true);
         if (e) {
             set_error("cuTensorMapEncodeTiled(x) failed (%d)", e);
+            return QNN_E_CUDA;
+        }
+    } else if (pl.ragged) {
+        // flat rows of 4 in_q floats (a multiple of 16 bytes whatever in_q is); un-swizzled boxes of 36 channels
+        const uint64_t dims[3] = {(uint64_t)xq * 4, (uint64_t)L, (uint64_t)g.batch};
+        const uint64_t str[2] = {(uint64_t)xq * 16, (uint64_t)L * xq * 16};
+        const uint32_t box[3] = {36, (uint32_t)pl.box_rows, 1};
+        int e = make_tmap_f32(&tmx, x, 3, dims, str, box, false);
+        if (e) {
+            set_error("cuTensorMapEncodeTiled(x, ragged) failed (%d)", e);
             return QNN_E_CUDA;
         }
     } else {

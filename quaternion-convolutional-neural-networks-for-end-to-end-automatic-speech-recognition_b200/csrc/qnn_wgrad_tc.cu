@@ -72,6 +72,7 @@ struct WP {
     int in_q, F, f_tile, R;      // in_q as the kernel sees x (padded to 4); R = taps * in_q rows
     int in_q_out;                // the layer's real in_q: rows with q >= in_q_out are padding and are not written
     int Lo;
+    int flat_x;                  // in_q % 4 != 0 (and 4 in_q <= 256): the x box spans the flat 4 in_q channel axis (4-D map)
     int Ho, h_off;               // rank 2: sequence s = (sample n, output row ho) reads input row ho + h_off (zero when outside)
     int rows, x_stages, x_stage_bytes;
     uint32_t b_stage_bytes;
@@ -203,7 +204,10 @@ k_hamilton_wgrad_tc(const __grid_constant__ CUtensorMap tmx, const WP p, const f
                 mbar_wait(&bars->x_empty[xs], xph ^ 1);
                 if (i < 24) trace(p, 8 + 8 * i + 6);
                 mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)(p.rows * 4 * p.in_q * 4));
-                tma_load_5d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], 0, 0, t0 - p.pad_lo, ho + p.h_off, n);
+                if (p.flat_x)
+                    tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], 0, t0 - p.pad_lo, ho + p.h_off, n);
+                else
+                    tma_load_5d(x_s + (size_t)xs * p.x_stage_bytes, &tmx, &bars->x_full[xs], 0, 0, t0 - p.pad_lo, ho + p.h_off, n);
                 if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
             }
         }
@@ -538,7 +542,12 @@ WgradPlan wgrad_plan(const Geom& g, int rank, int x3) {
     if (rank > 2) return no("rank 3");
     if (g.s[1] != 1 || g.s[2] != 1) return no("stride != 1");
     if (g.in_q < 4) return no("fewer than 4 quaternion input channels");
-    const int xq = (g.in_q + 3) & ~3;  // in_q % 4 != 0: channel-padding pre-pass (TMA alignment of the component blocks)
+    // in_q % 4 != 0: the component blocks of a row do not start on 16-byte boundaries, so the box cannot be (in_q, 4, rows).
+    // The row as a whole (4 in_q floats = a multiple of 16 bytes) can: the x stage is then the flat row and the converter's
+    // 4-byte gathers do not care about alignment -- as long as the row fits one TMA box (4 in_q <= 256).  Longer ragged rows
+    // (DECODA's in_q = 250) go through the channel-padding pre-pass.
+    const bool flat_x = (g.in_q % 4) != 0 && 4 * g.in_q <= 256;
+    const int xq = flat_x ? g.in_q : (g.in_q + 3) & ~3;
     if (xq > 256) return no("more than 256 quaternion input channels (TMA box limit)");
     if (g.F % 16) return no("filters not a multiple of 16");
     if (g.out_sp[2] < 1 || g.out_sp[1] < 1 || g.batch < 1) return no("empty problem");
@@ -561,6 +570,7 @@ WgradPlan wgrad_plan(const Geom& g, int rank, int x3) {
     pl.n_mblk = n_mblk;
     pl.rows = rows;
     pl.pad_x = xq != g.in_q;
+    pl.flat_x = flat_x ? 1 : 0;
     pl.x_stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / x_stage);
     pl.x_stage_bytes = x_stage;
     pl.smem_bytes = fixed + (size_t)pl.x_stages * x_stage;
@@ -602,7 +612,7 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
         set_error("dbias memset failed: %s", cudaGetErrorString(e));
         return QNN_E_CUDA;
     }
-    const int xq = (g.in_q + 3) & ~3;
+    const int xq = pl.flat_x ? g.in_q : (g.in_q + 3) & ~3;
     float* xp = nullptr;
     if (pl.pad_x) {
         const long long rows = (long long)g.batch * H * L;
@@ -639,12 +649,23 @@ int wgrad_tc(const Geom& g, int rank, int x3, const float* x, const float* dz, f
     p.R = taps * xq;
     p.Lo = Lo;
     p.Ho = Ho;
+    p.flat_x = pl.flat_x;
     p.rows = pl.rows;
     p.x_stages = pl.x_stages;
     p.x_stage_bytes = (int)pl.x_stage_bytes;
     p.b_stage_bytes = (uint32_t)(4 * 8 * pl.f_tile * 16 * (x3 ? 2 : 1));
     CUtensorMap tmx;
-    {
+    if (pl.flat_x) {
+        // x[nb][H][L][4 in_q]: one box = (the whole flat channel row, 32 + halo columns, one row, one sample), no swizzle
+        const uint64_t dims[4] = {(uint64_t)4 * xq, (uint64_t)L, (uint64_t)H, (uint64_t)g.batch};
+        const uint64_t str[3] = {(uint64_t)xq * 16, (uint64_t)L * xq * 16, (uint64_t)H * L * xq * 16};
+        const uint32_t box[4] = {(uint32_t)4 * xq, (uint32_t)pl.rows, 1, 1};
+        int rc = make_tmap_f32(&tmx, x, 4, dims, str, box, false);
+        if (rc) {
+            set_error("cuTensorMapEncodeTiled(x, wgrad, flat rows) failed (%d)", rc);
+            return QNN_E_CUDA;
+        }
+    } else {
         // x[nb][H][L][4][in_q]: one box = (all in_q channels, the 4 components, 32 + halo columns, one row, one sample), no swizzle
         const uint64_t dims[5] = {(uint64_t)xq, 4, (uint64_t)L, (uint64_t)H, (uint64_t)g.batch};
         const uint64_t str[4] = {(uint64_t)xq * 4, (uint64_t)xq * 16, (uint64_t)L * xq * 16, (uint64_t)H * L * xq * 16};

@@ -558,7 +558,7 @@ def test_empty_batch_and_short_sequences(cnn):
 
 def test_baseline_config3_stack_vs_oracle(cnn):
     """BASELINE.json configs[2] (as worded): 3 x QuaternionConv1D(64, 3, same, relu) + 2 x QuaternionDense(256, relu) on
-    TIMIT-shaped input [B, T, 4*41]; the first layer (in_q = 41) goes through the channel-padding pre-pass, all five
+    TIMIT-shaped input [B, T, 4*41]; the first layer (in_q = 41) reads its ragged channel blocks in place (un-swizzled 36-channel boxes), all five
     layers run on tensor cores.
     Checked layer by layer against the oracle fed with the GPU's own previous activations (so errors do not compound
     through relu masks) and end to end in the Frobenius norm."""
@@ -739,7 +739,7 @@ TC_BWD_CASES = [
     ("causal_k2_relu", (3, 131, 128), 48, 2, 3, "causal", "relu"),
     ("wide_rows_2_blocks", (2, 100, 256), 32, 3, 1, "same", "relu"),  # taps * in_q = 192 rows of dW -> two row blocks
     ("f128_two_filter_tiles", (1, 70, 64), 128, 2, 1, "same", "linear"),
-    ("timit_first_layer_inq41", (2, 96, 164), 64, 3, 1, "same", "relu"),   # ragged in_q: channel-padding pre-pass in wgrad
+    ("timit_first_layer_inq41", (2, 96, 164), 64, 3, 1, "same", "relu"),   # ragged in_q: flat-row x stage in wgrad, ragged stage mode in the forward
 ]
 
 
@@ -833,7 +833,7 @@ def test_tensor_core_dgrad_channels_first_vs_oracle(cnn, name, xs, F, k, d, pad,
 @pytest.mark.parametrize("name,xs,F,k,d,pad,act", [
     ("cl2_3x3_relu", (2, 6, 70, 128), 32, (3, 3), (1, 1), "same", "relu"),
     ("cl2_valid_d2", (1, 9, 40, 64), 64, (2, 3), (2, 1), "valid", "linear"),
-    ("cl2_ragged_q", (2, 5, 33, 20), 16, (3, 2), (1, 1), "same", "relu"),          # in_q = 5: channel-padding pre-pass
+    ("cl2_ragged_q", (2, 5, 33, 20), 16, (3, 2), (1, 1), "same", "relu"),          # in_q = 5: ragged channel count
 ], ids=lambda v: v if isinstance(v, str) else None)
 def test_tensor_core_backward_channels_last_conv2d_vs_oracle(cnn, name, xs, F, k, d, pad, act):
     """QuaternionConv2D channels_last backward: kernel gradient = one position-contraction launch per kernel row, data

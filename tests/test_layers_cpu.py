@@ -238,7 +238,7 @@ def test_abi_argument_errors_and_kernel_selection(native_lib):
     cfg2 = _native.make_conv_desc(1, 256, (256,), 40, 64, (3,), (1,), (1,), "same", "channels_last", "relu")
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cfg2)) == 1
     assert native_lib.qnn_dense_uses_tensor_cores(65536, 40, 64) == 1
-    assert native_lib.qnn_dense_uses_tensor_cores(32, 250, 128) == 1          # DECODA first layer: in_q % 4 != 0 -> padding pre-pass
+    assert native_lib.qnn_dense_uses_tensor_cores(32, 250, 128) == 1          # DECODA first layer: in_q % 4 != 0 -> ragged stage mode
     assert native_lib.qnn_dense_uses_tensor_cores(32, 250, 100) == 0          # q_units % 16 != 0
     tim = _native.make_conv_desc(1, 256, (256,), 41, 64, (3,), (1,), (1,), "same", "channels_last", "relu")
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(tim)) == 1      # cfg 3 first layer (TIMIT, in_q = 41)
@@ -299,7 +299,7 @@ def test_backward_kernel_selection_is_host_logic(native_lib):
     mk = _native.make_conv_desc
     # cfg 3 / 4 stack: inner conv layers (in_q = 64, F = 64): both gradients on tensor cores
     assert ask(mk(1, 256, (256,), 64, 64, (3,), (1,), (1,), "same", "channels_last", "relu")) == (1, 1)
-    # first layer (TIMIT in_q = 41): kernel gradient yes (padding pre-pass); data gradient would need F' = 41 filters
+    # first layer (TIMIT in_q = 41): kernel gradient yes (flat-row x stage); data gradient would need F' = 41 filters
     assert ask(mk(1, 256, (256,), 41, 64, (3,), (1,), (1,), "same", "channels_last", "relu")) == (0, 1)
     # cfg 2 (in_q = 40): dx needs a multiple of 16 "filters" in the transposed problem -> CUDA cores; dkernel on tensor cores
     assert ask(mk(1, 256, (256,), 40, 64, (3,), (1,), (1,), "same", "channels_last", "relu")) == (0, 1)
