@@ -4,7 +4,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libqnn_b200.so")
+# QNN_LIB_PATH: load another build of the same ABI (A/B timing of two builds on one box)
+LIB_PATH = os.environ.get("QNN_LIB_PATH") or os.path.join(os.path.dirname(_HERE), "lib", "libqnn_b200.so")
 
 PAD = {"valid": 0, "same": 1, "causal": 2}
 ACT = {None: 0, "linear": 0, "relu": 1, "tanh": 2, "sigmoid": 3, "hard_sigmoid": 4, "softplus": 5, "softsign": 6,

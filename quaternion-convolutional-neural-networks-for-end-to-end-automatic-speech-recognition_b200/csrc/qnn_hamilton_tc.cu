@@ -266,7 +266,9 @@ __device__ __forceinline__ void load_w_chunk(const TcParams& p, const uint8_t* w
     bulk_load(w_s + off, wp + (size_t)ft * p.w_img_bytes + off, n, bar);
 }
 
-template <bool CONJ, int ACT, bool X3>
+// RAGGED (in_q % 4 != 0) is a template parameter so that its converter path costs the common kernels nothing (as a runtime
+// branch it slowed cfg 2 by 2.8 %, A/B on one box); ragged layers are instantiated with the run-time activation only.
+template <bool CONJ, int ACT, bool X3, bool RAGGED>
 __global__ void __launch_bounds__(kThreads, 1)
 k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const TcParams p,
               const uint8_t* __restrict__ wp, const float* __restrict__ bias) {
@@ -471,8 +473,10 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     int kc = 32, shift = 0, kvalid = 32;
                     if (!p.flat) {
                         kc = min(32, p.in_q_pad - cch * 32);
-                        shift = (ca * p.in_q + cch * 32) & 3;   // ragged: channels the box starts below the chunk's first one
-                        kvalid = p.in_q - cch * 32;             // channels of the chunk that belong to this component
+                        if (RAGGED) {
+                            shift = (ca * p.in_q + cch * 32) & 3;   // channels the box starts below the chunk's first one
+                            kvalid = p.in_q - cch * 32;             // channels of the chunk that belong to this component
+                        }
                         if (++cch == p.n_chunks) { cch = 0; ++ca; }
                     }
                     if ((stage_i & 1) != cgrp) {  // the other group's stage: just advance the ring positions
@@ -507,7 +511,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                             const uint8_t* xrow = xb + row * 128u;
                             const uint32_t sw = row & 7u;
                             const uint32_t dst = t_a + lane_base + as_b * kASlotCols;
-                            if (p.ragged) {
+                            if (RAGGED) {
                                 // un-swizzled rows of 144 bytes; 4-byte loads at any channel shift (lanes 36 words apart:
                                 // 4-way bank conflicts, the price of skipping the padding pass over x).  Channels past the
                                 // component's end hold the NEXT component's data: zeroed (their weights are zero rows, but
@@ -771,14 +775,18 @@ __global__ void __launch_bounds__(256) k_pad_x(const float* __restrict__ x, floa
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams, const uint8_t*, const float*);
 
 template <bool X3>
-TcKernel pick_kernel_x(bool conj, int act) {
+TcKernel pick_kernel_x(bool conj, int act, bool ragged) {
+    if (ragged) return conj ? k_hamilton_tc<true, kActGeneric, X3, true> : k_hamilton_tc<false, kActGeneric, X3, true>;
     const int a = act == QNN_ACT_LINEAR ? kActLinear : (act == QNN_ACT_RELU ? kActRelu : kActGeneric);
-    if (conj) return a == kActLinear ? k_hamilton_tc<true, kActLinear, X3> : a == kActRelu ? k_hamilton_tc<true, kActRelu, X3>
-                                                                                            : k_hamilton_tc<true, kActGeneric, X3>;
-    return a == kActLinear ? k_hamilton_tc<false, kActLinear, X3> : a == kActRelu ? k_hamilton_tc<false, kActRelu, X3>
-                                                                                   : k_hamilton_tc<false, kActGeneric, X3>;
+    if (conj)
+        return a == kActLinear ? k_hamilton_tc<true, kActLinear, X3, false>
+                               : a == kActRelu ? k_hamilton_tc<true, kActRelu, X3, false> : k_hamilton_tc<true, kActGeneric, X3, false>;
+    return a == kActLinear ? k_hamilton_tc<false, kActLinear, X3, false>
+                           : a == kActRelu ? k_hamilton_tc<false, kActRelu, X3, false> : k_hamilton_tc<false, kActGeneric, X3, false>;
 }
-TcKernel pick_kernel(bool conj, int act, bool x3) { return x3 ? pick_kernel_x<true>(conj, act) : pick_kernel_x<false>(conj, act); }
+TcKernel pick_kernel(bool conj, int act, bool x3, bool ragged) {
+    return x3 ? pick_kernel_x<true>(conj, act, ragged) : pick_kernel_x<false>(conj, act, ragged);
+}
 
 unsigned long long* g_trace = nullptr;
 size_t g_trace_bytes = 0;
@@ -1002,7 +1010,7 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
             return QNN_E_CUDA;
         }
     }
-    TcKernel kern = pick_kernel(g.conj_w != 0, g.act, x3 != 0);
+    TcKernel kern = pick_kernel(g.conj_w != 0, g.act, x3 != 0, pl.ragged != 0);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
     const int grid = std::min(p.n_tiles, num_sms());
     p.trace = (g_trace && g_trace_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace : nullptr;
