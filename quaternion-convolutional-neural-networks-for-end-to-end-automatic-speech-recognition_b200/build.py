@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "lib", "libqnn_b200.so")
+LIB = os.environ.get("QNN_BUILD_LIB") or os.path.join(HERE, "lib", "libqnn_b200.so")  # QNN_BUILD_LIB: build a variant elsewhere
 SOURCES = ["qnn_api.cu", "qnn_general.cu", "qnn_smallk.cu", "qnn_hamilton_tc.cu", "qnn_hamilton_tc2d.cu", "qnn_wgrad_tc.cu"]
 HEADERS = ["qnn_common.h", "qnn_ptx.cuh", "qnn_tmap.h", os.path.join("..", "..", "include", "qnn.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -28,13 +28,15 @@ def build(force=False, verbose=False):
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     flags = list(NVCC_FLAGS)
+    if os.environ.get("QNN_NVCC_DEFINES"):  # experiment builds: e.g. QNN_NVCC_DEFINES="-DQNN_SLEEP_NS=32 -DQNN_WCHUNK_BARS=1"
+        flags += os.environ["QNN_NVCC_DEFINES"].split()
     if os.environ.get("QNN_SPIN_LIMIT"):  # debug builds: bounded mbarrier waits that trap instead of hanging the GPU
         flags.append("-DQNN_SPIN_LIMIT=" + os.environ["QNN_SPIN_LIMIT"])
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
     objs = []
     procs = []
     for s in SOURCES:
-        o = os.path.join(HERE, "lib", s.replace(".cu", ".o"))
+        o = os.path.join(os.path.dirname(LIB), s.replace(".cu", ".o"))
         objs.append(o)
         cmd = [nvcc] + flags + (["--use_fast_math"] if s in FAST_MATH else []) + ["-c", os.path.join(CSRC, s), "-o", o]
         procs.append((cmd, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))

@@ -66,15 +66,18 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // Polling with back-off for waits that are expected to be long (keeps the warp off the issue slots).
+#ifndef QNN_SLEEP_NS
+#define QNN_SLEEP_NS 128
+#endif
 __device__ __forceinline__ void mbar_wait_sleep(uint64_t* bar, uint32_t parity) {
 #if QNN_SPIN_LIMIT
     for (uint64_t i = 0; i < (uint64_t)QNN_SPIN_LIMIT / 16; ++i) {
         if (mbar_try_wait(bar, parity)) return;
-        __nanosleep(128);
+        __nanosleep(QNN_SLEEP_NS);
     }
     __trap();
 #else
-    while (!mbar_try_wait(bar, parity)) __nanosleep(128);
+    while (!mbar_try_wait(bar, parity)) __nanosleep(QNN_SLEEP_NS);
 #endif
 }
 
