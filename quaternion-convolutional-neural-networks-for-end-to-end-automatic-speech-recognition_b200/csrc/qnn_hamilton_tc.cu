@@ -189,11 +189,15 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_
         : "memory");
 }
 
+// the run-time activations (tanh, sigmoid, elu, ...) as ONE out-of-line function: inlined 64 times per epilogue thread they
+// made each generic-activation kernel 31 k instructions and dominated the library's compile time
+__device__ __noinline__ float act_apply_call(float v, int act) { return act_apply(v, act); }
+
 template <int ACT>
 __device__ __forceinline__ float activate(float v, int act_rt) {
     if (ACT == kActLinear) return v;
     if (ACT == kActRelu) return fmaxf(v, 0.f);
-    return act_apply(v, act_rt);
+    return act_apply_call(v, act_rt);
 }
 
 // Operand conversion.  TF32: "add half an ulp, let the tensor core truncate" = round to nearest, one integer add per
@@ -267,7 +271,7 @@ __device__ __forceinline__ void load_w_chunk(const TcParams& p, const uint8_t* w
 }
 
 // RAGGED (in_q % 4 != 0) is a template parameter so that its converter path costs the common kernels nothing (as a runtime
-// branch it slowed cfg 2 by 2.8 %, A/B on one box); ragged layers are instantiated with the run-time activation only.
+// branch it slowed cfg 2 by 2.8 %, A/B on one box).
 template <bool CONJ, int ACT, bool X3, bool RAGGED>
 __global__ void __launch_bounds__(kThreads, 1)
 k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const TcParams p,
@@ -774,18 +778,18 @@ __global__ void __launch_bounds__(256) k_pad_x(const float* __restrict__ x, floa
 
 typedef void (*TcKernel)(const CUtensorMap, const CUtensorMap, const TcParams, const uint8_t*, const float*);
 
-template <bool X3>
-TcKernel pick_kernel_x(bool conj, int act, bool ragged) {
-    if (ragged) return conj ? k_hamilton_tc<true, kActGeneric, X3, true> : k_hamilton_tc<false, kActGeneric, X3, true>;
+template <bool X3, bool RAGGED>
+TcKernel pick_kernel_xr(bool conj, int act) {
     const int a = act == QNN_ACT_LINEAR ? kActLinear : (act == QNN_ACT_RELU ? kActRelu : kActGeneric);
     if (conj)
-        return a == kActLinear ? k_hamilton_tc<true, kActLinear, X3, false>
-                               : a == kActRelu ? k_hamilton_tc<true, kActRelu, X3, false> : k_hamilton_tc<true, kActGeneric, X3, false>;
-    return a == kActLinear ? k_hamilton_tc<false, kActLinear, X3, false>
-                           : a == kActRelu ? k_hamilton_tc<false, kActRelu, X3, false> : k_hamilton_tc<false, kActGeneric, X3, false>;
+        return a == kActLinear ? k_hamilton_tc<true, kActLinear, X3, RAGGED>
+                               : a == kActRelu ? k_hamilton_tc<true, kActRelu, X3, RAGGED> : k_hamilton_tc<true, kActGeneric, X3, RAGGED>;
+    return a == kActLinear ? k_hamilton_tc<false, kActLinear, X3, RAGGED>
+                           : a == kActRelu ? k_hamilton_tc<false, kActRelu, X3, RAGGED> : k_hamilton_tc<false, kActGeneric, X3, RAGGED>;
 }
 TcKernel pick_kernel(bool conj, int act, bool x3, bool ragged) {
-    return x3 ? pick_kernel_x<true>(conj, act, ragged) : pick_kernel_x<false>(conj, act, ragged);
+    if (ragged) return x3 ? pick_kernel_xr<true, true>(conj, act) : pick_kernel_xr<false, true>(conj, act);
+    return x3 ? pick_kernel_xr<true, false>(conj, act) : pick_kernel_xr<false, false>(conj, act);
 }
 
 unsigned long long* g_trace = nullptr;

@@ -134,11 +134,15 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                  : "memory");
 }
 
+// the run-time activations (tanh, sigmoid, elu, ...) as ONE out-of-line function: inlined 64 times per epilogue thread they
+// made each generic-activation kernel 31 k instructions and dominated the library's compile time
+__device__ __noinline__ float act_apply_call(float v, int act) { return act_apply(v, act); }
+
 template <int ACT>
 __device__ __forceinline__ float activate(float v, int act_rt) {
     if (ACT == kActLinear) return v;
     if (ACT == kActRelu) return fmaxf(v, 0.f);
-    return act_apply(v, act_rt);
+    return act_apply_call(v, act_rt);
 }
 
 __device__ __forceinline__ void split_tf32(uint32_t v, uint32_t& hi, uint32_t& lo) {
