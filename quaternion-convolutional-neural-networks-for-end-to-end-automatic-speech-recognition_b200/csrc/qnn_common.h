@@ -113,6 +113,7 @@ struct Tc2dPlan {
     int wbox;        // x box per channel: one row of 128 + halo positions (rounded up to 4)
     int xshift;      // columns the box starts left of the first tap (16-byte alignment of the TMA start)
     int pad_rows;    // channels_first row length % 4 != 0: x / y go through row-padded scratch copies
+    int pad_q;       // in_q % 8 != 0: x goes through a quaternion-channel padding pre-pass (zero channels)
     int x_stages;
     size_t x_stage_bytes, smem_bytes;
     size_t packed_bytes;  // packed kernel image (hi [+ lo] blocks per (filter tile, 8-channel chunk, tap))

@@ -538,7 +538,7 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
 // when `flip`)  ->  wp[ft][qc][tap][part][c][kg][f][q%4]  (q = qc*8 + kg*4 + q%4): the K-major, un-swizzled core-matrix image of
 // each (filter tile, 8-channel chunk, tap) block, contiguous; part 0 = rn_tf32(v), part 1 (3xTF32 only) = rn_tf32(v - hi).
 // The strides select the forward image or the data gradient's transposed, tap-flipped one (q and f swap roles).
-__global__ void __launch_bounds__(256) k_pack_w2d(const float* __restrict__ w, float4* __restrict__ wp, int taps, int Q,
+__global__ void __launch_bounds__(256) k_pack_w2d(const float* __restrict__ w, float4* __restrict__ wp, int taps, int Q, int Qs,
                                                   int F, int Fp, int parts, long long s_tap, long long s_q, long long s_c,
                                                   long long s_f, int flip) {
     const int n_qc = Q >> 3, n_ft = F / Fp;
@@ -561,8 +561,8 @@ __global__ void __launch_bounds__(256) k_pack_w2d(const float* __restrict__ w, f
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const uint32_t v = __float_as_uint(__ldg(src + (long long)j * s_q));
-            if (parts == 1) {
+            const uint32_t v = (qc * 8 + kg * 4 + j < Qs) ? __float_as_uint(__ldg(src + (long long)j * s_q)) : 0u;  // rows past
+            if (parts == 1) {                                                          // the layer's in_q: zero (channel padding)
                 o[j] = v + 0x1000u;
             } else {
                 uint32_t hi, lo;
@@ -572,6 +572,33 @@ __global__ void __launch_bounds__(256) k_pack_w2d(const float* __restrict__ w, f
         }
         wp[i] = make_float4(__uint_as_float(o[0]), __uint_as_float(o[1]), __uint_as_float(o[2]), __uint_as_float(o[3]));
     }
+}
+
+// quaternion-channel padding for in_q % 8 != 0: x viewed as [outer][q_in][inner] -> [outer][q_out][inner], new channels
+// zero.  channels_first: outer = sample x component, inner = positions; channels_last: outer = position x component,
+// inner = 1.
+__global__ void __launch_bounds__(256) k_pad_q(const float* __restrict__ in, float* __restrict__ out, long long outer, int q_in,
+                                               int q_out, long long inner) {
+    const long long total = outer * q_out * inner;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const long long in_i = i % inner, t = i / inner;
+        const int q = (int)(t % q_out);
+        const long long o = t / q_out;
+        out[i] = q < q_in ? __ldg(in + (o * q_in + q) * inner + in_i) : 0.f;
+    }
+}
+
+int pad_q(const float* in, float* out, long long outer, int q_in, int q_out, long long inner, cudaStream_t st) {
+    const long long total = outer * q_out * inner;
+    if (total == 0) return QNN_OK;
+    k_pad_q<<<(unsigned)std::min<long long>((total + 255) / 256, 16LL * num_sms()), 256, 0, st>>>(in, out, outer, q_in, q_out, inner);
+    count_launch();
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_error("channel padding launch failed: %s", cudaGetErrorString(e));
+        return QNN_E_CUDA;
+    }
+    return QNN_OK;
 }
 
 // [rows][w_in] -> [rows][w_out] (w_out > w_in: zero-filled tail = padding; w_out < w_in: tail dropped)
@@ -637,7 +664,10 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3) {
     // convolution; a dense layer's own forward (conj table + activation) stays on the resident-sub-filter kernel
     if (g.conj_w && (g.dense || g.act != QNN_ACT_LINEAR)) return no("dense-layer forward (transposed sign table with an activation)");
     if (g.s[0] != 1 || g.s[1] != 1 || g.s[2] != 1) return no("stride != 1");
-    if (g.in_q % 8) return no("in_q not a multiple of 8");
+    // in_q % 8 != 0 (the TIMIT model's first layer has ONE quaternion input channel, interspeech_model.py:97): x goes through
+    // a channel-padding pre-pass to the next multiple of 8 (zero channels; the image gets zero rows)
+    pl.pad_q = (g.in_q % 8) ? 1 : 0;
+    const int Qp = (g.in_q + 7) & ~7;
     if (g.F % 32) return no("filters not a multiple of 32");
     // channels_first rows whose length is not a multiple of 4 (TMA strides must be multiples of 16 bytes; the reference's
     // TIMIT model has a free time axis, models/interspeech_model.py:81) run on row-padded scratch copies of x and y
@@ -665,7 +695,7 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3) {
     pl.x_stages = (int)std::min<size_t>(kMaxXStages, (kSmemLimit - fixed) / stage);
     pl.x_stage_bytes = stage;
     pl.smem_bytes = fixed + (size_t)pl.x_stages * stage;
-    pl.packed_bytes = (size_t)g.k[0] * g.k[1] * g.k[2] * g.in_q * 4 * g.F * sizeof(float) * (x3 ? 2 : 1);
+    pl.packed_bytes = (size_t)g.k[0] * g.k[1] * g.k[2] * Qp * 4 * g.F * sizeof(float) * (x3 ? 2 : 1);
     pl.why = "";
     return pl;
 }
@@ -687,15 +717,15 @@ int tc2d_pack(const Geom& g, int rank, int x3, int transposed, const float* w, v
         set_error("packed kernel image must be 16-byte aligned and the kernel non-NULL");
         return QNN_E_INVALID;
     }
-    const int taps = g.k[0] * g.k[1] * g.k[2], Q = g.in_q, F = g.F, parts = x3 ? 2 : 1;
+    const int taps = g.k[0] * g.k[1] * g.k[2], Qs = g.in_q, Q = (g.in_q + 7) & ~7, F = g.F, parts = x3 ? 2 : 1;
     long long s_tap, s_q, s_c, s_f;
     if (!transposed) {
-        s_tap = (long long)Q * 4 * F, s_q = 4LL * F, s_c = F, s_f = 1;
+        s_tap = (long long)Qs * 4 * F, s_q = 4LL * F, s_c = F, s_f = 1;
     } else {
-        s_tap = (long long)F * 4 * Q, s_q = 1, s_c = Q, s_f = 4LL * Q;
+        s_tap = (long long)F * 4 * Qs, s_q = 1, s_c = Qs, s_f = 4LL * Qs;
     }
     const int total = pl.n_ftiles * (Q / 8) * taps * parts * 8 * pl.f_tile;
-    k_pack_w2d<<<std::min((total + 255) / 256, 4 * num_sms()), 256, 0, st>>>(w, static_cast<float4*>(packed), taps, Q, F,
+    k_pack_w2d<<<std::min((total + 255) / 256, 4 * num_sms()), 256, 0, st>>>(w, static_cast<float4*>(packed), taps, Q, Qs, F,
                                                                           pl.f_tile, parts, s_tap, s_q, s_c, s_f,
                                                                           transposed ? 1 : 0);
     count_launch();
@@ -713,6 +743,20 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
     if (!pl.ok) {
         set_error("channels_first tensor-core kernel does not take this shape: %s", pl.why);
         return QNN_E_UNSUPPORTED;
+    }
+    if (pl.pad_q) {
+        // in_q % 8 != 0: zero-padded quaternion channels in a scratch copy of x; the packed image already has the zero rows
+        Geom gp = g;
+        gp.in_q = (g.in_q + 7) & ~7;
+        const long long S = (long long)g.in_sp[0] * g.in_sp[1] * g.in_sp[2];
+        float* xq = nullptr;
+        int rc = stream_scratch_alloc(reinterpret_cast<void**>(&xq), (size_t)g.batch * 4 * gp.in_q * S * sizeof(float), st);
+        if (!rc)
+            rc = g.channels_first ? pad_q(x, xq, (long long)g.batch * 4, g.in_q, gp.in_q, S, st)
+                                  : pad_q(x, xq, (long long)g.batch * S * 4, g.in_q, gp.in_q, 1, st);
+        if (!rc) rc = tc2d_forward_packed(gp, rank, x3, xq, packed, bias, y, st);
+        if (xq) cudaFreeAsync(xq, st);
+        return rc;
     }
     if (pl.pad_rows) {
         // ragged rows: x -> row-padded copy, kernel on the padded geometry (the extra input columns are zeros = the

@@ -606,9 +606,9 @@ def _tc_cf_shapes():
     lib = _native.lib()
     rng = np.random.default_rng(7)
     out = []
-    while len(out) < 20:
+    while len(out) < 28:
         rank = int(rng.choice([1, 2, 2, 2]))
-        in_q = int(rng.choice([8, 16, 24, 40]))
+        in_q = int(rng.choice([1, 5, 8, 12, 16, 24, 40, 41]))              # in_q % 8 != 0: channel-padding pre-pass
         F = int(rng.choice([32, 64, 96, 128]))
         k = tuple(int(v) for v in rng.integers(1, 5, size=rank))
         d = tuple(int(v) for v in rng.integers(1, 3, size=rank))

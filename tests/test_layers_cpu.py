@@ -253,6 +253,9 @@ def test_abi_argument_errors_and_kernel_selection(native_lib):
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cfg5)) == 1        # BASELINE config 5
     cf_odd = _native.make_conv_desc(2, 8, (16, 18), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu")
     assert native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(cf_odd)) == 1      # row length % 4 != 0: row-padded scratch copies
+    timit_1 = _native.make_conv_desc(2, 4, (41, 200), 1, 32, (3, 5), (1, 1), (1, 1), "same", "channels_first", "linear")
+    assert native_lib.qnn_conv_forward_kernel(ctypes.byref(timit_1)) == _native.KERNEL_TC_CF   # interspeech_model.py:97: ONE
+    #                                                  quaternion input channel, padded to 8 in a pre-pass for the tensor cores
     timit_t = _native.make_conv_desc(2, 4, (41, 333), 32, 32, (3, 5), (1, 1), (1, 1), "same", "channels_first", "linear")
     assert native_lib.qnn_conv_forward_kernel(ctypes.byref(timit_t)) == _native.KERNEL_TC_CF   # free time axis, T = 333
     cl2 = _native.make_conv_desc(2, 8, (16, 17), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_last", "relu")
@@ -379,7 +382,7 @@ def test_packed_image_queries_agree_with_kernel_selection(native_lib):
         nbytes = native_lib.qnn_conv_packed_bytes(ctypes.byref(d), _native.PACK_FORWARD)
         assert (nbytes > 0) == (kern in tc), (rank, cf, in_q, F, k, sp, act, math, kern, nbytes)
         if kern in tc:
-            per_part = int(np.prod(k)) * (-(-in_q // 8) * 8 if kern == _native.KERNEL_TC_ROWS else in_q) * 4 * F * 4
+            per_part = int(np.prod(k)) * (-(-in_q // 8) * 8) * 4 * F * 4     # both images pad in_q to a multiple of 8
             assert nbytes == per_part * (2 if math == "3xtf32" else 1)
     for in_q, q_units in ((40, 64), (128, 128), (250, 128), (64, 16), (3, 64), (16, 100)):
         for math in ("tf32", "3xtf32", "fp32"):
