@@ -213,6 +213,9 @@ __device__ __forceinline__ void split_tf32(uint32_t v, uint32_t& hi, uint32_t& l
 template <int ACT>
 __device__ __forceinline__ void stage_chunk(const uint32_t (&v)[32], const float* bias32, uint8_t* st, int r, int act_rt) {
     const float4* bs = reinterpret_cast<const float4*>(bias32);
+#ifdef QNN_DIAG_NOSTAGE  // timing experiment (wrong results): the epilogue does not write its staging tiles
+    if (v[0] != 0x7fc12345u) return;
+#endif
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
         const float4 bv = bs[j];
@@ -560,12 +563,19 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                                     uint32_t u[16];
 #pragma unroll
                                     for (int c4 = 0; c4 < 4; ++c4) {
+#ifdef QNN_DIAG_NOLOAD  // timing experiment (wrong results): the converters do not read shared memory
+                                        const uint4 v = make_uint4(row, sw, (uint32_t)(h * 4 + c4), (uint32_t)tb);
+#else
                                         const uint4 v = *reinterpret_cast<const uint4*>(xrow + (((h * 4 + c4) ^ sw) << 4));
+#endif
                                         u[4 * c4 + 0] = rn_tf32(v.x);
                                         u[4 * c4 + 1] = rn_tf32(v.y);
                                         u[4 * c4 + 2] = rn_tf32(v.z);
                                         u[4 * c4 + 3] = rn_tf32(v.w);
                                     }
+#ifdef QNN_DIAG_NOTMEMST  // timing experiment (wrong results): the converters do not write the A slots
+                                    if (u[0] == 0x7fc12345u)
+#endif
                                     tmem_st16_nc(dst + h * 16, u);
                                 }
                             } else {

@@ -10,7 +10,7 @@ cd $GRAFT_REPO_ROOT
 run() {  # $1 = workload, $2 = lib path or ""
   QNN_LIB_PATH=$2 timeout 200 python bench.py --workload $1 --steps 50 --warmup 5 --no-secondary 2>/dev/null | python -c "import sys,json; d=json.loads(sys.stdin.read().splitlines()[-1]); print('%.5f %.5f' % (d['ms_per_step'], d['sustained']['ms_per_step_median']))"
 }
-for i in 1 2 3; do
+for i in $(seq 1 ${ROUNDS:-3}); do
   for wl in cfg2 dense; do
     line="$wl run $i: default $(run $wl '')"
     for v in "$@"; do line="$line | ${v%%=*} $(run $wl $GRAFT_REPO_ROOT/${v#*=})"; done
