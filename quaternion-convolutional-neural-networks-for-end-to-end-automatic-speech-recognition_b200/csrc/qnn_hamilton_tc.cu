@@ -108,6 +108,8 @@ struct TcParams {
     uint32_t w_chunk;      // bulk-copy granule of the image load (multiple of 16 bytes)
     int handshake;         // taps >= A slots: converter groups hand over stage by stage (see the converter role)
     int n_st;              // output staging tiles: 2 (group pairs take turns), 4 (one per epilogue group) or 8 (one per chunk)
+    int full_rounds, rem;  // work of a pass: full_rounds tiles per CTA (tile = cta + k * grid), then `rem` tiles in a last round
+    int split;             // the last round's tiles are split along the filters, see WorkItem
 };
 
 struct __align__(8) Barriers {
@@ -145,6 +147,31 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                      smem_u32(smem_dst)),
                  "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
                  : "memory");
+}
+
+// Work items of a CTA in one pass: `full_rounds` whole tiles, then the last, partial round.  When that round would keep at
+// most half of the CTAs busy (and the filter tile is 64 wide) its tiles are SPLIT along the filters: CTA i takes filters
+// [32 (i & 1), +32) of tile i / 2 -- N = 32 MMAs into 4 x 32 accumulator columns (N = 32 issues at ~29 cycles instead of
+// ~37: 0.77 of a whole tile), half the output stores (the tail of the kernel is the last tile's stores at the SM's
+// ~28 B/clk write port), x read twice.  Every output element keeps its accumulation order: results are bit-identical.
+struct WorkItem {
+    int tile, f0, fe;  // tile, first filter of the tile's filter range, filters per component (f_tile or 32)
+};
+__device__ __forceinline__ int n_items(const TcParams& p) {
+    return p.full_rounds + ((int)blockIdx.x < (p.split ? 2 * p.rem : p.rem) ? 1 : 0);
+}
+__device__ __forceinline__ WorkItem work_item(const TcParams& p, int k) {
+    WorkItem w;
+    if (k < p.full_rounds || !p.split) {
+        w.tile = (int)blockIdx.x + k * (int)gridDim.x;
+        w.f0 = 0;
+        w.fe = p.f_tile;
+    } else {
+        w.tile = p.full_rounds * (int)gridDim.x + ((int)blockIdx.x >> 1);
+        w.f0 = ((int)blockIdx.x & 1) * 32;
+        w.fe = 32;
+    }
+    return w;
 }
 
 // Walks the x stages of a tile without integer division: for every stage the number of k-steps (8 channels each)
@@ -232,20 +259,20 @@ __device__ __forceinline__ void stage_chunk(const uint32_t (&v)[32], const float
 // chunk (bias + activation), both groups meet, its thread 0 issues the TMA store and waits until the tile has been read.
 template <int ACT>
 __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn, int which, int pair, int turn, int r,
-                                          int n_out, int Fp, int ft, int t0, int b, const TcParams& p,
+                                          int n_out, int Fp, int fe, int f0, int ft, int t0, int b, const TcParams& p,
                                           const float* bias_s, uint8_t* st, const CUtensorMap* tmy) {
     const int c_act = pair + 2 * act_turn + 4 * which;  // 32-column chunk handled in this phase on this staging tile
     if (c_act >= n_out) return;                        // uniform across the pair
     const bool mine = turn == act_turn;
+    // accumulator column c*32 -> component (c*32)/fe, filter f0 + (c*32)%fe of this pass' filter tile
+    const int col = c_act * 32, comp = col / fe, fi = f0 + col % fe;
     if (mine) {
-        stage_chunk<ACT>(v, bias_s + c_act * 32, st, r, p.act);
+        stage_chunk<ACT>(v, bias_s + comp * Fp + fi, st, r, p.act);
         fence_proxy_async_smem();
     }
     named_bar_sync(5 + pair, 256);
     if (mine && r == 0) {
-        // accumulator column c*32 -> output channel: component (c*32)/Fp, filter ft*Fp + (c*32)%Fp
-        const int col = c_act * 32;
-        tma_store_3d(tmy, st, (col / Fp) * p.F + ft * Fp + (col % Fp), t0, b);
+        tma_store_3d(tmy, st, comp * p.F + ft * Fp + fi, t0, b);
         tma_store_commit();
         tma_store_wait_read<0>();  // the staging tile may now be overwritten by the partner group
     }
@@ -325,11 +352,10 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         __syncwarp();
         asm volatile("griddepcontrol.wait;" ::: "memory");  // x / the packed kernel may be the previous kernel's output
         const int lane = tid & 31;
-        const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-        const int total_stages = my_tiles * p.n_stages;
+        const int total_stages = n_items(p) * p.n_stages;
         if (lane < p.x_stages && lane < total_stages) {
             const int j = lane / p.n_stages, s = lane - j * p.n_stages;
-            const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+            const int tile = work_item(p, j).tile;
             const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
             load_x_stage(p, &tmx, x_s + (size_t)lane * p.x_stage_bytes, &bars->x_full[lane], s, t0 * p.stride - p.pad_lo, b);
             if (lane == 0) trace(p, kTrFirstTma);
@@ -380,8 +406,8 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 }
             }
             __syncwarp();
-            const uint32_t idesc_pos = idesc_tf32(kTileM, Fp, false, false);
-            const uint32_t idesc_neg = idesc_tf32(kTileM, Fp, false, true);
+            const uint32_t idesc_pos_f = idesc_tf32(kTileM, Fp, false, false), idesc_neg_f = idesc_tf32(kTileM, Fp, false, true);
+            const uint32_t idesc_pos_h = idesc_tf32(kTileM, 32, false, false), idesc_neg_h = idesc_tf32(kTileM, 32, false, true);
             const uint64_t d0 = smem_desc_kmajor_noswz(smem_u32(w_s), (uint32_t)Fp * 16u, 128);
             const uint32_t w_lo = (uint32_t)d0, desc_hi = (uint32_t)(d0 >> 32);
             const uint32_t sub_stride = (uint32_t)KQ * Fp;  // descriptor-lo units (16 B) between sub-filters
@@ -390,8 +416,12 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             constexpr uint32_t neg_table = CONJ ? kNegDense : kNegConv;
             mbar_wait(&bars->w_ready, ft & 1);  // this pass' image has landed (async-proxy writes, read by the tensor core)
             if (warp == kWarpIssuer0 && elected && ft == 0) trace(p, kTrWReady);
-            int tcount = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
+            const int items = n_items(p);
+            for (int tcount = 0; tcount < items; ++tcount) {
+                const WorkItem wi = work_item(p, tcount);
+                const uint32_t idesc_pos = wi.fe == Fp ? idesc_pos_f : idesc_pos_h;
+                const uint32_t idesc_neg = wi.fe == Fp ? idesc_neg_f : idesc_neg_h;
+                const uint32_t d_col = t_acc + b * wi.fe;  // this issuer's accumulator: 4 x fe compact columns
                 mbar_wait(&bars->acc_empty, accph ^ 1);
                 tc_fence_after_sync();
                 if (warp == kWarpIssuer0 && elected && ft == 0) trace(p, kTrTile0 + 5 * tcount);
@@ -410,7 +440,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                         if (elected) {
                             if (warp == kWarpIssuer0 && ft == 0 && tcount == 0 && s == 0 && tap == 0) trace(p, kTrFirstA);
                             const uint32_t a_col = t_a + as * kASlotCols;
-                            const uint32_t tap_lo = w_lo + tap * tap_stride;
+                            const uint32_t tap_lo = w_lo + tap * tap_stride + wi.f0;  // (a filter row is 16 bytes)
 #pragma unroll
                             for (int ks = 0; ks < 4; ++ks) {
                                 if (ks >= nks) break;
@@ -420,11 +450,11 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                                 const uint32_t idesc = ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos;
                                 if (X3) {
                                     // small terms first, then the leading one: x_lo.w_hi + x_hi.w_lo + x_hi.w_hi
-                                    mma_ts(t_acc + b * Fp, a_col + 32 + ks * 8, k_lo, desc_hi, idesc, accumulate);
-                                    mma_ts(t_acc + b * Fp, a_col + ks * 8, k_lo + lo_off, desc_hi, idesc, 1);
-                                    mma_ts(t_acc + b * Fp, a_col + ks * 8, k_lo, desc_hi, idesc, 1);
+                                    mma_ts(d_col, a_col + 32 + ks * 8, k_lo, desc_hi, idesc, accumulate);
+                                    mma_ts(d_col, a_col + ks * 8, k_lo + lo_off, desc_hi, idesc, 1);
+                                    mma_ts(d_col, a_col + ks * 8, k_lo, desc_hi, idesc, 1);
                                 } else {
-                                    mma_ts(t_acc + b * Fp, a_col + ks * 8, k_lo, desc_hi, idesc, accumulate);
+                                    mma_ts(d_col, a_col + ks * 8, k_lo, desc_hi, idesc, accumulate);
                                 }
                                 accumulate = 1;
                             }
@@ -456,12 +486,12 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             const int cgrp = (tid - kWarpConv0 * 32) >> 7;
             const int r = (tid - kWarpConv0 * 32) & 127;
             const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
-            const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-            const int total_stages = my_tiles * p.n_stages;  // of this CTA in this pass
+            const int items = n_items(p);
+            const int total_stages = items * p.n_stages;  // of this CTA in this pass
             // issue the x load of this pass' stage number `i` (counted over this CTA's tiles) into ring slot `slot`
             auto issue_stage = [&](int i, uint32_t slot) {
                 const int j = i / p.n_stages, s = i - j * p.n_stages;
-                const int tile = (int)blockIdx.x + j * (int)gridDim.x;
+                const int tile = work_item(p, j).tile;
                 const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
                 load_x_stage(p, &tmx, x_s + (size_t)slot * p.x_stage_bytes, &bars->x_full[slot], s, t0 * p.stride - p.pad_lo, b);
             };
@@ -473,8 +503,8 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     issue_stage(i, slot >= (uint32_t)p.x_stages ? slot - p.x_stages : slot);
             }
             int stage_i = 0;  // stage number inside this pass
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-                const bool detail = r == 0 && ft == 0 && tile == (int)(blockIdx.x + gridDim.x);
+            for (int it = 0; it < items; ++it) {
+                const bool detail = r == 0 && ft == 0 && it == 1;
                 int cch = 0, ca = 0;  // padded mode: chunk inside the component, component
                 for (int s = 0; s < p.n_stages; ++s, ++stage_i) {
                     int kc = 32, shift = 0, kvalid = 32;
@@ -501,8 +531,10 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     if (detail && s < 8) trace(p, kTrConv + 8 * s);
                     if (r == 0 && stage_i == 0 && ft == 0) trace(p, kTrFirstX);
                     const uint8_t* xb = x_s + (size_t)xs * p.x_stage_bytes;
-                    for (int tap0 = 0; tap0 < p.taps; tap0 += kMaxTapBatch) {
-                        const int nb = min(kMaxTapBatch, p.taps - tap0);
+                    // (the kernel's very first stage goes tap by tap: the first MMAs start one tap's conversion after x landed)
+                    const int batch = (stage_i == 0 && ft == 0) ? 1 : kMaxTapBatch;
+                    for (int tap0 = 0, nb = 0; tap0 < p.taps; tap0 += nb) {
+                        nb = min(batch, p.taps - tap0);
                         // all slots of the batch must be free before the first store; one fence for the batch
                         uint32_t as_b = as, aph_b = aph;
                         for (int tb = 0; tb < nb; ++tb) {
@@ -622,10 +654,12 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             const int grp = e >> 7, r = e & 127;
             const int pair = grp & 1, turn = grp >> 1;
             const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
-            const int n_out = (4 * Fp) >> 5;  // 32-column chunks per tile: 2, 4, 6 or 8
             uint8_t* st = y_s + pair * kStagingBytes;
-            int tcount = 0;
-            for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, ++tcount) {
+            const int items = n_items(p);
+            for (int tcount = 0; tcount < items; ++tcount) {
+                const WorkItem wi = work_item(p, tcount);
+                const int tile = wi.tile, fe = wi.fe, f0 = wi.f0;
+                const int n_out = (4 * fe) >> 5;  // 32-column chunks of this item: 2, 4, 6 or 8
                 const int b = tile / p.tiles_per_seq, t0 = (tile % p.tiles_per_seq) * kTileM;
                 mbar_wait_sleep(&bars->acc_full, accph);  // long wait: back off, leave the issue slots to the other roles
                 tc_fence_after_sync();
@@ -638,7 +672,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 tc_fence_before_sync();
                 mbar_arrive(&bars->acc_empty);  // accumulators are in registers: the next tile's MMAs may start
                 if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 3);
-                if (p.n_st == 2 && tile + (int)gridDim.x >= p.n_tiles && ft == p.n_ftiles - 1 &&
+                if (p.n_st == 2 && tcount == items - 1 && ft == p.n_ftiles - 1 &&
                     (size_t)p.x_stages * p.x_stage_bytes >= 4 * (size_t)kStagingBytes) {
                     // Last tile of this CTA in the last pass: every x stage has been consumed and every MMA has read its
                     // sub-filters, so the x ring and the sub-filter region are free: each group gets two private staging
@@ -654,15 +688,15 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                             if (r == 0) tma_store_wait_read<0>();
                             named_bar_sync(1 + grp, 128);
                         }
+                        const int col = c * 32, comp = col / fe, fi = f0 + col % fe;
                         if (which == 0)
-                            stage_chunk<ACT>(v0, bias_s + c * 32, sto, r, p.act);
+                            stage_chunk<ACT>(v0, bias_s + comp * Fp + fi, sto, r, p.act);
                         else
-                            stage_chunk<ACT>(v1, bias_s + c * 32, sto, r, p.act);
+                            stage_chunk<ACT>(v1, bias_s + comp * Fp + fi, sto, r, p.act);
                         fence_proxy_async_smem();
                         named_bar_sync(1 + grp, 128);
                         if (r == 0) {
-                            const int col = c * 32;
-                            tma_store_3d(&tmy, sto, (col / Fp) * p.F + ft * Fp + (col % Fp), t0, b);
+                            tma_store_3d(&tmy, sto, comp * p.F + ft * Fp + fi, t0, b);
                             tma_store_commit();
                         }
                     }
@@ -688,15 +722,15 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                                 tma_store_wait_read<0>();
                         }
                         named_bar_sync(1 + grp, 128);
+                        const int col = c * 32, comp = col / fe, fi = f0 + col % fe;
                         if (which == 0)
-                            stage_chunk<ACT>(v0, bias_s + c * 32, sto, r, p.act);
+                            stage_chunk<ACT>(v0, bias_s + comp * Fp + fi, sto, r, p.act);
                         else
-                            stage_chunk<ACT>(v1, bias_s + c * 32, sto, r, p.act);
+                            stage_chunk<ACT>(v1, bias_s + comp * Fp + fi, sto, r, p.act);
                         fence_proxy_async_smem();
                         named_bar_sync(1 + grp, 128);
                         if (r == 0) {
-                            const int col = c * 32;
-                            tma_store_3d(&tmy, sto, (col / Fp) * p.F + ft * Fp + (col % Fp), t0, b);
+                            tma_store_3d(&tmy, sto, comp * p.F + ft * Fp + fi, t0, b);
                             tma_store_commit();
                         }
                     }
@@ -705,10 +739,10 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     continue;
                 }
                 // four lock-step phases on this pair's staging tile: (turn 0, chunk set 0), (1, 0), (0, 1), (1, 1)
-                epi_phase<ACT>(v0, 0, 0, pair, turn, r, n_out, Fp, ft, t0, b, p, bias_s, st, &tmy);
-                epi_phase<ACT>(v0, 1, 0, pair, turn, r, n_out, Fp, ft, t0, b, p, bias_s, st, &tmy);
-                epi_phase<ACT>(v1, 0, 1, pair, turn, r, n_out, Fp, ft, t0, b, p, bias_s, st, &tmy);
-                epi_phase<ACT>(v1, 1, 1, pair, turn, r, n_out, Fp, ft, t0, b, p, bias_s, st, &tmy);
+                epi_phase<ACT>(v0, 0, 0, pair, turn, r, n_out, Fp, fe, f0, ft, t0, b, p, bias_s, st, &tmy);
+                epi_phase<ACT>(v0, 1, 0, pair, turn, r, n_out, Fp, fe, f0, ft, t0, b, p, bias_s, st, &tmy);
+                epi_phase<ACT>(v1, 0, 1, pair, turn, r, n_out, Fp, fe, f0, ft, t0, b, p, bias_s, st, &tmy);
+                epi_phase<ACT>(v1, 1, 1, pair, turn, r, n_out, Fp, fe, f0, ft, t0, b, p, bias_s, st, &tmy);
                 if (e == 0 && ft == 0) trace(p, kTrTile0 + 5 * tcount + 4);
                 accph ^= 1;
             }
@@ -1026,7 +1060,23 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
     }
     TcKernel kern = pick_kernel(g.conj_w != 0, g.act, x3 != 0, pl.ragged != 0);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
-    const int grid = std::min(p.n_tiles, num_sms());
+    // Work split (WorkItem): whole rounds of one tile per CTA, then the remainder -- split along the filters into twice as
+    // many half-width items when that keeps no more CTAs busy than there are SMs (only 64-wide filter tiles split into
+    // 32-column store chunks that stay inside one component).  QNN_TC_NOSPLIT=1 keeps whole tiles (A/B timing).
+    static const bool no_split = [] { const char* e = getenv("QNN_TC_NOSPLIT"); return e && atoi(e) != 0; }();
+    const int sms = num_sms();
+    int grid;
+    if (p.n_tiles >= sms) {
+        grid = sms;
+        p.full_rounds = p.n_tiles / sms;
+        p.rem = p.n_tiles % sms;
+        p.split = (!no_split && p.f_tile == 64 && p.rem > 0 && 2 * p.rem <= sms) ? 1 : 0;
+    } else {
+        p.full_rounds = 0;
+        p.rem = p.n_tiles;
+        p.split = (!no_split && p.f_tile == 64 && 2 * p.rem <= sms) ? 1 : 0;
+        grid = p.split ? 2 * p.rem : p.rem;
+    }
     p.trace = (g_trace && g_trace_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace : nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);
