@@ -535,17 +535,15 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                     const int batch = (stage_i == 0 && ft == 0) ? 1 : kMaxTapBatch;
                     for (int tap0 = 0, nb = 0; tap0 < p.taps; tap0 += nb) {
                         nb = min(batch, p.taps - tap0);
-                        // all slots of the batch must be free before the first store; one fence for the batch
+                        // a tap's stores go out as soon as ITS slot is free (the MMAs free the slots one by one, ~600 cycles
+                        // apart: waiting for the whole batch first kept the first taps' stores back for no reason)
                         uint32_t as_b = as, aph_b = aph;
                         for (int tb = 0; tb < nb; ++tb) {
                             mbar_wait(&bars->a_empty[as_b], aph_b ^ 1);
                             if (detail && s < 8 && tap0 == 0) trace(p, kTrConv + 8 * s + 1 + tb);
-                            if (++as_b == kASlots) { as_b = 0; aph_b ^= 1; }
-                        }
-                        tc_fence_after_sync();
-                        if (p.handshake && tap0 + nb >= p.taps && stage_i + 1 < total_stages) named_bar_arrive(12 + cgrp, 256);
-                        as_b = as;
-                        for (int tb = 0; tb < nb; ++tb) {
+                            tc_fence_after_sync();
+                            if (p.handshake && tb == nb - 1 && tap0 + nb >= p.taps && stage_i + 1 < total_stages)
+                                named_bar_arrive(12 + cgrp, 256);
                             const uint32_t row = (uint32_t)(r * p.stride + (tap0 + tb) * p.dil);
                             const uint8_t* xrow = xb + row * 128u;
                             const uint32_t sw = row & 7u;
@@ -619,7 +617,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                                     tmem_st8_nc(dst + k0, u);
                                 }
                             }
-                            if (++as_b == kASlots) as_b = 0;
+                            if (++as_b == kASlots) { as_b = 0; aph_b ^= 1; }
                         }
                         tmem_wait_st();  // one wait for the whole batch of taps
                         if (detail && s < 8 && tap0 == 0) trace(p, kTrConv + 8 * s + 5);
