@@ -30,6 +30,7 @@
 // Warp roles and the TMEM plan are those of qnn_hamilton_tc.cu: warps 0-15 epilogue, 16-19 MMA issuers (one per output
 // component), 20-27 converters (two groups on alternate stages), 28 / 29 producers (x stages / sub-filter blocks); TMEM [0,256) accumulators, [256,512) eight A slots.
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include "qnn_common.h"
 #include "qnn_ptx.cuh"
@@ -88,6 +89,8 @@ struct P2 {
     int comp_stride;       // channels_last: bytes between the component blocks of an x stage (wbox * 32 rounded up to 128)
     int handshake;         // KW >= A slots: converter groups hand over stage by stage (see the converter role)
     uint32_t b_blk_bytes;  // one B slot: 4 sub-filters x 2 k-groups x f_tile x 16 B (3xTF32: twice that, hi block | lo block)
+    int full_rounds, rem;  // work of a CTA: full_rounds items (item = cta + k * grid), then `rem` items in a last round
+    int split;             // the last round's items are split along the filters, see Work
 };
 
 struct __align__(8) Bars {
@@ -172,6 +175,30 @@ __device__ __forceinline__ void stage_chunk_rows(const uint32_t (&v)[32], const 
     }
 }
 
+// Work of a CTA: `full_rounds` whole items, then the last, partial round.  When that round would keep at most half of the
+// CTAs busy (and the filter tile is 64 wide) its items are SPLIT along the filters, as in qnn_hamilton_tc.cu: CTA i takes
+// filters [32 (i & 1), +32) of item i / 2 -- N = 32 MMAs on the same (whole) sub-filter blocks, 4 x 32 accumulator columns,
+// half the output stores.  Every output element keeps its accumulation order: results are bit-identical.
+struct Work {
+    int item, f0, fe;
+};
+__device__ __forceinline__ int n_work(const P2& p) {
+    return p.full_rounds + ((int)blockIdx.x < (p.split ? 2 * p.rem : p.rem) ? 1 : 0);
+}
+__device__ __forceinline__ Work work_of(const P2& p, int k) {
+    Work w;
+    if (k < p.full_rounds || !p.split) {
+        w.item = (int)blockIdx.x + k * (int)gridDim.x;
+        w.f0 = 0;
+        w.fe = p.f_tile;
+    } else {
+        w.item = p.full_rounds * (int)gridDim.x + ((int)blockIdx.x >> 1);
+        w.f0 = ((int)blockIdx.x & 1) * 32;
+        w.fe = 32;
+    }
+    return w;
+}
+
 struct ItemPos {
     int ft, b, dpos, ho, w0;
 };
@@ -190,12 +217,12 @@ __device__ __forceinline__ ItemPos item_pos(const P2& p, int item) {
 
 template <bool CL, int ACT>
 __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn, int which, int pair, int turn, int r,
-                                          int n_out, int Fp, const ItemPos& ip, const P2& p, const float* bias_s,
-                                          float* st, const CUtensorMap* tmy) {
+                                          int n_out, int Fp, int fe, int f0, const ItemPos& ip, const P2& p,
+                                          const float* bias_s, float* st, const CUtensorMap* tmy) {
     const int c_act = pair + 2 * act_turn + 4 * which;  // 32-column chunk handled in this phase on this staging tile
     if (c_act >= n_out) return;                        // uniform across the pair
     const int col = c_act * 32;
-    const int ch0 = (col / Fp) * p.F + ip.ft * Fp + (col % Fp);  // first of 32 consecutive output channels
+    const int ch0 = (col / fe) * p.F + ip.ft * Fp + f0 + (col % fe);  // first of 32 consecutive output channels
     const bool mine = turn == act_turn;
     if (mine) {
         if (CL)
@@ -275,8 +302,8 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
         reg_dealloc<kRegsWg0>();
         const bool elected = elect_one();
         const int b = warp - kWarpIssuer0;  // this issuer's output component
-        const uint32_t idesc_pos = idesc_tf32(kTileM, Fp, false, false);
-        const uint32_t idesc_neg = idesc_tf32(kTileM, Fp, false, true);
+        const uint32_t idesc_pos_f = idesc_tf32(kTileM, Fp, false, false), idesc_neg_f = idesc_tf32(kTileM, Fp, false, true);
+        const uint32_t idesc_pos_h = idesc_tf32(kTileM, 32, false, false), idesc_neg_h = idesc_tf32(kTileM, 32, false, true);
         const uint64_t d0 = smem_desc_kmajor_noswz(smem_u32(b_s), (uint32_t)Fp * 16u, 128);
         const uint32_t w_lo = (uint32_t)d0, desc_hi = (uint32_t)(d0 >> 32);
         const uint32_t sub_stride = 2u * Fp;             // descriptor-lo units (16 B) between sub-filters of a block
@@ -284,8 +311,12 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
         const uint32_t lo_off = p.b_blk_bytes >> 5;       // 3xTF32: the lo block follows the hi block inside a slot
         constexpr uint32_t neg_table = CONJ ? kNegDense : kNegConv;
         const int slots_per_item = p.n_stages * p.KW;
-        int icount = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
+        const int nw = n_work(p);
+        for (int icount = 0; icount < nw; ++icount) {
+            const Work wk = work_of(p, icount);
+            const uint32_t idesc_pos = wk.fe == Fp ? idesc_pos_f : idesc_pos_h;
+            const uint32_t idesc_neg = wk.fe == Fp ? idesc_neg_f : idesc_neg_h;
+            const uint32_t d_col = t_acc + b * wk.fe;  // this issuer's accumulator: 4 x fe compact columns
             mbar_wait(&bars->acc_empty, accph ^ 1);
             tc_fence_after_sync();
             const bool tr = b == 0 && elected && icount < 12;
@@ -299,17 +330,17 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
                 tc_fence_after_sync();
                 if (elected) {
                     const uint32_t a_col = t_a + as * kSlotCols;
-                    const uint32_t blk_lo = w_lo + as * slot_stride;
+                    const uint32_t blk_lo = w_lo + as * slot_stride + wk.f0;  // (a filter row is 16 bytes)
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
                         const int c = a ^ b;  // sub-filter index: IDX[a][b] = a xor b
                         const uint32_t idesc = ((neg_table >> (a * 4 + b)) & 1u) ? idesc_neg : idesc_pos;
                         if (X3) {  // x_lo.w_hi + x_hi.w_lo + x_hi.w_hi
-                            mma_ts(t_acc + b * Fp, a_col + 32 + a * 8, blk_lo + c * sub_stride, desc_hi, idesc, accumulate);
-                            mma_ts(t_acc + b * Fp, a_col + a * 8, blk_lo + lo_off + c * sub_stride, desc_hi, idesc, 1);
-                            mma_ts(t_acc + b * Fp, a_col + a * 8, blk_lo + c * sub_stride, desc_hi, idesc, 1);
+                            mma_ts(d_col, a_col + 32 + a * 8, blk_lo + c * sub_stride, desc_hi, idesc, accumulate);
+                            mma_ts(d_col, a_col + a * 8, blk_lo + lo_off + c * sub_stride, desc_hi, idesc, 1);
+                            mma_ts(d_col, a_col + a * 8, blk_lo + c * sub_stride, desc_hi, idesc, 1);
                         } else {
-                            mma_ts(t_acc + b * Fp, a_col + a * 8, blk_lo + c * sub_stride, desc_hi, idesc, accumulate);
+                            mma_ts(d_col, a_col + a * 8, blk_lo + c * sub_stride, desc_hi, idesc, accumulate);
                         }
                         accumulate = 1;
                     }
@@ -331,8 +362,9 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
             // spanning the component axis would need a 32-byte inner row per line under a swizzle, or non-monotonic strides).
             const int comp = CL ? (tid & 31) : 0;
             uint32_t xs = 0, xph = 0;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const ItemPos ip = item_pos(p, item);
+            const int nw = n_work(p);
+            for (int k = 0; k < nw; ++k) {
+                const ItemPos ip = item_pos(p, work_of(p, k).item);
                 const int cx = ip.w0 - p.pad_w - p.xshift, cy = ip.ho - p.pad_h, cz = ip.dpos - p.pad_d, cb = 4 * ip.b;
                 for (int qc = 0; qc < p.n_qc; ++qc)
                     for (int kr = 0; kr < p.KD * p.KH; ++kr) {  // kernel planes x kernel rows: one stage each
@@ -354,8 +386,9 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
             // block (ft, stage s, kw) of the packed sub-filters goes into the B slot paired with the A slot of (s, kw)
             const size_t blk_floats = p.b_blk_bytes >> 2;
             const int slots_per_item = p.n_stages * p.KW;
-            for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-                const float* src = wp + (size_t)(item % p.n_ftiles) * slots_per_item * blk_floats;
+            const int nw = n_work(p);
+            for (int k = 0; k < nw; ++k) {  // (a half item streams the whole blocks: the MMAs read half of their rows)
+                const float* src = wp + (size_t)(work_of(p, k).item % p.n_ftiles) * slots_per_item * blk_floats;
                 for (int i = 0; i < slots_per_item; ++i, src += blk_floats) {
                     mbar_wait(&bars->a_empty[as], aph ^ 1);
                     mbar_arrive_expect_tx(&bars->b_full[as], p.b_blk_bytes);
@@ -376,10 +409,10 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
         const int ch_stride = p.wbox;  // floats between channels of a stage
         int stage_i = 0;
         uint32_t xs = 0, xph = 0;
-        const int my_items = (p.n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+        const int my_items = n_work(p);
         const int total_stages = my_items * p.n_stages;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-            const bool tr = cgrp == 0 && r == 0 && item == (int)(blockIdx.x + gridDim.x);
+        for (int k = 0; k < my_items; ++k) {
+            const bool tr = cgrp == 0 && r == 0 && k == 1;
             for (int s = 0; s < p.n_stages; ++s, ++stage_i) {
                 if ((stage_i & 1) != cgrp) {  // the other group's stage: just advance the ring positions
                     if (++xs == (uint32_t)p.x_stages) { xs = 0; xph ^= 1; }
@@ -504,11 +537,13 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
         const int grp = e >> 7, r = e & 127;
         const int pair = grp & 1, turn = grp >> 1;
         const uint32_t lane_base = (uint32_t)(r & ~31) << 16;
-        const int n_out = (4 * Fp) >> 5;  // 32-column chunks per item: 4 or 8
         float* st = reinterpret_cast<float*>(y_s + pair * kStagingBytes);
-        int icount = 0;
-        for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++icount) {
-            const ItemPos ip = item_pos(p, item);
+        const int nw = n_work(p);
+        for (int icount = 0; icount < nw; ++icount) {
+            const Work wk = work_of(p, icount);
+            const int fe = wk.fe, f0 = wk.f0;
+            const int n_out = (4 * fe) >> 5;  // 32-column chunks of this item: 4 or 8
+            const ItemPos ip = item_pos(p, wk.item);
             mbar_wait_sleep(&bars->acc_full, accph);
             tc_fence_after_sync();
             if (e == 0 && icount < 12) trace(p, kTrItem + 4 * icount + 2);
@@ -518,10 +553,10 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
             tmem_wait_ld();
             tc_fence_before_sync();
             mbar_arrive(&bars->acc_empty);  // accumulators are in registers: the next item's MMAs may start
-            epi_phase<CL, ACT>(v0, 0, 0, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
-            epi_phase<CL, ACT>(v0, 1, 0, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
-            epi_phase<CL, ACT>(v1, 0, 1, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
-            epi_phase<CL, ACT>(v1, 1, 1, pair, turn, r, n_out, Fp, ip, p, bias_s, st, &tmy);
+            epi_phase<CL, ACT>(v0, 0, 0, pair, turn, r, n_out, Fp, fe, f0, ip, p, bias_s, st, &tmy);
+            epi_phase<CL, ACT>(v0, 1, 0, pair, turn, r, n_out, Fp, fe, f0, ip, p, bias_s, st, &tmy);
+            epi_phase<CL, ACT>(v1, 0, 1, pair, turn, r, n_out, Fp, fe, f0, ip, p, bias_s, st, &tmy);
+            epi_phase<CL, ACT>(v1, 1, 1, pair, turn, r, n_out, Fp, fe, f0, ip, p, bias_s, st, &tmy);
             if (e == 0 && icount < 12) trace(p, kTrItem + 4 * icount + 3);
             accph ^= 1;
         }
@@ -884,7 +919,22 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
     }
     Tc2dKernel kern = pick_kernel(g.act, !g.channels_first, x3 != 0, g.conj_w != 0);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
-    const int grid = std::min(p.n_items, num_sms());
+    // work split (Work): whole rounds of one item per CTA, then the remainder -- split along the filters into twice as many
+    // half-width items when that keeps no more CTAs busy than there are SMs.  QNN_TC_NOSPLIT=1: whole items (A/B timing)
+    static const bool no_split = [] { const char* e = getenv("QNN_TC_NOSPLIT"); return e && atoi(e) != 0; }();
+    const int sms = num_sms();
+    int grid;
+    if (p.n_items >= sms) {
+        grid = sms;
+        p.full_rounds = p.n_items / sms;
+        p.rem = p.n_items % sms;
+        p.split = (!no_split && p.f_tile == 64 && p.rem > 0 && 2 * p.rem <= sms) ? 1 : 0;
+    } else {
+        p.full_rounds = 0;
+        p.rem = p.n_items;
+        p.split = (!no_split && p.f_tile == 64 && 2 * p.rem <= sms) ? 1 : 0;
+        grid = p.split ? 2 * p.rem : p.rem;
+    }
     p.trace = (g_trace2d && g_trace2d_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace2d : nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

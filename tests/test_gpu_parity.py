@@ -427,6 +427,36 @@ def test_northstar_dense_full_size(cnn):
     check(y3.cpu().numpy(), ref, X3_TOL, "dense north star 3xtf32")
 
 
+@pytest.mark.parametrize("math", ["tf32", "3xtf32"])
+def test_split_last_round_is_bit_identical(cnn, native_lib, math):
+    """The resident-sub-filter kernel splits the tiles of a last, partial round along the filters (two N = 32 half items on
+    two CTAs instead of one N = 64 tile, qnn_hamilton_tc.cu WorkItem).  Every output keeps its accumulation order, so a
+    sequence must come out with the same BITS whether its tile ran whole (148 tiles: one full round) or split (40 tiles)."""
+    from complexnn import _native, _ops
+    from complexnn._layer import Variable
+    rng = np.random.default_rng(11)
+    n_sm = torch.cuda.get_device_properties(0).multi_processor_count
+    F, k, T, in_q = 64, 3, 128, 40
+    x = dev(rng.normal(size=(n_sm, T, 4 * in_q)).astype(np.float32))
+    kern = Variable((rng.normal(size=(k, in_q, 4 * F)) * 0.1).astype(np.float32))
+    bias = Variable(rng.normal(size=(4 * F,)).astype(np.float32))
+    desc = _native.make_conv_desc(1, n_sm, (T,), in_q, F, (k,), (1,), (1,), "same", "channels_last", "relu", math=math)
+    if native_lib.qnn_conv_uses_tensor_cores(ctypes.byref(desc)) != 1:
+        pytest.skip("shape not on the tensor-core kernel in this mode")
+    run = lambda xs: _ops.conv_forward(xs, kern, bias, F, (k,), (1,), "same", "channels_last", (1,), "relu", math=math,
+                                       algo="tensor")
+    y_full = run(x)                      # n_sm tiles: one whole round, nothing to split
+    y_part = run(x[:40].contiguous())    # 40 tiles <= n_sm / 2: split into 80 half items
+    assert torch.equal(y_part, y_full[:40])
+    y_mix = run(torch.cat([x, x[:40]]).contiguous())  # n_sm + 40 tiles: one whole round + a split round
+    assert torch.equal(y_mix[:n_sm], y_full) and torch.equal(y_mix[n_sm:], y_full[:40])
+    ref = O.qconv_forward(x[:40].cpu().numpy(), kern.numpy(), bias.numpy(), F, 1, "same", "channels_last", 1, "relu")
+    if math == "3xtf32":
+        check_contract(y_part.cpu().numpy(), ref, "split round")
+    else:
+        check(y_part.cpu().numpy(), ref, TF32_TOL, "split round")
+
+
 def test_quaternion_norm_is_multiplicative_on_gpu(cnn):
     """|w (x) x| = |w| |x| for single quaternions: a property no sign-table mistake survives."""
     rng = np.random.default_rng(3)
