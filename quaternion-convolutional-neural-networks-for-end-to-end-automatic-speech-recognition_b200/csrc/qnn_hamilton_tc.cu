@@ -115,7 +115,7 @@ struct TcParams {
 struct __align__(8) Barriers {
     uint64_t x_full[kMaxXStages];
     uint64_t a_full[kMaxASlots], a_empty[kMaxASlots];
-    uint64_t acc_full, acc_empty, w_ready;
+    uint64_t acc_full, acc_empty, w_ready, pass_done;
     uint32_t tmem_base;
 };
 
@@ -343,6 +343,7 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
         mbar_init(&bars->acc_full, 4);
         mbar_init(&bars->acc_empty, kEpiThreads);
         mbar_init(&bars->w_ready, 1);
+        mbar_init(&bars->pass_done, kThreads);
         fence_mbar_init();
     }
     if (warp == kWarpAlloc) {
@@ -471,8 +472,11 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 accph ^= 1;
             }
         }
-        named_bar_sync(14, kThreads);  // every role is done with this f-tile's sub-filters (one barrier, three call
-                                       // sites: a named barrier, not __syncthreads, which wants ONE call site per block)
+        // every role is done with this f-tile's sub-filters before the next pass' image overwrites them.  An mbarrier
+        // (count = all threads), not bar.sync: the three roles reach it from three call sites, which compute-sanitizer's
+        // synccheck reports as divergence for a hardware barrier
+        mbar_arrive(&bars->pass_done);
+        mbar_wait(&bars->pass_done, ft & 1);
       }
     } else if (warp >= kWarpConv0) {
       reg_dealloc<kRegsWg1>();
@@ -635,8 +639,11 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
                 }
             }
         }
-        named_bar_sync(14, kThreads);  // every role is done with this f-tile's sub-filters (one barrier, three call
-                                       // sites: a named barrier, not __syncthreads, which wants ONE call site per block)
+        // every role is done with this f-tile's sub-filters before the next pass' image overwrites them.  An mbarrier
+        // (count = all threads), not bar.sync: the three roles reach it from three call sites, which compute-sanitizer's
+        // synccheck reports as divergence for a hardware barrier
+        mbar_arrive(&bars->pass_done);
+        mbar_wait(&bars->pass_done, ft & 1);
       }
     } else {
       reg_alloc<kRegsEpi>();
@@ -746,8 +753,11 @@ k_hamilton_tc(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ C
             }
             if (r == 0) tma_store_wait_read<0>();  // smem may be released; completion of the writes is the kernel's end
         }
-        named_bar_sync(14, kThreads);  // every role is done with this f-tile's sub-filters (one barrier, three call
-                                       // sites: a named barrier, not __syncthreads, which wants ONE call site per block)
+        // every role is done with this f-tile's sub-filters before the next pass' image overwrites them.  An mbarrier
+        // (count = all threads), not bar.sync: the three roles reach it from three call sites, which compute-sanitizer's
+        // synccheck reports as divergence for a hardware barrier
+        mbar_arrive(&bars->pass_done);
+        mbar_wait(&bars->pass_done, ft & 1);
       }
     }
 

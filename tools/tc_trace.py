@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Per-CTA pipeline timeline of the tensor-core kernel (diagnostics).  Runs one forward with qnn_debug_trace enabled
 and prints, for a few CTAs, the clock64() of each pipeline event relative to the CTA's start (in SM cycles).
-  python tools/tc_trace.py [cfg2|dense]"""
+  python tools/tc_trace.py [cfg2|dense|timit|few]"""
 import ctypes
 import os
 import sys
@@ -20,6 +20,9 @@ np.random.seed(0)
 if which in ("cfg2", "few"):
     layer = complexnn.QuaternionConv1D(64, 3, padding="same", activation="relu")
     x = torch.randn(256 if which == "cfg2" else 2, 256, 160, device="cuda")   # "few": 4 tiles -> 4 CTAs, same weights
+elif which == "timit":   # first layer of the cfg 3 stack: 41 TIMIT features per component (ragged channel count)
+    layer = complexnn.QuaternionConv1D(64, 3, padding="same", activation="relu")
+    x = torch.randn(256, 256, 164, device="cuda")
 else:
     layer = complexnn.QuaternionDense(256, activation="relu")
     x = torch.randn(65536, 160, device="cuda")
