@@ -199,10 +199,17 @@ int forward_kernel(const Geom& g, int rank, int math, int algo) {
     // tiles or the layer is one tile; when it only fits with 32-filter tiles the kernel makes twice the passes over x with
     // N = 32 MMAs that cost as much as N = 64 ones (measured: cfg 3 conv layers 60 us vs ~35 us) -- the streamed-sub-filter
     // kernel then takes the problem if it qualifies (in_q % 8 == 0, F % 32 == 0).
+    // Ragged channel counts (in_q % 4 != 0) whose image leaves room for two x stages only (the TIMIT first layer of the
+    // cfg 3 stack, in_q = 41, F = 64, k = 3: 147 KB of image): every converter group then has ONE x buffer and waits out a
+    // whole load per stage (23 k cycles per tile against 11 k of MMAs) -- the streamed-sub-filter kernel, which reads such
+    // rows in place too (twelve-channel boxes), takes them.  QNN_RAGGED_STREAM=0 keeps them on the resident kernel.
+    static const bool ragged_stream = [] { const char* e = getenv("QNN_RAGGED_STREAM"); return !(e && atoi(e) == 0); }();
     const TcPlan tcp = tc_plan(g, rank, x3);
-    const bool resident_good = tcp.ok && (tcp.n_ftiles == 1 || tcp.f_tile >= 64);
+    const Tc2dPlan t2p = tc2d_plan(g, rank, x3);
+    const bool ragged_starved = tcp.ok && tcp.ragged && tcp.x_stages < 4 && ragged_stream && t2p.ok && t2p.rag;
+    const bool resident_good = tcp.ok && (tcp.n_ftiles == 1 || tcp.f_tile >= 64) && !ragged_starved;
     if (resident_good) return kKernTc;
-    if (tc2d_plan(g, rank, x3).ok) return kKernTc2d;
+    if (t2p.ok) return kKernTc2d;
     if (tcp.ok) return kKernTc;
     return kKernGeneral;
 }

@@ -114,6 +114,7 @@ struct Tc2dPlan {
     int xshift;      // columns the box starts left of the first tap (16-byte alignment of the TMA start)
     int pad_rows;    // channels_first row length % 4 != 0: x / y go through row-padded scratch copies
     int pad_q;       // in_q % 8 != 0: x goes through a quaternion-channel padding pre-pass (zero channels)
+    int rag;         // channels_last, in_q % 8 != 0, in_q >= 8: read in place through twelve-channel boxes (no pre-pass)
     int x_stages;
     size_t x_stage_bytes, smem_bytes;
     size_t packed_bytes;  // packed kernel image (hi [+ lo] blocks per (filter tile, 8-channel chunk, tap))

@@ -89,6 +89,10 @@ struct P2 {
     int comp_stride;       // channels_last: bytes between the component blocks of an x stage (wbox * 32 rounded up to 128)
     int handshake;         // KW >= A slots: converter groups hand over stage by stage (see the converter role)
     uint32_t b_blk_bytes;  // one B slot: 4 sub-filters x 2 k-groups x f_tile x 16 B (3xTF32: twice that, hi block | lo block)
+    int rag;               // channels_last, in_q % 8 != 0, read in place: a component's 8 channels of a stage do not start on a
+                           // 16-byte boundary -- the stage is four un-swizzled boxes of TWELVE flat channels (48 bytes per
+                           // position) starting at the aligned channel at or below, the converter selects its 8 by the shift
+    int in_q;              // the tensor's own quaternion channel count (n_qc counts the zero-padded one)
     int full_rounds, rem;  // work of a CTA: full_rounds items (item = cta + k * grid), then `rem` items in a last round
     int split;             // the last round's items are split along the filters, see Work
 };
@@ -245,7 +249,7 @@ __device__ __forceinline__ void epi_phase(const uint32_t (&v)[32], int act_turn,
     named_bar_sync(5 + pair, 256);
 }
 
-template <bool CONJ, bool CL, int ACT, bool X3>
+template <bool CONJ, bool CL, int ACT, bool X3, bool RAG>
 __global__ void __launch_bounds__(kThreads, 1)
 k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__ CUtensorMap tmy, const P2 p,
                 const float* __restrict__ wp, const float* __restrict__ bias) {
@@ -370,8 +374,12 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
                     for (int kr = 0; kr < p.KD * p.KH; ++kr) {  // kernel planes x kernel rows: one stage each
                         const int kd = kr / p.KH, kh = kr - kd * p.KH;
                         mbar_wait(&bars->x_empty[xs], xph ^ 1);
-                        if (comp == 0) mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)(32 * p.wbox * 4));
-                        if (CL)  // x[nb][H][W][4][Q]: box (8 q, 1 component, wbox columns, 1 row, 1 sample) -> dense [w][8 q]
+                        if (comp == 0) mbar_arrive_expect_tx(&bars->x_full[xs], (uint32_t)((RAG ? 48 : 32) * p.wbox * 4));
+                        if (CL && RAG)  // flat channel axis: box (12 channels, wbox columns, 1 row, 1 sample) from the aligned
+                                        // channel at or below component * in_q + 8 qc
+                            tma_load_4d(x_s + (size_t)xs * p.x_stage_bytes + (size_t)comp * p.comp_stride, &tmx, &bars->x_full[xs],
+                                        (comp * p.in_q + qc * 8) & ~3, ip.w0 - p.pad_w, cy + kh * p.dh, ip.b);
+                        else if (CL)  // x[nb][H][W][4][Q]: box (8 q, 1 component, wbox columns, 1 row, 1 sample) -> dense [w][8 q]
                             tma_load_5d(x_s + (size_t)xs * p.x_stage_bytes + (size_t)comp * p.comp_stride, &tmx, &bars->x_full[xs],
                                         qc * 8, comp, ip.w0 - p.pad_w, cy + kh * p.dh, ip.b);
                         else if (p.rank3)  // x[nb*4][Q][D][H][W]: box (wbox positions, 1 row, 1 plane, 8 q, 4 components)
@@ -441,7 +449,41 @@ k_hamilton_tc2d(const __grid_constant__ CUtensorMap tmx, const __grid_constant__
                     as_b = as;
                     for (int tb = 0; tb < nb; ++tb) {
                         const uint32_t dst = t_a + lane_base + as_b * kSlotCols;
-                        if (CL) {
+                        if (CL && RAG) {
+                            // stage = [component][w][12 flat channels] fp32, un-swizzled: 48 bytes per position (lanes 3
+                            // 16-byte units apart: a quarter warp's loads of one unit fall on 8 different bank groups).
+                            // The component's 8 channels start `shift` (0..3) channels in; channels past the component's
+                            // end belong to the next one: zeroed (their weights are zero rows, but 0 x inf is NaN).
+                            const uint32_t row = (uint32_t)(r + (tap0 + tb) * p.dw);
+                            const uint8_t* xrow = x_s + (size_t)xs * p.x_stage_bytes + row * 48u;
+                            const int qc8 = (s / (p.KD * p.KH)) * 8;
+                            const int kvalid = p.in_q - qc8;  // channels of this 8-group that exist
+#pragma unroll
+                            for (int a = 0; a < 4; ++a) {
+                                const uint4* xc = reinterpret_cast<const uint4*>(xrow + a * (uint32_t)p.comp_stride);
+                                const uint4 c0 = xc[0], c1 = xc[1], c2 = xc[2];
+                                uint32_t v[8];
+                                switch ((a * p.in_q + qc8) & 3) {
+                                    case 0: v[0] = c0.x; v[1] = c0.y; v[2] = c0.z; v[3] = c0.w; v[4] = c1.x; v[5] = c1.y; v[6] = c1.z; v[7] = c1.w; break;
+                                    case 1: v[0] = c0.y; v[1] = c0.z; v[2] = c0.w; v[3] = c1.x; v[4] = c1.y; v[5] = c1.z; v[6] = c1.w; v[7] = c2.x; break;
+                                    case 2: v[0] = c0.z; v[1] = c0.w; v[2] = c1.x; v[3] = c1.y; v[4] = c1.z; v[5] = c1.w; v[6] = c2.x; v[7] = c2.y; break;
+                                    default: v[0] = c0.w; v[1] = c1.x; v[2] = c1.y; v[3] = c1.z; v[4] = c1.w; v[5] = c2.x; v[6] = c2.y; v[7] = c2.z; break;
+                                }
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) v[k] &= (k < kvalid ? 0xffffffffu : 0u);
+                                if (X3) {
+                                    uint32_t hi[8], lo[8];
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) split_tf32(v[k], hi[k], lo[k]);
+                                    tmem_st8_nc(dst + a * 8, hi);
+                                    tmem_st8_nc(dst + 32 + a * 8, lo);
+                                } else {
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) v[k] += 0x1000u;  // round to nearest tf32
+                                    tmem_st8_nc(dst + a * 8, v);
+                                }
+                            }
+                        } else if (CL) {
                             // stage = [component][w][8 q] fp32, un-swizzled: a thread's position holds 32 bytes per component.
                             // Lanes are 32 bytes apart, so a quarter-warp's 16-byte loads of the SAME half would hit each
                             // bank twice; lanes 4..7 of every eight read the other half first -> conflict-free.
@@ -665,16 +707,17 @@ typedef void (*Tc2dKernel)(const CUtensorMap, const CUtensorMap, const P2, const
 unsigned long long* g_trace2d = nullptr;
 size_t g_trace2d_bytes = 0;
 
-template <bool CL, bool X3>
+template <bool CL, bool X3, bool RAG>
 Tc2dKernel pick_kernel_x(int a, bool conj) {
-    if (conj) return k_hamilton_tc2d<true, CL, kActLinear, X3>;  // transposed sign table: the data gradient (no activation)
-    return a == kActLinear ? k_hamilton_tc2d<false, CL, kActLinear, X3>
-                           : a == kActRelu ? k_hamilton_tc2d<false, CL, kActRelu, X3> : k_hamilton_tc2d<false, CL, kActGeneric, X3>;
+    if (conj) return k_hamilton_tc2d<true, CL, kActLinear, X3, RAG>;  // transposed sign table: the data gradient (no activation)
+    return a == kActLinear ? k_hamilton_tc2d<false, CL, kActLinear, X3, RAG>
+                           : a == kActRelu ? k_hamilton_tc2d<false, CL, kActRelu, X3, RAG> : k_hamilton_tc2d<false, CL, kActGeneric, X3, RAG>;
 }
-Tc2dKernel pick_kernel(int act, bool channels_last, bool x3, bool conj) {
+Tc2dKernel pick_kernel(int act, bool channels_last, bool x3, bool conj, bool rag) {
     const int a = act == QNN_ACT_LINEAR ? kActLinear : (act == QNN_ACT_RELU ? kActRelu : kActGeneric);
-    if (channels_last) return x3 ? pick_kernel_x<true, true>(a, conj) : pick_kernel_x<true, false>(a, conj);
-    return x3 ? pick_kernel_x<false, true>(a, conj) : pick_kernel_x<false, false>(a, conj);
+    if (channels_last && rag) return x3 ? pick_kernel_x<true, true, true>(a, conj) : pick_kernel_x<true, false, true>(a, conj);
+    if (channels_last) return x3 ? pick_kernel_x<true, true, false>(a, conj) : pick_kernel_x<true, false, false>(a, conj);
+    return x3 ? pick_kernel_x<false, true, false>(a, conj) : pick_kernel_x<false, false, false>(a, conj);
 }
 
 }  // namespace
@@ -701,7 +744,12 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3) {
     if (g.s[0] != 1 || g.s[1] != 1 || g.s[2] != 1) return no("stride != 1");
     // in_q % 8 != 0 (the TIMIT model's first layer has ONE quaternion input channel, interspeech_model.py:97): x goes through
     // a channel-padding pre-pass to the next multiple of 8 (zero channels; the image gets zero rows)
-    pl.pad_q = (g.in_q % 8) ? 1 : 0;
+    // channels_last tensors with at least 8 quaternion channels are read IN PLACE instead (twelve-channel boxes from the
+    // aligned channel below each component's 8-group, Tc2dPlan::rag): no pre-pass, no scratch copy of x.
+    // QNN_TC2D_RAG=0 keeps the pre-pass (A/B timing)
+    static const bool allow_rag = [] { const char* e = getenv("QNN_TC2D_RAG"); return !(e && atoi(e) == 0); }();
+    pl.rag = (allow_rag && cl && g.in_q % 8 && g.in_q >= 8) ? 1 : 0;
+    pl.pad_q = (g.in_q % 8 && !pl.rag) ? 1 : 0;
     const int Qp = (g.in_q + 7) & ~7;
     if (g.F % 32) return no("filters not a multiple of 32");
     // channels_first rows whose length is not a multiple of 4 (TMA strides must be multiples of 16 bytes; the reference's
@@ -718,7 +766,7 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3) {
     const int f_tile = g.F % 64 == 0 ? 64 : 32;
     const size_t blk = (size_t)32 * f_tile * 4 * (x3 ? 2 : 1);
     // channels_last: four component blocks per stage, each starting on a 128-byte boundary (TMA destination alignment)
-    const size_t comp_stride = ((size_t)wbox * 32 + 127) & ~size_t(127);
+    const size_t comp_stride = ((size_t)wbox * (pl.rag ? 48 : 32) + 127) & ~size_t(127);
     const size_t stage = ((cl ? 4 * comp_stride : (size_t)32 * wbox * 4) + 1023) & ~size_t(1023);
     const size_t fixed = 1024 + slots * blk + 2 * kStagingBytes + (((size_t)g.F * 16 + 1023) & ~size_t(1023)) + 512;
     if (fixed + 2 * stage > kSmemLimit) return no("x stages do not fit in shared memory");
@@ -839,7 +887,9 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
     p.dw = g.d[2];
     p.pad_h = g.pad_lo[1];
     p.pad_w = g.pad_lo[2];
-    p.n_qc = Q / 8;
+    p.n_qc = (Q + 7) / 8;
+    p.rag = pl.rag;
+    p.in_q = Q;
     p.n_stages = p.n_qc * p.KD * p.KH;
     p.F = F;
     p.f_tile = pl.f_tile;
@@ -851,7 +901,7 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
     p.has_bias = bias != nullptr;
     p.b_blk_bytes = (uint32_t)(32 * pl.f_tile * 4 * (x3 ? 2 : 1));
     p.handshake = p.KW >= (x3 ? 4 : 8) ? 1 : 0;
-    p.comp_stride = (int)(((size_t)pl.wbox * 32 + 127) & ~size_t(127));
+    p.comp_stride = (int)(((size_t)pl.wbox * (pl.rag ? 48 : 32) + 127) & ~size_t(127));
 
     CUtensorMap tmx, tmy;
     if (g.channels_first && rank == 3) {
@@ -902,7 +952,12 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
         const uint64_t dims[5] = {(uint64_t)Q, 4, (uint64_t)W, (uint64_t)H, (uint64_t)g.batch};
         const uint64_t str[4] = {(uint64_t)Q * 4, (uint64_t)Q * 16, (uint64_t)W * Q * 16, (uint64_t)H * W * Q * 16};
         const uint32_t box[5] = {8, 1, (uint32_t)pl.wbox, 1, 1};
-        int e = make_tmap_f32(&tmx, x, 5, dims, str, box, false);
+        // in_q % 8 != 0 (the component blocks do not start on 16-byte boundaries): the flat channel axis, boxes of twelve
+        // channels from the aligned channel at or below (component, 8-group); out-of-range channels of the last box read 0
+        const uint64_t rdims[4] = {(uint64_t)Q * 4, (uint64_t)W, (uint64_t)H, (uint64_t)g.batch};
+        const uint64_t rstr[3] = {(uint64_t)Q * 16, (uint64_t)W * Q * 16, (uint64_t)H * W * Q * 16};
+        const uint32_t rbox[4] = {12, (uint32_t)pl.wbox, 1, 1};
+        int e = pl.rag ? make_tmap_f32(&tmx, x, 4, rdims, rstr, rbox, false) : make_tmap_f32(&tmx, x, 5, dims, str, box, false);
         if (e) {
             set_error("cuTensorMapEncodeTiled(x, channels_last rank 2) failed (%d)", e);
             return QNN_E_CUDA;
@@ -917,7 +972,7 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
             return QNN_E_CUDA;
         }
     }
-    Tc2dKernel kern = pick_kernel(g.act, !g.channels_first, x3 != 0, g.conj_w != 0);
+    Tc2dKernel kern = pick_kernel(g.act, !g.channels_first, x3 != 0, g.conj_w != 0, pl.rag != 0);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
     // work split (Work): whole rounds of one item per CTA, then the remainder -- split along the filters into twice as many
     // half-width items when that keeps no more CTAs busy than there are SMs.  QNN_TC_NOSPLIT=1: whole items (A/B timing)

@@ -919,8 +919,14 @@ def _tc_cl2_shapes():
     rng = np.random.default_rng(21)
     out = [(1, (4, 128), 8, 32, (3, 3), (1, 1), "same", "relu", True), (2, (5, 131), 16, 64, (3, 5), (1, 1), "same", "relu", True),
            (1, (9, 70), 8, 128, (3, 2), (2, 1), "valid", "relu", True),
-           (2, (300,), 128, 128, (5,), (1,), "same", "relu", True)]      # rank 1: 1.3 MB of sub-filters, streamed
-    while len(out) < 14:
+           (2, (300,), 128, 128, (5,), (1,), "same", "relu", True),      # rank 1: 1.3 MB of sub-filters, streamed
+           # quaternion channel counts that are not multiples of 8: read in place through twelve-channel boxes (every shift
+           # 0..3 of a component's 8-group, the masked last group, in_q % 4 == 0 too); the rank-1 one is the TIMIT first
+           # layer of the cfg 3 stack, which the selection sends here (two x stages only on the resident kernel)
+           (2, (5, 131), 9, 32, (3, 3), (1, 1), "same", "relu", True), (1, (3, 70), 41, 64, (3, 5), (1, 1), "same", "relu", True),
+           (2, (300,), 41, 64, (3,), (1,), "same", "relu", True), (1, (4, 128), 12, 32, (2, 2), (1, 1), "valid", "linear", False),
+           (1, (2, 64), 43, 32, (1, 3), (1, 2), "same", "tanh", True)]
+    while len(out) < 19:
         in_q = int(rng.choice([8, 16, 24, 40]))
         F = int(rng.choice([32, 64, 96, 128]))
         k = tuple(int(v) for v in rng.integers(1, 5, size=2))
