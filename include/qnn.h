@@ -107,6 +107,12 @@ typedef enum qnn_kernel {
 QNN_API int qnn_conv_forward_kernel(const qnn_conv_desc* d);
 QNN_API int qnn_dense_forward_kernel(int64_t rows, int32_t in_q, int32_t q_units, int32_t activation, int32_t math,
                              int32_t algo);
+/* How the persistent tensor-core forward kernel of this descriptor spreads its work over the SMs (host-only, needs no GPU;
+ * 148 SMs are assumed when no device is present): out4 = { CTAs, whole rounds of one work item (a tile of 128 output
+ * positions x one filter tile) per CTA, items of the last partial round, 1 when that round's items are split along the
+ * filters into twice as many half-width items }.  Returns the qnn_kernel (out4 stays 0 for the CUDA-core kernels) or a
+ * negative qnn_status.  Diagnostics / tests: every item is computed exactly once whatever the split. */
+QNN_API int qnn_conv_work_split(const qnn_conv_desc* d, int32_t* out4);
 QNN_API int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units);
 
 /* Which gradients of this layer qnn_*_backward computes on the tensor cores (1) or on the CUDA-core kernels (0) under

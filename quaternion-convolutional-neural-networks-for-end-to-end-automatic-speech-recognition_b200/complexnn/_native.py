@@ -36,6 +36,7 @@ SIGNATURES = {
     "qnn_launch_count": (ctypes.c_uint64, []),
     "qnn_conv_uses_tensor_cores": (ctypes.c_int, [ctypes.POINTER(ConvDesc)]),
     "qnn_conv_forward_kernel": (ctypes.c_int, [ctypes.POINTER(ConvDesc)]),
+    "qnn_conv_work_split": (ctypes.c_int, [ctypes.POINTER(ConvDesc), ctypes.POINTER(ctypes.c_int32)]),
     "qnn_dense_forward_kernel": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
                                                 ctypes.c_int32, ctypes.c_int32]),
     "qnn_dense_uses_tensor_cores": (ctypes.c_int, [ctypes.c_int64, ctypes.c_int32, ctypes.c_int32]),

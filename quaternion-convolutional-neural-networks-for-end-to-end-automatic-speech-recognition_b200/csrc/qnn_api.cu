@@ -729,6 +729,35 @@ int qnn_conv_forward_kernel(const qnn_conv_desc* d) {
     return empty_out(g) ? QNN_KERNEL_GENERAL : forward_kernel(g, d->rank, d->math, d->algo);
 }
 
+int qnn_conv_work_split(const qnn_conv_desc* d, int32_t* out4) {
+    Geom g;
+    if (build_geom(d, &g)) return QNN_E_INVALID;
+    if (!valid_math(d->math) || !valid_algo(d->algo) || !out4) return QNN_E_INVALID;
+    out4[0] = out4[1] = out4[2] = out4[3] = 0;
+    if (empty_out(g)) return QNN_KERNEL_GENERAL;
+    const int kern = forward_kernel(g, d->rank, d->math, d->algo);
+    const int x3 = d->math == QNN_MATH_3XTF32;
+    long long items = 0;
+    int f_tile = 0;
+    if (kern == kKernTc) {
+        items = tc_work_items(g);
+        f_tile = tc_plan(g, d->rank, x3).f_tile;
+    } else if (kern == kKernTc2d) {
+        const Tc2dPlan pl = tc2d_plan(g, d->rank, x3);
+        items = tc2d_work_items(g, pl);
+        f_tile = pl.f_tile;
+    } else {
+        return kern;
+    }
+    if (items > 0x7fffffffLL / 64) return QNN_E_UNSUPPORTED;
+    const WorkSplit ws = plan_work_split((int)items, f_tile, num_sms());
+    out4[0] = ws.grid;
+    out4[1] = ws.full_rounds;
+    out4[2] = ws.rem;
+    out4[3] = ws.split;
+    return kern;
+}
+
 int qnn_dense_uses_tensor_cores(int64_t rows, int32_t in_q, int32_t q_units) {
     Geom g;
     if (build_dense_geom(rows, in_q, q_units, QNN_ACT_LINEAR, &g)) return 0;

@@ -1,5 +1,6 @@
 // Internal declarations shared by the kernels and the C-ABI translation unit.
 #pragma once
+#include <cstdlib>
 #include <cstdint>
 #include <cstdarg>
 #include <cstdio>
@@ -60,6 +61,30 @@ int cf_to_cl(const float* in, float* out, int batch, int C, long long S, cudaStr
 
 // tensor-core kernel (tcgen05 / TMEM / TMA): channels_last rows with taps along the innermost spatial axis.
 // `x3` selects 3xTF32 arithmetic (hi / lo operand split, three MMAs per block) instead of plain TF32.
+// How a persistent tensor-core forward kernel spreads its work items (tiles x filter tiles) over the SMs: `full_rounds`
+// whole items per CTA (item = cta + k * grid), then `rem` items in a last round; `split`: that round's items are split along
+// the filters into 2 * rem half-width items (WorkItem in qnn_hamilton_tc.cu, Work in qnn_hamilton_tc2d.cu) -- only 64-wide
+// filter tiles split, and only when the halves keep no more CTAs busy than there are SMs.  QNN_TC_NOSPLIT=1 switches it off.
+struct WorkSplit {
+    int grid, full_rounds, rem, split;
+};
+inline WorkSplit plan_work_split(int n_items, int f_tile, int sms) {
+    static const bool no_split = [] { const char* e = getenv("QNN_TC_NOSPLIT"); return e && atoi(e) != 0; }();
+    WorkSplit w{};
+    if (n_items >= sms) {
+        w.grid = sms;
+        w.full_rounds = n_items / sms;
+        w.rem = n_items % sms;
+        w.split = (!no_split && f_tile == 64 && w.rem > 0 && 2 * w.rem <= sms) ? 1 : 0;
+    } else {
+        w.full_rounds = 0;
+        w.rem = n_items;
+        w.split = (!no_split && f_tile == 64 && 2 * w.rem <= sms) ? 1 : 0;
+        w.grid = w.split ? 2 * w.rem : w.rem;
+    }
+    return w;
+}
+
 struct TcPlan {
     int ok;           // shape qualifies
     int f_tile;       // filters per pass (<= 64)
@@ -77,6 +102,7 @@ struct TcPlan {
     const char* why;  // reason when !ok
 };
 TcPlan tc_plan(const Geom& g, int rank, int x3);
+long long tc_work_items(const Geom& g);  // work items per filter-tile pass (tiles of 128 output positions)
 void tc_set_trace(void* device_buffer, size_t bytes);
 // x[rows][4][in_q] -> xp[rows][4][xq], xq = in_q rounded up to 4, new channels zero (ragged channel counts)
 int pad_x_channels(const float* x, float* xp, long long rows, int in_q, int xq, cudaStream_t st);
@@ -121,6 +147,7 @@ struct Tc2dPlan {
     const char* why;
 };
 Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3);
+long long tc2d_work_items(const Geom& g, const Tc2dPlan& pl);  // (tile, filter tile) items
 void tc2d_set_trace(void* device_buffer, size_t bytes);
 size_t tc2d_packed_bytes(const Geom& g, int rank, int x3);
 int tc2d_pack(const Geom& g, int rank, int x3, int transposed, const float* w, void* packed, cudaStream_t st);

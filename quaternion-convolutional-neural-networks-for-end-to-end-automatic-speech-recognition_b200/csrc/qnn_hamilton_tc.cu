@@ -945,6 +945,10 @@ TcPlan tc_plan(const Geom& g, int rank, int x3) {
     return pl;
 }
 
+long long tc_work_items(const Geom& g) {
+    return (long long)g.batch * ((g.out_sp[2] + kTileM - 1) / kTileM);
+}
+
 size_t tc_packed_bytes(const Geom& g, int rank, int x3) {
     const TcPlan pl = tc_plan(g, rank, x3);
     return pl.ok ? pl.packed_bytes : 0;
@@ -1068,23 +1072,11 @@ int tc_forward_packed(const Geom& g, int rank, int x3, const float* x, const voi
     }
     TcKernel kern = pick_kernel(g.conj_w != 0, g.act, x3 != 0, pl.ragged != 0);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
-    // Work split (WorkItem): whole rounds of one tile per CTA, then the remainder -- split along the filters into twice as
-    // many half-width items when that keeps no more CTAs busy than there are SMs (only 64-wide filter tiles split into
-    // 32-column store chunks that stay inside one component).  QNN_TC_NOSPLIT=1 keeps whole tiles (A/B timing).
-    static const bool no_split = [] { const char* e = getenv("QNN_TC_NOSPLIT"); return e && atoi(e) != 0; }();
-    const int sms = num_sms();
-    int grid;
-    if (p.n_tiles >= sms) {
-        grid = sms;
-        p.full_rounds = p.n_tiles / sms;
-        p.rem = p.n_tiles % sms;
-        p.split = (!no_split && p.f_tile == 64 && p.rem > 0 && 2 * p.rem <= sms) ? 1 : 0;
-    } else {
-        p.full_rounds = 0;
-        p.rem = p.n_tiles;
-        p.split = (!no_split && p.f_tile == 64 && 2 * p.rem <= sms) ? 1 : 0;
-        grid = p.split ? 2 * p.rem : p.rem;
-    }
+    const WorkSplit ws = plan_work_split(p.n_tiles, p.f_tile, num_sms());  // (qnn_common.h)
+    const int grid = ws.grid;
+    p.full_rounds = ws.full_rounds;
+    p.rem = ws.rem;
+    p.split = ws.split;
     p.trace = (g_trace && g_trace_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace : nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

@@ -783,6 +783,11 @@ Tc2dPlan tc2d_plan(const Geom& g, int rank, int x3) {
     return pl;
 }
 
+long long tc2d_work_items(const Geom& g, const Tc2dPlan& pl) {
+    const int tiles_w = (g.out_sp[2] + kTileM - 1) / kTileM;
+    return (long long)g.batch * g.out_sp[0] * g.out_sp[1] * tiles_w * pl.n_ftiles;
+}
+
 size_t tc2d_packed_bytes(const Geom& g, int rank, int x3) {
     const Tc2dPlan pl = tc2d_plan(g, rank, x3);
     return pl.ok ? pl.packed_bytes : 0;
@@ -974,22 +979,11 @@ int tc2d_forward_packed(const Geom& g, int rank, int x3, const float* x, const v
     }
     Tc2dKernel kern = pick_kernel(g.act, !g.channels_first, x3 != 0, g.conj_w != 0, pl.rag != 0);
     if (int rc = ensure_dynamic_smem(reinterpret_cast<const void*>(kern), (int)kSmemLimit)) return rc;
-    // work split (Work): whole rounds of one item per CTA, then the remainder -- split along the filters into twice as many
-    // half-width items when that keeps no more CTAs busy than there are SMs.  QNN_TC_NOSPLIT=1: whole items (A/B timing)
-    static const bool no_split = [] { const char* e = getenv("QNN_TC_NOSPLIT"); return e && atoi(e) != 0; }();
-    const int sms = num_sms();
-    int grid;
-    if (p.n_items >= sms) {
-        grid = sms;
-        p.full_rounds = p.n_items / sms;
-        p.rem = p.n_items % sms;
-        p.split = (!no_split && p.f_tile == 64 && p.rem > 0 && 2 * p.rem <= sms) ? 1 : 0;
-    } else {
-        p.full_rounds = 0;
-        p.rem = p.n_items;
-        p.split = (!no_split && p.f_tile == 64 && 2 * p.rem <= sms) ? 1 : 0;
-        grid = p.split ? 2 * p.rem : p.rem;
-    }
+    const WorkSplit ws = plan_work_split(p.n_items, p.f_tile, num_sms());  // (qnn_common.h)
+    const int grid = ws.grid;
+    p.full_rounds = ws.full_rounds;
+    p.rem = ws.rem;
+    p.split = ws.split;
     p.trace = (g_trace2d && g_trace2d_bytes >= (size_t)grid * kTraceSlots * 8) ? g_trace2d : nullptr;
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid);

@@ -392,3 +392,55 @@ def test_packed_image_queries_agree_with_kernel_selection(native_lib):
             assert len(kerns) == 1, (in_q, q_units, math, kerns)
             nbytes = native_lib.qnn_dense_packed_bytes(1000, in_q, q_units, m, 0, _native.PACK_FORWARD)
             assert (nbytes > 0) == (kerns.pop() in tc), (in_q, q_units, math)
+
+
+def test_work_split_covers_every_item_exactly_once(native_lib):
+    """Host logic of the persistent tensor-core forward kernels (qnn_conv_work_split, no GPU needed): the (grid, whole
+    rounds, last-round items, split) plan together with the device-side mapping -- WorkItem in qnn_hamilton_tc.cu, Work in
+    qnn_hamilton_tc2d.cu, restated below -- must compute every (item, filter half) exactly once, split only 64-wide
+    filter tiles, and never use more CTAs than SMs."""
+    from complexnn import _native
+    n_sm = 148  # what the library assumes when no device is present
+    out = (ctypes.c_int32 * 4)()
+
+    def items_of(grid, full, rem, split):
+        """(item, first filter, filters) of every CTA, as the kernels enumerate them"""
+        got = []
+        for cta in range(grid):
+            n = full + (1 if cta < (2 * rem if split else rem) else 0)
+            for k in range(n):
+                if k < full or not split:
+                    got.append((cta + k * grid, 0, 64 if split else None))
+                else:
+                    got.append((full * grid + (cta >> 1), (cta & 1) * 32, 32))
+        return got
+
+    cases = []
+    # cfg 2: 512 tiles = 3 rounds + 68 -> 136 half items; cfg 2 with a full last round; small problems; dense
+    for batch, T, in_q, F, k in ((256, 256, 40, 64, 3), (296, 128, 40, 64, 3), (10, 128, 40, 64, 3), (75, 128, 40, 64, 3),
+                                 (256, 256, 8, 32, 3), (3, 1000, 16, 64, 5), (256, 256, 64, 64, 3), (300, 256, 64, 128, 3)):
+        cases.append(_native.make_conv_desc(1, batch, (T,), in_q, F, (k,), (1,), (1,), "same", "channels_last", "relu"))
+    cases.append(_native.make_conv_desc(2, 4, (30, 200), 64, 128, (3, 3), (1, 1), (1, 1), "same", "channels_first", "relu"))
+    cases.append(_native.make_conv_desc(2, 1, (5, 131), 16, 64, (3, 5), (1, 1), (1, 1), "same", "channels_last", "relu"))
+    seen_split = seen_whole = False
+    for d in cases:
+        kern = native_lib.qnn_conv_work_split(ctypes.byref(d), out)
+        assert kern in (_native.KERNEL_TC_ROWS, _native.KERNEL_TC_CF), kern
+        grid, full, rem, split = (int(v) for v in out)
+        assert 1 <= grid <= n_sm and rem >= 0 and full >= 0
+        total = full * grid + rem if full else rem
+        assert (not full) or grid == n_sm
+        if split:
+            assert 0 < 2 * rem <= n_sm
+        got = items_of(grid, full, rem, split)
+        whole = sorted(i for i, f0, fe in got if fe != 32)
+        halves = sorted((i, f0) for i, f0, fe in got if fe == 32)
+        first_split = full * grid if split else total
+        assert whole == list(range(first_split)), "whole items"
+        assert halves == [(i, f0) for i in range(first_split, total) for f0 in (0, 32)], "half items"
+        seen_split |= bool(split)
+        seen_whole |= not split
+    assert seen_split and seen_whole
+    # a CUDA-core problem has no persistent grid
+    d = _native.make_conv_desc(1, 4, (100,), 8, 24, (3,), (2,), (1,), "same", "channels_last", "relu")
+    assert native_lib.qnn_conv_work_split(ctypes.byref(d), out) == _native.KERNEL_GENERAL and list(out) == [0, 0, 0, 0]
