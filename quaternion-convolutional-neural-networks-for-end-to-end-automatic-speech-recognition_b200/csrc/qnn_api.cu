@@ -199,14 +199,16 @@ int forward_kernel(const Geom& g, int rank, int math, int algo) {
     // tiles or the layer is one tile; when it only fits with 32-filter tiles the kernel makes twice the passes over x with
     // N = 32 MMAs that cost as much as N = 64 ones (measured: cfg 3 conv layers 60 us vs ~35 us) -- the streamed-sub-filter
     // kernel then takes the problem if it qualifies (in_q % 8 == 0, F % 32 == 0).
-    // Ragged channel counts (in_q % 4 != 0) whose image leaves room for two x stages only (the TIMIT first layer of the
-    // cfg 3 stack, in_q = 41, F = 64, k = 3: 147 KB of image): every converter group then has ONE x buffer and waits out a
-    // whole load per stage (23 k cycles per tile against 11 k of MMAs) -- the streamed-sub-filter kernel, which reads such
-    // rows in place too (twelve-channel boxes), takes them.  QNN_RAGGED_STREAM=0 keeps them on the resident kernel.
-    static const bool ragged_stream = [] { const char* e = getenv("QNN_RAGGED_STREAM"); return !(e && atoi(e) == 0); }();
+    // A resident image that leaves room for fewer than four x stages starves the converters: with two stages every
+    // converter group has ONE x buffer and waits out a whole load per stage (the TIMIT first layer of the cfg 3 stack,
+    // in_q = 41, F = 64, k = 3, 147 KB of image: 23 k cycles per tile against 11 k of MMAs).  The streamed-sub-filter kernel
+    // (six x stages, ragged rows read in place) takes such layers when it needs no pre-pass -- measured on one box
+    // (profiles/r02_ab_starved_layers.txt): in_q = 41: stack -9.5 %; in_q = 44 / 48 / 96 (F = 32): -22 / -10 / -15 %.
+    // QNN_STARVED_STREAM=0 keeps them on the resident kernel (A/B timing).
+    static const bool starved_stream = [] { const char* e = getenv("QNN_STARVED_STREAM"); return !(e && atoi(e) == 0); }();
     const TcPlan tcp = tc_plan(g, rank, x3);
     const Tc2dPlan t2p = tc2d_plan(g, rank, x3);
-    const bool ragged_starved = tcp.ok && tcp.ragged && tcp.x_stages < 4 && ragged_stream && t2p.ok && t2p.rag;
+    const bool ragged_starved = starved_stream && tcp.ok && tcp.x_stages < 4 && t2p.ok && !t2p.pad_q && !t2p.pad_rows;
     const bool resident_good = tcp.ok && (tcp.n_ftiles == 1 || tcp.f_tile >= 64) && !ragged_starved;
     if (resident_good) return kKernTc;
     if (t2p.ok) return kKernTc2d;
