@@ -209,7 +209,13 @@ int forward_kernel(const Geom& g, int rank, int math, int algo) {
     const TcPlan tcp = tc_plan(g, rank, x3);
     const Tc2dPlan t2p = tc2d_plan(g, rank, x3);
     const bool ragged_starved = starved_stream && tcp.ok && tcp.x_stages < 4 && t2p.ok && !t2p.pad_q && !t2p.pad_rows;
-    const bool resident_good = tcp.ok && (tcp.n_ftiles == 1 || tcp.f_tile >= 64) && !ragged_starved;
+    // (QNN_FORCE_STREAM=1, experiments: the streamed kernel whenever it takes the problem)
+    static const bool force_stream = [] { const char* e = getenv("QNN_FORCE_STREAM"); return e && atoi(e) != 0; }();
+    // More than one filter-tile pass (F > 64): the resident kernel re-reads x and reloads an image per pass; the streamed
+    // kernel is 1.5-3 % faster at two passes and 10 % at four (profiles/r02_ab_starved_layers.txt, second block)
+    const bool multi_pass = tcp.ok && tcp.n_ftiles > 1 && t2p.ok && !t2p.pad_q && !t2p.pad_rows && starved_stream;
+    const bool resident_good = tcp.ok && (tcp.n_ftiles == 1 || tcp.f_tile >= 64) && !ragged_starved && !multi_pass &&
+                               !(force_stream && t2p.ok && !t2p.pad_q);
     if (resident_good) return kKernTc;
     if (t2p.ok) return kKernTc2d;
     if (tcp.ok) return kKernTc;
