@@ -57,6 +57,18 @@ for it in range(N):
         if not err <= tol:
             bad.append({"shape": [rank, layout, B, list(sp), in_q, F, list(k), list(d), pad, act], "math": math, "kernel": kid,
                         "err": err})
+    # gradients (relu / linear layers): the kernels the library picks vs the CUDA-core kernels, all on the fp32 forward's y
+    if act in ("relu", "linear"):
+        dy = torch.from_numpy(rng.normal(size=tuple(ref.shape)).astype(np.float32)).cuda()
+        g_ref = _ops.conv_backward(x, ref, dy, kern, bias is not None, F, k, ones, pad, layout, d, act, math="fp32", algo="general")
+        g_tc = _ops.conv_backward(x, ref, dy, kern, bias is not None, F, k, ones, pad, layout, d, act, math="tf32", algo="auto")
+        for name, a, b in zip(("dx", "dkernel", "dbias"), g_tc, g_ref):
+            if a is None:
+                continue
+            err = float((a - b).abs().max()) / (float(b.abs().max()) + 1e-30)
+            worst["grad_" + name] = max(worst.get("grad_" + name, 0.0), err)
+            if not err <= 4e-3:
+                bad.append({"shape": [rank, layout, B, list(sp), in_q, F, list(k), list(d), pad, act], "grad": name, "err": err})
 torch.cuda.synchronize()
 print(json.dumps({"shapes": N, "kernel_histogram (0 general, 1 resident, 2 streamed, 3 small-K)": hist, "worst_max_rel": worst,
                   "violations": bad}))
